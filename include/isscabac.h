@@ -1,0 +1,234 @@
+/* isscabac.h -- C ABI of the B200-native many-stream CABAC engine.
+ *
+ * One shared library (isscabac_b200/libisscabac.so), plain C types only.  It is
+ * the drop-in boundary for the reference's CABAC path:
+ *
+ *   reference interface (paths relative to the reference repo)      replaced by
+ *   --------------------------------------------------------------  ------------------------
+ *   CABAC_ArithmeticEncoder::start/encodeBin/encodeBinEP/            cabac_encode_ops*        (batch)
+ *     encodeBinsEP/encodeBinTrm/finish                               simplecabac_* handle API (1 stream)
+ *     (CABAC/CABAC_ArithmeticEncoder.h:52-72, .cpp:54-412)
+ *   CABAC_ArithmeticDecoder::start/decodeBin/decodeBinEP/            cabac_decode_ops*        (batch)
+ *     decodeBinsEP/decodeBinTrm/finish                               simplecabac_* handle API
+ *     (CABAC/CABAC_ArithmeticDecoder.h:46-61, .cpp:54-472)
+ *   CABAC_BitstreamFile (byte sink/source, .h:56-73)                 slab / payload + offset table
+ *   CABAC_ContextModels::initContextModelsByMpsState/ByP0Prob        cabac_ctx_from_prob / _from_state
+ *     (CABAC/CABAC_ContextModelsInit.cpp:51-148)
+ *   mexFunction command protocol (CABAC/SimpleCABACMex.cpp:100-472)  simplecabac_dispatch
+ *   cabacBinarizer.m / cabacDebinarizer.m /                          cabac_binarize_symbols,
+ *     cabacDecodeSymbolFinished.m / cabacContextSelection.m /        cabac_encode_symbols,
+ *     cabacEncode.m:45-70 / cabacDecode.m:29-55 / cabacDemo.m:101-186  cabac_decode_symbols
+ *
+ * Conventions
+ *   - every function returns 0 (ISSCABAC_OK) or a negative ISSCABAC_ERR_* code; no
+ *     exceptions cross the ABI; isscabac_last_error() gives a thread-local detail string.
+ *   - "d_" pointers are DEVICE pointers on the current CUDA device, "h_" pointers are host
+ *     pointers.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *     Device entry points are stream-ordered and do not synchronise unless stated.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ *     with ISSCABAC_ERR_CUDA.
+ *
+ * Op format (one op per bin; engine-level API of the reference, one call = one op)
+ *   op = (code << 1) | bin
+ *   u8  ops (op_width 1): code 0..124 = context index, 125 = terminate bin, 126 = bypass bin
+ *   u16 ops (op_width 2): code 0..998 = context index, 0x7FFD terminate, 0x7FFE bypass
+ * Context state byte: (state << 1) | mps, state 0..63 (CABAC/ContextModel.h:78-80).
+ */
+#ifndef ISSCABAC_H
+#define ISSCABAC_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define ISSCABAC_VERSION 100
+
+#define ISSCABAC_OK 0
+#define ISSCABAC_ERR_INVALID (-1)     /* bad argument */
+#define ISSCABAC_ERR_CUDA (-2)        /* CUDA runtime error / no device */
+#define ISSCABAC_ERR_OVERFLOW (-3)    /* an output buffer was too small */
+#define ISSCABAC_ERR_NOMEM (-4)
+#define ISSCABAC_ERR_UNSUPPORTED (-5)
+#define ISSCABAC_ERR_STATE (-6)       /* handle used out of order (e.g. encodeBin before encodeStart) */
+#define ISSCABAC_ERR_IO (-7)          /* bitstream file could not be opened */
+#define ISSCABAC_ERR_CORRUPT (-8)     /* decodeFinish: terminate bin / stop bit check failed */
+
+#define ISSCABAC_OP8_TRM 125u
+#define ISSCABAC_OP8_EP 126u
+#define ISSCABAC_OP16_TRM 0x7FFDu
+#define ISSCABAC_OP16_EP 0x7FFEu
+#define ISSCABAC_MAX_CTX 999u         /* RWTH_MAX_NUM_CONTEXTS-1, CABAC/CommonDef.h:56 */
+
+/* binarization methods (CABAC/cabacBinarizer.m:12-27) */
+enum { ISSCABAC_BIN_TU = 0, ISSCABAC_BIN_EG0 = 1, ISSCABAC_BIN_EG1 = 2, ISSCABAC_BIN_EG2 = 3,
+       ISSCABAC_BIN_FL32 = 4 };
+/* context-selection profiles */
+enum { ISSCABAC_PROFILE_DEMO = 0,       /* CABAC/cabacDemo.m:113-121 (3 contexts)                 */
+       ISSCABAC_PROFILE_ISS = 1,        /* ISS/+coder/cabacContextSelection.m:24-67 (7*Nlbp+2)    */
+       ISSCABAC_PROFILE_FLAT = 2,       /* neighbour-free restriction of ISS (2*Nlbp+2 contexts)  */
+       ISSCABAC_PROFILE_FLAT_EPSUF = 3  /* FLAT prefix contexts, suffix bins bypass (Nlbp+1)      */ };
+/* ISS cmTypes mask (ISS/ISS.m:51) */
+enum { ISSCABAC_CM_COND0 = 1, ISSCABAC_CM_COND1 = 2, ISSCABAC_CM_CONDBINLFT = 4,
+       ISSCABAC_CM_CONDS0 = 8, ISSCABAC_CM_CONDS1 = 16 };
+
+typedef struct {
+  int32_t profile;   /* ISSCABAC_PROFILE_* */
+  int32_t method;    /* ISSCABAC_BIN_* */
+  uint32_t Nq;       /* number of quantisation levels (symbols are 0..Nq-1) */
+  int32_t Nlbp;      /* last bin position modelled with its own context (ISS.m:52) */
+  uint32_t types;    /* ISSCABAC_CM_* mask (ISS profile) */
+  uint32_t rows;     /* ISS profile: matrix rows of the column-major stream; 0 = one column */
+} isscabac_symcfg;
+
+/* ---- library ------------------------------------------------------------- */
+int isscabac_version(void);
+const char* isscabac_strerror(int code);
+const char* isscabac_last_error(void);
+/* sm_count / cc = properties of the current device */
+int isscabac_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* ---- context initialisation (host, double arithmetic like the reference) -- */
+/* CABAC_ContextModelsInit.cpp:124-148 (xMapProbabilityToState) over n probabilities p(0) */
+int cabac_ctx_from_prob(const double* p0, uint32_t n, uint8_t* ctx_out);
+/* CABAC_ContextModelsInit.cpp:51-80: n triples [ctxIdx mps state]; ctxIdx is ignored */
+int cabac_ctx_from_state(const double* triples, uint32_t n, uint8_t* ctx_out);
+/* number of contexts a profile uses */
+int cabac_profile_num_ctx(int profile, int Nlbp);
+
+/* ---- batch encode / decode over op arrays (device pointers) --------------- */
+/* Stream s codes ops[op_off[s] .. op_off[s+1]) as start(); ops...; finish().
+ * d_ctx_init: n_ctx state bytes shared by all streams, or n_streams*n_ctx when
+ * per_stream_init != 0.  Stream s is written to d_slab + s*slab_stride
+ * (slab_stride % 16 == 0, d_slab 16-byte aligned); d_lengths[s] = its byte length.
+ * A stream longer than slab_stride sets bit 0 of *d_overflow (optional) and its
+ * length is still reported, so the caller can retry with a larger stride.
+ * cabac_slab_stride_bound() gives a stride that can never overflow. */
+int cabac_encode_ops(uint32_t n_streams, const uint64_t* d_op_off, const void* d_ops, int op_width,
+                     const uint8_t* d_ctx_init, uint32_t n_ctx, int per_stream_init,
+                     uint8_t* d_slab, uint64_t slab_stride, uint32_t* d_lengths,
+                     uint32_t* d_overflow, void* stream);
+uint64_t cabac_slab_stride_bound(uint64_t max_ops_per_stream);
+
+/* Stream s is d_bytes[byte_off[s] .. byte_off[s+1]); the op array gives the kind of
+ * every bin (bit 0 ignored); d_bins[i] = decoded bin of op i.  d_finish_ok[s]
+ * (optional) = 1 when Decoder::finish()'s two checks hold (Decoder.cpp:75-81). */
+int cabac_decode_ops(uint32_t n_streams, const uint64_t* d_byte_off, const uint8_t* d_bytes,
+                     const uint64_t* d_op_off, const void* d_ops, int op_width,
+                     const uint8_t* d_ctx_init, uint32_t n_ctx, int per_stream_init,
+                     uint8_t* d_bins, uint8_t* d_finish_ok, void* stream);
+
+/* ---- length scan + compaction --------------------------------------------- */
+/* d_byte_off[0..n] = exclusive scan of d_lengths (u64); streams copied back to back
+ * into d_payload (capacity payload_cap bytes; overflow -> bit 1 of *d_overflow).
+ * d_scratch: cabac_compact_scratch_bytes(n_streams) bytes. */
+size_t cabac_compact_scratch_bytes(uint32_t n_streams);
+int cabac_compact(uint32_t n_streams, const uint8_t* d_slab, uint64_t slab_stride,
+                  const uint32_t* d_lengths, uint8_t* d_payload, uint64_t payload_cap,
+                  uint64_t* d_byte_off, void* d_scratch, uint32_t* d_overflow, void* stream);
+
+/* ---- symbol level: binarizer + context selection on device ---------------- */
+/* symbols -> ops (u8 op format).  Two calls: with d_ops == NULL only d_op_off[0..n_streams]
+ * (u64, exclusive scan of bins per stream) is produced; then call again with a d_ops buffer of
+ * at least op_off[n_streams] bytes.  sym_width 1, 2 or 4 bytes per symbol.
+ * d_scratch: cabac_binarize_scratch_bytes(n_symbols) bytes. */
+size_t cabac_binarize_scratch_bytes(uint64_t n_symbols, uint32_t n_streams);
+int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_sym_off,
+                           const void* d_symbols, int sym_width, uint64_t n_symbols,
+                           uint64_t* d_op_off, uint8_t* d_ops, uint64_t ops_cap,
+                           void* d_scratch, void* stream);
+/* fused symbols -> bytes (binarize + select + encode in one kernel, no op array in HBM);
+ * d_bits_after_symbol (optional, u32 per symbol) = getNumBits() after the symbol
+ * (CABAC_BitstreamFile.h:70 semantics; feeds the heat map H of cabacEncode.m:49,67). */
+int cabac_encode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_sym_off,
+                         const void* d_symbols, int sym_width,
+                         const uint8_t* d_ctx_init, uint32_t n_ctx, int per_stream_init,
+                         uint8_t* d_slab, uint64_t slab_stride, uint32_t* d_lengths,
+                         uint32_t* d_bits_after_symbol, uint32_t* d_overflow, void* stream);
+/* bytes -> symbols: decode loop with on-device finish detector, context selection and
+ * debinarizer (cabacDecode.m:29-55,62-66). */
+int cabac_decode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_byte_off,
+                         const uint8_t* d_bytes, const uint64_t* d_sym_off,
+                         const uint8_t* d_ctx_init, uint32_t n_ctx, int per_stream_init,
+                         void* d_symbols, int sym_width, uint8_t* d_finish_ok, void* stream);
+
+/* ---- host-buffer API (what a reference-side caller binds) ------------------ */
+/* Same semantics with HOST pointers; all host<->device copies happen inside the call.
+ * Encode returns the compacted payload and the offset table: h_payload (capacity
+ * payload_cap), h_byte_off[n_streams+1].  Pinned host memory makes the copies
+ * asynchronous/pipelined but is not required.  These calls synchronise. */
+int cabac_encode_ops_host(uint32_t n_streams, const uint64_t* h_op_off, const void* h_ops, int op_width,
+                          const uint8_t* h_ctx_init, uint32_t n_ctx, int per_stream_init,
+                          uint8_t* h_payload, uint64_t payload_cap, uint64_t* h_byte_off);
+int cabac_decode_ops_host(uint32_t n_streams, const uint64_t* h_byte_off, const uint8_t* h_bytes,
+                          const uint64_t* h_op_off, const void* h_ops, int op_width,
+                          const uint8_t* h_ctx_init, uint32_t n_ctx, int per_stream_init,
+                          uint8_t* h_bins, uint8_t* h_finish_ok);
+int cabac_encode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* h_sym_off,
+                              const void* h_symbols, int sym_width,
+                              const uint8_t* h_ctx_init, uint32_t n_ctx, int per_stream_init,
+                              uint8_t* h_payload, uint64_t payload_cap, uint64_t* h_byte_off,
+                              uint32_t* h_bits_after_symbol);
+int cabac_decode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* h_byte_off,
+                              const uint8_t* h_bytes, const uint64_t* h_sym_off,
+                              const uint8_t* h_ctx_init, uint32_t n_ctx, int per_stream_init,
+                              void* h_symbols, int sym_width, uint8_t* h_finish_ok);
+/* pinned host allocations for the callers above */
+int cabac_host_alloc(void** p, size_t bytes);
+int cabac_host_free(void* p);
+
+/* ---- single-stream engine handle (backs the SimpleCABAC C++ facade) -------- */
+/* One handle = the reference's `class CABAC` aggregate (SimpleCABACMex.cpp:69-80): a
+ * bitstream name or memory buffer, an encoder context set and a decoder context set.
+ * The coder state lives on the GPU; encode ops are queued on the host and executed by
+ * the encode kernel at finish() / getNumBits(); decode calls run the decode kernel. */
+typedef struct simplecabac simplecabac;
+int simplecabac_create(simplecabac** h, const char* filename /* may be NULL: memory sink */);
+int simplecabac_destroy(simplecabac* h);
+int simplecabac_init_by_prob(simplecabac* h, const double* p0, uint32_t n);          /* initByProb  */
+int simplecabac_init_by_state(simplecabac* h, const double* triples, uint32_t n);    /* initByState */
+int simplecabac_encode_start(simplecabac* h);
+int simplecabac_encode_bin(simplecabac* h, unsigned bin, unsigned ctx_idx);
+int simplecabac_encode_bin_ep(simplecabac* h, unsigned bin);
+int simplecabac_encode_bins_ep(simplecabac* h, unsigned bins, int n);
+int simplecabac_encode_bin_trm(simplecabac* h, unsigned bin);
+int simplecabac_get_num_bits(simplecabac* h, uint64_t* bits);
+int simplecabac_get_bins_coded(simplecabac* h, uint64_t* bins);
+int simplecabac_encode_finish(simplecabac* h);
+/* memory sink access after encode_finish (valid until the next encode_start/destroy) */
+int simplecabac_get_bytes(simplecabac* h, const uint8_t** bytes, uint64_t* n);
+/* memory source for decoding (instead of the file) */
+int simplecabac_set_bytes(simplecabac* h, const uint8_t* bytes, uint64_t n);
+int simplecabac_decode_start(simplecabac* h);
+int simplecabac_decode_bin(simplecabac* h, unsigned ctx_idx, unsigned* bin);
+int simplecabac_decode_bin_ep(simplecabac* h, unsigned* bin);
+int simplecabac_decode_bins_ep(simplecabac* h, int n, unsigned* bins);
+int simplecabac_decode_bin_trm(simplecabac* h, unsigned* bin);
+/* batched form of the three calls above: kinds as u16 ops (bit 0 ignored) */
+int simplecabac_decode_ops(simplecabac* h, const uint16_t* ops, uint32_t n, uint8_t* bins);
+int simplecabac_decode_finish(simplecabac* h);   /* ISSCABAC_ERR_CORRUPT if the checks fail */
+int simplecabac_get_ctx_state(simplecabac* h, int decoder_set, unsigned ctx_idx, unsigned* state, unsigned* mps);
+
+/* ---- MEX command protocol (CABAC/SimpleCABACMex.cpp:100-472) ---------------- */
+/* One call = one mexFunction invocation.  args[0] is the command string; numeric
+ * arguments are MATLAB doubles (column-major m x n).  Returns 0, or 1 when the
+ * reference would have raised mexErrMsgTxt -- the same message text is written to err. */
+typedef struct {
+  int32_t is_char;
+  const char* s;      /* is_char != 0 */
+  const double* d;    /* is_char == 0 */
+  int32_t m, n;
+} isscabac_mxarg;
+int simplecabac_dispatch(int nlhs, double* out, int out_cap, int* out_n,
+                         int nrhs, const isscabac_mxarg* args, char* err, int errcap);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,622 @@
+// kernels.cu -- sm_100a kernels of the many-stream CABAC engine + the device-pointer C ABI.
+//
+// Work decomposition: one LANE (thread) per CABAC stream -- a stream is a serial
+// recurrence on (low, range) resp. (value, range), so the data parallelism is across
+// streams.  Per CTA of 128 lanes, shared memory holds
+//   * the fused state table (cabac_lane.cuh: LPS sub-ranges + both next states, 8 B per
+//     state byte), REPLICATED PER LANE: row st of lane l lives at tab[st*32 + l], so the
+//     32 lanes of a warp always hit 32 distinct banks (LDS.64, conflict-free by
+//     construction whatever the 32 states are);
+//   * the context states, one 32-bit word per (context, lane): ctx[c*128 + tid] -- bank =
+//     lane, again conflict-free for arbitrary per-lane context indices.
+// The arithmetic-coder registers (low/range/bitsLeft, output accumulator) stay in
+// registers; output bytes are packed four at a time and stored as 32-bit words to the
+// lane's slab (the L2 merges the partial sectors); a later scan+compaction pass builds the
+// contiguous bitstream.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/isscabac.h"
+#include "cabac_lane.cuh"
+#include "internal.h"
+
+using namespace cabac;
+
+namespace {
+
+constexpr int NT = 128;            // lanes (streams) per CTA
+constexpr int TAB_WORDS = 128 * 32;  // uint2 entries of the lane-replicated table
+
+struct RowTable {
+  uint2 r[128];
+  constexpr RowTable() : r{} {
+    for (uint32_t i = 0; i < 128; ++i) r[i] = fused_row(i);
+  }
+};
+__constant__ RowTable c_rows = RowTable();
+
+__device__ __forceinline__ void fill_table(uint2* tab) {
+  for (int i = threadIdx.x; i < TAB_WORDS; i += blockDim.x) tab[i] = c_rows.r[i >> 5];
+}
+
+template <int W>
+struct OpTraits;
+template <>
+struct OpTraits<1> {
+  typedef uint8_t T;
+  static constexpr uint32_t EP = ISSCABAC_OP8_EP, TRM = ISSCABAC_OP8_TRM;
+};
+template <>
+struct OpTraits<2> {
+  typedef uint16_t T;
+  static constexpr uint32_t EP = ISSCABAC_OP16_EP, TRM = ISSCABAC_OP16_TRM;
+};
+
+// Context storage policies ----------------------------------------------------
+// smem: word per (context, lane).  gmem: byte per (context, stream) in a scratch
+// array laid out [ctx][stream] so that a warp's accesses to one context coalesce
+// (used when n_ctx is too large for shared memory, up to the API limit of 999).
+struct CtxSmem {
+  uint32_t* p;  // this lane's column
+  __device__ __forceinline__ uint32_t load(uint32_t c) const { return p[c * NT]; }
+  __device__ __forceinline__ void store(uint32_t c, uint32_t v) const { p[c * NT] = v; }
+};
+struct CtxGmem {
+  uint8_t* p;  // this stream's column
+  uint64_t stride;
+  __device__ __forceinline__ uint32_t load(uint32_t c) const { return p[c * stride]; }
+  __device__ __forceinline__ void store(uint32_t c, uint32_t v) const { p[c * stride] = (uint8_t)v; }
+};
+
+struct CodecParams {
+  uint32_t n_streams, n_ctx;
+  int per_stream_init;
+  const uint64_t* op_off;
+  const void* ops;
+  const uint8_t* ctx_init;
+  uint8_t* ctx_scratch;  // CtxGmem only
+  // encode
+  uint8_t* slab;
+  uint64_t slab_stride;
+  uint32_t* lengths;
+  uint32_t* overflow;
+  // decode
+  const uint64_t* byte_off;
+  const uint8_t* bytes;
+  uint8_t* bins;
+  uint8_t* finish_ok;
+};
+
+template <class Ctx>
+__device__ __forceinline__ Ctx make_ctx(const CodecParams& P, uint8_t* smem_after_tab, uint32_t s, bool valid);
+
+template <>
+__device__ __forceinline__ CtxSmem make_ctx<CtxSmem>(const CodecParams& P, uint8_t* smem_after_tab, uint32_t s, bool valid) {
+  uint32_t* base = reinterpret_cast<uint32_t*>(smem_after_tab);
+  const uint8_t* init = P.ctx_init + (P.per_stream_init && valid ? (uint64_t)s * P.n_ctx : 0);
+  for (uint32_t c = 0; c < P.n_ctx; ++c) base[c * NT + threadIdx.x] = init[c];
+  return CtxSmem{base + threadIdx.x};
+}
+template <>
+__device__ __forceinline__ CtxGmem make_ctx<CtxGmem>(const CodecParams& P, uint8_t*, uint32_t s, bool valid) {
+  CtxGmem g{P.ctx_scratch + s, P.n_streams};
+  if (valid) {
+    const uint8_t* init = P.ctx_init + (P.per_stream_init ? (uint64_t)s * P.n_ctx : 0);
+    for (uint32_t c = 0; c < P.n_ctx; ++c) g.store(c, init[c]);
+  }
+  return g;
+}
+
+// ---------------------------------------------------------------------------
+// encode: one op
+// ---------------------------------------------------------------------------
+// Context-coded and bypass bins share one straight-line sequence (the 32 lanes of a warp
+// hold unrelated streams, so a branch on the op kind would execute both sides anyway):
+// the context path is computed unconditionally on a clamped context index, the bypass
+// result is blended in with selects, and a single write-out test follows.  Only the
+// terminate bin -- at most a handful per stream -- is a real branch.
+template <int W, class Ctx>
+__device__ __forceinline__ void encode_one(EncLane& L, uint32_t o, const Ctx& ctx, const uint2* mytab, uint32_t ctx_max) {
+  typedef OpTraits<W> OT;
+  const uint32_t code = o >> 1, bin = o & 1u;
+  if (code == OT::TRM) {
+    enc_bin_trm<false>(L, bin);
+    return;
+  }
+  const bool is_ep = code > OT::TRM;
+  const uint32_t c = min(code, ctx_max);  // a context >= n_ctx aliases onto the last one (never out of bounds)
+  uint32_t st = ctx.load(c);
+  const uint2 row = mytab[st * 32];
+  // encodeBin (Encoder.cpp:113-178), see enc_bin_ctx in cabac_lane.cuh
+  const uint32_t lps = cb_perm(0, row.x, L.range >> 6);
+  const uint32_t rmps = L.range - lps;
+  const uint32_t is_lps = (st ^ o) & 1u;
+  const uint32_t rsel = is_lps ? lps : rmps;
+  int n = cb_clz(rsel) - 23;
+  n = n > 6 ? 6 : n;
+  const uint32_t low_c = (L.low + (is_lps ? rmps : 0u)) << n;
+  const uint32_t range_c = rsel << n;
+  st = cb_perm(row.y, 0, is_lps | 0x4440u);
+  // encodeBinEP (Encoder.cpp:250-270)
+  const uint32_t low_e = (L.low << 1) + (bin ? L.range : 0u);
+  L.low = is_ep ? low_e : low_c;
+  L.range = is_ep ? L.range : range_c;
+  L.bits_left -= is_ep ? 1 : n;
+  if (!is_ep) ctx.store(c, st);
+  if (L.bits_left < 12) enc_write_out<false>(L);
+}
+
+template <int W, class Ctx>
+__global__ void __launch_bounds__(NT) k_encode_ops(CodecParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint2* tab = reinterpret_cast<uint2*>(smem);
+  fill_table(tab);
+  const uint32_t s = blockIdx.x * NT + threadIdx.x;
+  const bool valid = s < P.n_streams;
+  Ctx ctx = make_ctx<Ctx>(P, smem + TAB_WORDS * sizeof(uint2), valid ? s : 0, valid);
+  __syncthreads();
+  if (!valid) return;
+  const uint2* mytab = tab + (threadIdx.x & 31);
+  const uint32_t ctx_max = P.n_ctx ? P.n_ctx - 1 : 0;
+
+  typedef typename OpTraits<W>::T OpT;
+  const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
+  const OpT* p = reinterpret_cast<const OpT*>(P.ops) + o0;
+  uint64_t n = o1 - o0;
+
+  EncLane L;
+  uint32_t cap = (uint32_t)(P.slab_stride > 0xfffffffcull ? 0xfffffffcull : P.slab_stride);
+  enc_start(L, P.slab + (uint64_t)s * P.slab_stride, cap);
+
+  uint64_t i = 0;
+  // head: up to the first 16-byte boundary
+  while (i < n && (reinterpret_cast<uintptr_t>(p + i) & 15u)) {
+    encode_one<W, Ctx>(L, p[i], ctx, mytab, ctx_max);
+    ++i;
+  }
+  // body: 16 bytes of ops per load, next block prefetched while this one is coded
+  constexpr int PER = 16 / W;
+  if (i + PER <= n) {
+    uint4 cur = __ldg(reinterpret_cast<const uint4*>(p + i));
+    for (;;) {
+      const bool more = i + 2 * PER <= n;
+      uint4 nxt = cur;
+      if (more) nxt = __ldg(reinterpret_cast<const uint4*>(p + i + PER));
+      const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int b = 0; b < 4 / W; ++b) {
+          uint32_t o = (W == 1) ? ((w[k] >> (8 * b)) & 0xffu) : ((w[k] >> (16 * b)) & 0xffffu);
+          encode_one<W, Ctx>(L, o, ctx, mytab, ctx_max);
+        }
+      }
+      i += PER;
+      if (!more) break;
+      cur = nxt;
+    }
+  }
+  // tail
+  for (; i < n; ++i) encode_one<W, Ctx>(L, p[i], ctx, mytab, ctx_max);
+
+  enc_finish<false>(L);
+  enc_flush_pending(L);
+  P.lengths[s] = L.nbytes;
+  if ((L.overflow || L.nbytes > cap) && P.overflow) atomicOr(P.overflow, 1u);
+}
+
+// ---------------------------------------------------------------------------
+// decode
+// ---------------------------------------------------------------------------
+template <int W, class Ctx>
+__device__ __forceinline__ uint32_t decode_one(DecLane& D, uint32_t o, const Ctx& ctx, const uint2* mytab, uint32_t ctx_max) {
+  typedef OpTraits<W> OT;
+  const uint32_t code = o >> 1;
+  if (code == OT::TRM) return dec_bin_trm(D);
+  const bool is_ep = code > OT::TRM;
+  const uint32_t c = min(code, ctx_max);
+  uint32_t st = ctx.load(c);
+  const uint2 row = mytab[st * 32];
+  // decodeBinEP shifts (and possibly reads) BEFORE its compare (Decoder.cpp:288-331),
+  // decodeBin compares first and renormalises after (Decoder.cpp:87-190).  One byte is
+  // consumed per op at most, so both orders share a single read: the bypass pre-shift
+  // reserves the byte position, the byte itself is added when it is fetched below --
+  // adding it before or after the compare/subtract is the same because the compare is
+  // made against a value whose low bits (the not-yet-read byte) are below one unit only
+  // for the context path; for the bypass path the byte is needed first, so it is fetched
+  // up front there.
+  uint32_t value = D.value;
+  int bn = D.bits_needed;
+  uint32_t bin;
+  if (is_ep) {
+    value <<= 1;
+    if (++bn >= 0) { bn = -8; value += dec_read(D); }
+    const uint32_t scaled = D.range << 7;
+    bin = value >= scaled ? 1u : 0u;
+    value -= bin ? scaled : 0u;
+  } else {
+    const uint32_t lps = cb_perm(0, row.x, D.range >> 6);
+    const uint32_t rmps = D.range - lps;
+    const uint32_t scaled = rmps << 7;
+    const uint32_t is_lps = value >= scaled ? 1u : 0u;
+    const uint32_t rsel = is_lps ? lps : rmps;
+    int n = cb_clz(rsel) - 23;
+    n = n > 6 ? 6 : n;
+    value = (value - (is_lps ? scaled : 0u)) << n;
+    D.range = rsel << n;
+    bin = (st ^ is_lps) & 1u;
+    st = cb_perm(row.y, 0, is_lps | 0x4440u);
+    ctx.store(c, st);
+    bn += n;
+    if (bn >= 0) { value += dec_read(D) << bn; bn -= 8; }
+  }
+  D.value = value;
+  D.bits_needed = bn;
+  return bin;
+}
+
+template <int W, class Ctx>
+__global__ void __launch_bounds__(NT) k_decode_ops(CodecParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint2* tab = reinterpret_cast<uint2*>(smem);
+  fill_table(tab);
+  const uint32_t s = blockIdx.x * NT + threadIdx.x;
+  const bool valid = s < P.n_streams;
+  Ctx ctx = make_ctx<Ctx>(P, smem + TAB_WORDS * sizeof(uint2), valid ? s : 0, valid);
+  __syncthreads();
+  if (!valid) return;
+  const uint2* mytab = tab + (threadIdx.x & 31);
+  const uint32_t ctx_max = P.n_ctx ? P.n_ctx - 1 : 0;
+
+  typedef typename OpTraits<W>::T OpT;
+  const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
+  const OpT* p = reinterpret_cast<const OpT*>(P.ops) + o0;
+  uint8_t* q = P.bins + o0;
+  uint64_t n = o1 - o0;
+
+  const uint64_t b0 = P.byte_off[s], b1 = P.byte_off[s + 1];
+  DecLane D;
+  dec_start(D, P.bytes + b0, (uint32_t)(b1 - b0));
+
+  uint64_t i = 0;
+  while (i < n && (reinterpret_cast<uintptr_t>(p + i) & 15u)) {
+    q[i] = (uint8_t)decode_one<W, Ctx>(D, p[i], ctx, mytab, ctx_max);
+    ++i;
+  }
+  constexpr int PER = 16 / W;
+  // the bins of one op block are packed and stored with one vector store when the output
+  // address is aligned too (it is whenever P.bins is 16-byte aligned and W == 1)
+  const bool out_vec = (W == 1) && ((reinterpret_cast<uintptr_t>(q + i) & 15u) == 0);
+  if (i + PER <= n) {
+    uint4 cur = __ldg(reinterpret_cast<const uint4*>(p + i));
+    for (;;) {
+      const bool more = i + 2 * PER <= n;
+      uint4 nxt = cur;
+      if (more) nxt = __ldg(reinterpret_cast<const uint4*>(p + i + PER));
+      const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+      uint32_t r[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int b = 0; b < 4 / W; ++b) {
+          uint32_t o = (W == 1) ? ((w[k] >> (8 * b)) & 0xffu) : ((w[k] >> (16 * b)) & 0xffffu);
+          uint32_t bin = decode_one<W, Ctx>(D, o, ctx, mytab, ctx_max);
+          if (W == 1) r[k] |= bin << (8 * b);
+          else q[i + k * 2 + b] = (uint8_t)bin;
+        }
+      }
+      if (W == 1) {
+        if (out_vec) {
+          *reinterpret_cast<uint4*>(q + i) = make_uint4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) q[i + k] = (uint8_t)(r[k >> 2] >> (8 * (k & 3)));
+        }
+      }
+      i += PER;
+      if (!more) break;
+      cur = nxt;
+    }
+  }
+  for (; i < n; ++i) q[i] = (uint8_t)decode_one<W, Ctx>(D, p[i], ctx, mytab, ctx_max);
+
+  if (P.finish_ok) P.finish_ok[s] = (uint8_t)dec_finish(D);
+}
+
+// ---------------------------------------------------------------------------
+// device-wide exclusive scan (u32 -> u64), single pass, decoupled look-back
+// ---------------------------------------------------------------------------
+// Tiles of SCAN_TILE elements; tile order is taken from an atomic ticket so a tile only
+// ever waits for tiles that already started.  Tile descriptor: bit 63 = inclusive prefix
+// available, bit 62 = tile aggregate available, low 62 bits = value.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr unsigned long long FLAG_P = 1ull << 63, FLAG_A = 1ull << 62, VAL_MASK = (1ull << 62) - 1;
+
+__global__ void k_scan_init(unsigned long long* desc, uint32_t n_tiles, uint32_t* ticket) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_tiles) desc[i] = 0;
+  if (i == 0) *ticket = 0;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_u32_u64(const uint32_t* in, uint64_t* out, uint64_t n,
+                                                                unsigned long long* desc, uint32_t* ticket) {
+  __shared__ uint32_t s_tile;
+  __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+  __shared__ unsigned long long s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t base = (uint64_t)tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  unsigned long long local = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    local += v[k];
+  }
+  // warp inclusive scan of the per-thread sums
+  unsigned long long inc = local;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  unsigned long long warp_off = 0, tile_sum = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+    if (w < wid) warp_off += s_warp[w];
+    tile_sum += s_warp[w];
+  }
+  // publish the aggregate, then look back (warp 0)
+  if (wid == 0) {
+    if (lane == 0) {
+      unsigned long long d = (tile == 0 ? FLAG_P : FLAG_A) | tile_sum;
+      atomicExch(&desc[tile], d);
+    }
+    unsigned long long prefix = 0;
+    if (tile > 0) {
+      int64_t look = (int64_t)tile - 1 - lane;
+      for (;;) {
+        unsigned long long d = 0;
+        bool have;
+        do {
+          d = look >= 0 ? atomicAdd(&desc[look >= 0 ? look : 0], 0ull) : FLAG_P;
+          have = (d & (FLAG_P | FLAG_A)) != 0;
+        } while (!__all_sync(0xffffffffu, have));
+        // first lane (closest predecessor first) holding an inclusive prefix ends the walk
+        unsigned has_p = __ballot_sync(0xffffffffu, (d & FLAG_P) != 0);
+        int stop = has_p ? __ffs(has_p) - 1 : 32;
+        unsigned long long contrib = (lane <= stop && look >= 0) ? (d & VAL_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_down_sync(0xffffffffu, contrib, o);
+        contrib = __shfl_sync(0xffffffffu, contrib, 0);
+        prefix += contrib;
+        if (has_p) break;
+        look -= 32;
+      }
+      if (lane == 0) atomicExch(&desc[tile], FLAG_P | (prefix + tile_sum));
+    }
+    if (lane == 0) s_prefix = prefix;
+  }
+  __syncthreads();
+  unsigned long long run = s_prefix + warp_off + (inc - local);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (base <= n - 1 && n - 1 < base + SCAN_ITEMS) out[n] = run;  // total
+}
+
+// One warp per stream: copy lengths[s] bytes from the 16-byte aligned slab row to an
+// arbitrarily aligned payload position.  Destination-aligned 32-bit words are built from
+// two aligned source words with a funnel shift, so every store is a full, coalesced word.
+__global__ void __launch_bounds__(256) k_compact_copy(const uint8_t* slab, uint64_t stride, const uint32_t* lengths,
+                                                       const uint64_t* off, uint8_t* payload, uint64_t cap,
+                                                       uint32_t n_streams, uint32_t* overflow) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_streams) return;
+  uint32_t len = lengths[warp];
+  if (len > stride) len = (uint32_t)stride;
+  const uint64_t d0 = off[warp];
+  if (d0 + len > cap) {
+    if (lane == 0 && overflow) atomicOr(overflow, 2u);
+    return;
+  }
+  const uint8_t* src = slab + (uint64_t)warp * stride;
+  uint8_t* dst = payload + d0;
+  // head bytes up to the first aligned destination word
+  uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+  if (head > len) head = len;
+  if (lane < head) dst[lane] = src[lane];
+  const uint32_t nwords = (len - head) >> 2;
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src);
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+  const uint32_t sh = 8 * head;  // source byte offset of destination word 0 is `head` (0..3)
+  for (uint32_t w = lane; w < nwords; w += 32) {
+    uint32_t lo = sw[w], hi = sh ? sw[w + 1] : 0u;  // sw[w+1] stays inside the slab row: head>0 => bytes remain
+    dw[w] = sh ? __funnelshift_r(lo, hi, sh) : lo;
+  }
+  const uint32_t done = head + (nwords << 2);
+  if (lane < len - done) dst[done + lane] = src[done + lane];
+}
+
+}  // namespace
+
+// ===========================================================================
+// host side of the device-pointer C ABI
+// ===========================================================================
+namespace isscabac_internal {
+
+thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return ISSCABAC_ERR_CUDA;
+}
+
+size_t smem_limit() {
+  static size_t lim = 0;
+  if (!lim) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess)
+      lim = (size_t)v;
+  }
+  return lim;
+}
+
+}  // namespace isscabac_internal
+using namespace isscabac_internal;
+
+namespace {
+
+template <class K>
+int launch_codec(K kernel, const CodecParams& P, size_t smem, cudaStream_t st, const char* name) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  }
+  uint32_t grid = (P.n_streams + NT - 1) / NT;
+  kernel<<<grid, NT, smem, st>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, name);
+  return ISSCABAC_OK;
+}
+
+// picks the context-storage policy; allocates the global scratch when needed
+template <bool ENC>
+int run_codec(CodecParams P, int op_width, cudaStream_t st) {
+  if (op_width != 1 && op_width != 2) { set_error("op_width must be 1 or 2"); return ISSCABAC_ERR_INVALID; }
+  if (P.n_ctx > ISSCABAC_MAX_CTX) { set_error("n_ctx > %u", ISSCABAC_MAX_CTX); return ISSCABAC_ERR_INVALID; }
+  if (P.n_streams == 0) return ISSCABAC_OK;
+  const size_t tab_bytes = TAB_WORDS * sizeof(uint2);
+  const size_t smem_ctx = tab_bytes + (size_t)P.n_ctx * NT * 4;
+  const size_t lim = smem_limit();
+  if (!lim) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
+  // keep at least 2 CTAs per SM resident on the shared-memory path
+  const bool use_smem = smem_ctx <= lim / 2;
+  int rc;
+  if (use_smem) {
+    if (op_width == 1)
+      rc = ENC ? launch_codec(k_encode_ops<1, CtxSmem>, P, smem_ctx, st, "k_encode_ops")
+               : launch_codec(k_decode_ops<1, CtxSmem>, P, smem_ctx, st, "k_decode_ops");
+    else
+      rc = ENC ? launch_codec(k_encode_ops<2, CtxSmem>, P, smem_ctx, st, "k_encode_ops")
+               : launch_codec(k_decode_ops<2, CtxSmem>, P, smem_ctx, st, "k_decode_ops");
+    return rc;
+  }
+  void* scratch = nullptr;
+  cudaError_t e = cudaMallocAsync(&scratch, (size_t)P.n_ctx * P.n_streams, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(ctx scratch)");
+  P.ctx_scratch = static_cast<uint8_t*>(scratch);
+  if (op_width == 1)
+    rc = ENC ? launch_codec(k_encode_ops<1, CtxGmem>, P, tab_bytes, st, "k_encode_ops")
+             : launch_codec(k_decode_ops<1, CtxGmem>, P, tab_bytes, st, "k_decode_ops");
+  else
+    rc = ENC ? launch_codec(k_encode_ops<2, CtxGmem>, P, tab_bytes, st, "k_encode_ops")
+             : launch_codec(k_decode_ops<2, CtxGmem>, P, tab_bytes, st, "k_decode_ops");
+  cudaFreeAsync(scratch, st);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cabac_encode_ops(uint32_t n_streams, const uint64_t* d_op_off, const void* d_ops, int op_width,
+                     const uint8_t* d_ctx_init, uint32_t n_ctx, int per_stream_init,
+                     uint8_t* d_slab, uint64_t slab_stride, uint32_t* d_lengths,
+                     uint32_t* d_overflow, void* stream) {
+  if (n_streams && (!d_op_off || !d_slab || !d_lengths || (n_ctx && !d_ctx_init))) {
+    set_error("cabac_encode_ops: null pointer");
+    return ISSCABAC_ERR_INVALID;
+  }
+  if ((slab_stride & 15u) || slab_stride < 16 || (reinterpret_cast<uintptr_t>(d_slab) & 15u)) {
+    set_error("cabac_encode_ops: slab and slab_stride must be 16-byte aligned");
+    return ISSCABAC_ERR_INVALID;
+  }
+  CodecParams P;
+  memset(&P, 0, sizeof P);
+  P.n_streams = n_streams; P.n_ctx = n_ctx; P.per_stream_init = per_stream_init;
+  P.op_off = d_op_off; P.ops = d_ops; P.ctx_init = d_ctx_init;
+  P.slab = d_slab; P.slab_stride = slab_stride; P.lengths = d_lengths; P.overflow = d_overflow;
+  return run_codec<true>(P, op_width, static_cast<cudaStream_t>(stream));
+}
+
+// <= 6 shift bits per context bin, 1 per bypass bin, 7 per terminate bin, <= 13 tail bits
+// in finish(): 7 bits per op is a proof-level bound.
+uint64_t cabac_slab_stride_bound(uint64_t max_ops) {
+  uint64_t b = (max_ops * 7 + 7) / 8 + 8;
+  return (b + 15) & ~15ull;
+}
+
+int cabac_decode_ops(uint32_t n_streams, const uint64_t* d_byte_off, const uint8_t* d_bytes,
+                     const uint64_t* d_op_off, const void* d_ops, int op_width,
+                     const uint8_t* d_ctx_init, uint32_t n_ctx, int per_stream_init,
+                     uint8_t* d_bins, uint8_t* d_finish_ok, void* stream) {
+  if (n_streams && (!d_byte_off || !d_bytes || !d_op_off || !d_bins || (n_ctx && !d_ctx_init))) {
+    set_error("cabac_decode_ops: null pointer");
+    return ISSCABAC_ERR_INVALID;
+  }
+  CodecParams P;
+  memset(&P, 0, sizeof P);
+  P.n_streams = n_streams; P.n_ctx = n_ctx; P.per_stream_init = per_stream_init;
+  P.op_off = d_op_off; P.ops = d_ops; P.ctx_init = d_ctx_init;
+  P.byte_off = d_byte_off; P.bytes = d_bytes; P.bins = d_bins; P.finish_ok = d_finish_ok;
+  return run_codec<false>(P, op_width, static_cast<cudaStream_t>(stream));
+}
+
+size_t cabac_compact_scratch_bytes(uint32_t n_streams) {
+  size_t tiles = ((size_t)n_streams + SCAN_TILE - 1) / SCAN_TILE;
+  return (tiles + 1) * sizeof(unsigned long long) + 256;
+}
+
+}  // extern "C"
+
+namespace isscabac_internal {
+
+int exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, void* d_scratch, cudaStream_t st) {
+  if (n == 0) {
+    cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(uint64_t), st);
+    return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "cudaMemsetAsync");
+  }
+  uint32_t tiles = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+  unsigned long long* desc = static_cast<unsigned long long*>(d_scratch);
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(desc + tiles);
+  k_scan_init<<<(tiles + 255) / 256, 256, 0, st>>>(desc, tiles, ticket);
+  k_scan_u32_u64<<<tiles, SCAN_THREADS, 0, st>>>(d_in, d_out, n, desc, ticket);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_scan_u32_u64");
+}
+
+}  // namespace isscabac_internal
+
+extern "C" int cabac_compact(uint32_t n_streams, const uint8_t* d_slab, uint64_t slab_stride,
+                             const uint32_t* d_lengths, uint8_t* d_payload, uint64_t payload_cap,
+                             uint64_t* d_byte_off, void* d_scratch, uint32_t* d_overflow, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!d_byte_off || (n_streams && (!d_slab || !d_lengths || !d_scratch))) {
+    set_error("cabac_compact: null pointer");
+    return ISSCABAC_ERR_INVALID;
+  }
+  int rc = exclusive_scan_u32_u64(d_lengths, d_byte_off, n_streams, d_scratch, st);
+  if (rc || n_streams == 0 || !d_payload) return rc;
+  uint32_t blocks = (uint32_t)(((uint64_t)n_streams * 32 + 255) / 256);
+  k_compact_copy<<<blocks, 256, 0, st>>>(d_slab, slab_stride, d_lengths, d_byte_off, d_payload, payload_cap,
+                                         n_streams, d_overflow);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_compact_copy");
+}

@@ -200,6 +200,18 @@ def gen_mex():
     for c in ctxs:
         hcall(1, "decodeBin", [float(c)])
     hcall(0, "decodeFinish")
+    # the SAME handle codes a second stream: contexts are NOT re-initialised by encodeStart
+    # (SimpleCABACMex.cpp:186-209) and the bit counter keeps running (CABAC_BitstreamFile.h:70)
+    hcall(0, "encodeStart")
+    bins2 = (rng.random(150) < 0.3).astype(int)
+    ctxs2 = rng.integers(0, 5, size=150)          # contexts 3,4 were never initialised: constructor default
+    for i, (b, c) in enumerate(zip(bins2, ctxs2)):
+        hcall(0, "encodeBin", [float(b)], [float(c)])
+        if i % 25 == 24:
+            hcall(1, "getNumBits")
+    hcall(0, "encodeFinish")
+    hcall(1, "getNumBits")
+    log.append(dict(file=open(fn, "rb").read().hex()))
     os.unlink(fn)
     with open(os.path.join(OUT, "mex_session.json"), "w") as f:
         json.dump(log, f)

@@ -1,0 +1,107 @@
+// TEST INFRASTRUCTURE: compiles the product's per-lane coder logic
+// (isscabac_b200/csrc/cabac_lane.cuh, the exact code the CUDA kernels run) with g++
+// and drives it one stream at a time, so the algorithmic restructuring (eager byte
+// output + walk-back carries, fused MPS/LPS step, closed-form binarizer) can be
+// checked against the oracle on a machine without a GPU.  Never part of the product.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../isscabac_b200/csrc/cabac_lane.cuh"
+
+using namespace cabac;
+
+extern "C" {
+
+int emul_encode_ops(uint32_t n_streams, const uint64_t* op_off, const void* ops, int width,
+                    const uint8_t* ctx_init, uint32_t n_ctx, int per_stream,
+                    uint8_t* slab, uint64_t stride, uint32_t* lens, uint32_t* bits_trace) {
+  const uint32_t ep = width == 1 ? 126u : 0x7FFEu, trm = width == 1 ? 125u : 0x7FFDu;
+  std::vector<uint32_t> ctx(n_ctx ? n_ctx : 1);
+  int ovf = 0;
+  for (uint32_t s = 0; s < n_streams; ++s) {
+    for (uint32_t c = 0; c < n_ctx; ++c) ctx[c] = ctx_init[(per_stream ? (uint64_t)s * n_ctx : 0) + c];
+    EncLane L;
+    enc_start(L, slab + s * stride, (uint32_t)stride);
+    for (uint64_t i = op_off[s]; i < op_off[s + 1]; ++i) {
+      uint32_t o = width == 1 ? ((const uint8_t*)ops)[i] : ((const uint16_t*)ops)[i];
+      uint32_t code = o >> 1, bin = o & 1u;
+      if (code == ep) enc_bin_ep<true>(L, bin);
+      else if (code == trm) enc_bin_trm<true>(L, bin);
+      else enc_bin_ctx<true>(L, bin, ctx[code], fused_row(ctx[code]));
+      if (bits_trace) bits_trace[i] = enc_bits_written(L);
+    }
+    enc_finish<true>(L);
+    enc_flush_pending(L);
+    lens[s] = L.nbytes;
+    ovf |= L.overflow;
+  }
+  return ovf;
+}
+
+int emul_decode_ops(uint32_t n_streams, const uint64_t* byte_off, const uint8_t* bytes,
+                    const uint64_t* op_off, const void* ops, int width,
+                    const uint8_t* ctx_init, uint32_t n_ctx, int per_stream,
+                    uint8_t* bins, uint8_t* ok) {
+  const uint32_t ep = width == 1 ? 126u : 0x7FFEu, trm = width == 1 ? 125u : 0x7FFDu;
+  std::vector<uint32_t> ctx(n_ctx ? n_ctx : 1);
+  for (uint32_t s = 0; s < n_streams; ++s) {
+    for (uint32_t c = 0; c < n_ctx; ++c) ctx[c] = ctx_init[(per_stream ? (uint64_t)s * n_ctx : 0) + c];
+    DecLane D;
+    dec_start(D, bytes + byte_off[s], (uint32_t)(byte_off[s + 1] - byte_off[s]));
+    for (uint64_t i = op_off[s]; i < op_off[s + 1]; ++i) {
+      uint32_t o = width == 1 ? ((const uint8_t*)ops)[i] : ((const uint16_t*)ops)[i];
+      uint32_t code = o >> 1;
+      if (code == ep) bins[i] = (uint8_t)dec_bin_ep(D);
+      else if (code == trm) bins[i] = (uint8_t)dec_bin_trm(D);
+      else bins[i] = (uint8_t)dec_bin_ctx(D, ctx[code], fused_row(ctx[code]));
+    }
+    ok[s] = (uint8_t)dec_finish(D);
+  }
+  return 0;
+}
+
+// symbols -> ops through the closed-form binarizer + context selection
+uint64_t emul_symbols_to_ops(const int32_t* cfgv, const uint32_t* sym, uint64_t n, uint8_t* ops) {
+  SymCfg cfg{cfgv[0], cfgv[1], (uint32_t)cfgv[2], cfgv[3], (uint32_t)cfgv[4], (uint32_t)cfgv[5]};
+  uint64_t k = 0;
+  SymCode prev{0, 0, 0};
+  for (uint64_t i = 0; i < n; ++i) {
+    SymCode c = sym_code(sym[i], cfg.Nq, cfg.method);
+    bool up = sym_has_up(cfg, i);
+    for (uint32_t b = 1; b <= c.len; ++b) {
+      int cx = select_ctx(cfg, b, c.np, prev, up);
+      uint32_t code = cx < 0 ? 126u : (uint32_t)cx;
+      ops[k++] = (uint8_t)((code << 1) | sym_bin(c, b));
+    }
+    prev = c;
+  }
+  return k;
+}
+
+// bytes -> symbols through the incremental symbol decoder
+int emul_decode_symbols(const int32_t* cfgv, const uint8_t* bytes, uint32_t len, uint64_t n_sym,
+                        const uint8_t* ctx_init, uint32_t n_ctx, uint32_t* out, uint8_t* ok) {
+  SymCfg cfg{cfgv[0], cfgv[1], (uint32_t)cfgv[2], cfgv[3], (uint32_t)cfgv[4], (uint32_t)cfgv[5]};
+  std::vector<uint32_t> ctx(n_ctx ? n_ctx : 1);
+  for (uint32_t c = 0; c < n_ctx; ++c) ctx[c] = ctx_init[c];
+  DecLane D;
+  dec_start(D, bytes, len);
+  SymCode prev{0, 0, 0};
+  for (uint64_t i = 0; i < n_sym; ++i) {
+    SymDec sd;
+    symdec_reset(sd);
+    bool up = sym_has_up(cfg, i);
+    uint32_t v = 0;
+    for (;;) {
+      int cx = select_ctx(cfg, sd.n + 1, sd.np, prev, up);
+      uint32_t bin = cx < 0 ? dec_bin_ep(D) : dec_bin_ctx(D, ctx[cx], fused_row(ctx[cx]));
+      if (symdec_push(sd, bin, cfg, v)) break;
+    }
+    out[i] = v;
+    prev = sym_code(v, cfg.Nq, cfg.method);
+  }
+  *ok = (uint8_t)dec_finish(D);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+"""GPU parity tests for the symbol-level kernels (binarizer + context selection + coder)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ALLT = O.CM_COND0 | O.CM_COND1 | O.CM_CONDS0 | O.CM_CONDS1
+
+
+@pytest.fixture(scope="module")
+def I():
+    import isscabac_b200 as I
+    assert torch.cuda.is_available()
+    return I
+
+
+def test_golden_symbol_cases(I, golden_dir):
+    """ops from the device binarizer == oracle ops; fused encode == bytes from the REFERENCE engine."""
+    z = np.load(os.path.join(golden_dir, "symbols_refengine.npz"))
+    names = sorted({k[:-4] for k in z.files if k.endswith("_sym")})
+    for nm in names:
+        prof, meth, Nq, Nlbp, types, rows = [int(x) for x in z[nm + "_cfg"]]
+        cfg = I.make_cfg(prof, meth, Nq, Nlbp, types, rows)
+        sym = z[nm + "_sym"].astype(np.uint32)
+        off = np.array([0, len(sym)], dtype=np.int64)
+        ops, op_off = I.binarize_symbols(cfg, sym, off)
+        assert (ops.cpu().numpy() == z[nm + "_ops"]).all(), nm
+        assert int(op_off[-1].item()) == len(z[nm + "_ops"])
+        want = z[nm + "_bytes"]
+        enc = I.encode_symbols(cfg, sym, off, z[nm + "_ctx"], slab_stride=len(want) + 64)
+        assert int(enc.lengths[0].item()) == len(want), nm
+        assert (enc.slab[0, :len(want)].cpu().numpy() == want).all(), nm
+        pay = I.compact(enc)
+        dec, ok = I.decode_symbols(cfg, pay, off, z[nm + "_ctx"])
+        assert bool(ok.all().item()) and (dec.cpu().numpy().astype(np.uint32) == sym).all(), nm
+        # two-kernel route (binarize -> ops encoder) gives the same bytes
+        enc2 = I.encode_ops(ops, op_off, z[nm + "_ctx"], slab_stride=len(want) + 64)
+        assert (enc2.slab[0, :len(want)].cpu().numpy() == want).all(), nm
+
+
+@pytest.mark.parametrize("prof,meth,Nq,rows,dtype", [
+    (O.PROFILE_DEMO, O.BIN_TU, 4, 0, np.uint8),
+    (O.PROFILE_DEMO, O.BIN_EG0, 4, 0, np.uint8),
+    (O.PROFILE_ISS, O.BIN_EG0, 8, 400, np.uint8),       # W matrices of ISS.m: 400 x 20
+    (O.PROFILE_ISS, O.BIN_EG0, 8, 109, np.uint16),      # H matrices: 109 x 20
+    (O.PROFILE_ISS, O.BIN_EG2, 64, 50, np.uint32),
+    (O.PROFILE_ISS, O.BIN_TU, 8, 20, np.uint8),
+    (O.PROFILE_FLAT, O.BIN_EG0, 16, 0, np.uint8),       # config C4 segments
+    (O.PROFILE_FLAT_EPSUF, O.BIN_EG2, 256, 0, np.uint8),  # config C5 streams
+    (O.PROFILE_FLAT, O.BIN_FL32, 0, 0, np.uint32),
+])
+def test_many_streams_vs_oracle(I, prof, meth, Nq, rows, dtype):
+    rng = np.random.default_rng(21)
+    n_streams = 700
+    if rows:
+        counts = np.full(n_streams, rows * 20)
+        counts[:50] = rng.integers(0, rows * 3, size=50)     # ragged: partial last column
+    else:
+        counts = np.clip(np.round(rng.lognormal(np.log(256), 1.0, size=n_streams)), 1, 4000).astype(np.int64)
+    counts[0] = 0
+    off = np.zeros(n_streams + 1, dtype=np.uint64)
+    np.cumsum(counts, out=off[1:])
+    n = int(off[-1])
+    if meth == O.BIN_FL32:
+        sym = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    else:
+        sym = np.minimum(np.floor(rng.exponential(Nq / 6.0 + 0.5, size=n)), Nq - 1).astype(dtype)
+    nctx = O.num_ctx(prof, 3)
+    ci = rng.integers(0, 126, size=(n_streams, nctx)).astype(np.uint8)
+    cfg = I.make_cfg(prof, meth, Nq, 3, ALLT, rows)
+    ocfg = O.make_cfg(prof, meth, Nq, 3, ALLT, rows)
+    stride = 16 * 1024 if meth != O.BIN_FL32 else 32 * 1024
+    enc, bits = I.encode_symbols(cfg, sym, off.astype(np.int64), ci, slab_stride=stride, want_bits=True)
+    s_ref, l_ref, bits_ref = O.encode_symbols(ocfg, sym, off, ci, stride, n_threads=8, want_bits=True)
+    torch.cuda.synchronize()
+    enc.check_overflow()
+    assert (enc.lengths.cpu().numpy().astype(np.uint32) == l_ref).all()
+    w = int(l_ref.max())
+    assert (enc.slab[:, :w].cpu().numpy() == s_ref[:, :w]).all()
+    assert (bits.cpu().numpy().astype(np.uint32) == bits_ref).all()        # getNumBits() after every symbol
+    pay = I.compact(enc)
+    tdt = {np.uint8: torch.uint8, np.uint16: torch.int16, np.uint32: torch.int32}[dtype]
+    dec, ok = I.decode_symbols(cfg, pay, off.astype(np.int64), ci, sym_dtype=tdt)
+    assert bool(ok.all().item())
+    assert (dec.cpu().numpy().view(dtype) == sym).all()
+    # symbol-parallel binarizer against the oracle's op stream
+    ops, op_off = I.binarize_symbols(cfg, sym, off.astype(np.int64))
+    want = np.concatenate([O.symbols_to_ops(ocfg, sym[int(off[s]):int(off[s + 1])]) for s in range(n_streams)])
+    assert (ops.cpu().numpy() == want).all()
+
+
+def test_symbol_host_api(I):
+    rng = np.random.default_rng(22)
+    sym = rng.integers(0, 8, size=400 * 20).astype(np.uint8)
+    off = np.array([0, len(sym)], dtype=np.uint64)
+    ci = O.ctx_from_p0(np.full(23, 128 / 255.0))
+    cfg = I.make_cfg(I.PROFILE_ISS, "DEC2EG0", 8, 3, ["cond0", "cond1", "conds0", "conds1"], rows=400)
+    payload, boff, bits = I.encode_symbols_host(cfg, sym, off, ci, want_bits=True)
+    s_ref, l_ref, b_ref = O.encode_symbols(O.make_cfg(O.PROFILE_ISS, O.BIN_EG0, 8, 3, ALLT, 400), sym, off, ci, 8192, want_bits=True)
+    assert bytes(payload) == bytes(s_ref[0, :l_ref[0]]) and (bits == b_ref).all()
+    dec, ok = I.decode_symbols_host(cfg, payload, boff, off, ci, dtype=np.uint8)
+    assert ok.all() and (dec == sym).all()
