@@ -111,7 +111,8 @@ def test_random_vs_oracle(I, seed, n_streams, n_ops, n_ctx, p_ep, ragged):
     s_ref, l_ref = O.encode_ops(ops, off, ci, out_stride=stride, n_threads=8)
     assert (lens == l_ref).all()
     w = int(l_ref.max())
-    assert (slab[:, :w] == s_ref[:, :w]).all()
+    live = np.arange(w)[None, :] < l_ref[:, None]   # bytes past a stream's length are unspecified
+    assert (slab[:, :w][live] == s_ref[:, :w][live]).all()
     p_ref, b_ref = O.compact(s_ref, l_ref)
     assert (boff == b_ref).all() and (payload[:len(p_ref)] == p_ref).all()
     assert ok.all() and (bins == (ops & 1)).all()

@@ -81,7 +81,8 @@ def test_many_streams_vs_oracle(I, prof, meth, Nq, rows, dtype):
     enc.check_overflow()
     assert (enc.lengths.cpu().numpy().astype(np.uint32) == l_ref).all()
     w = int(l_ref.max())
-    assert (enc.slab[:, :w].cpu().numpy() == s_ref[:, :w]).all()
+    live = np.arange(w)[None, :] < l_ref[:, None]   # bytes past a stream's length are unspecified
+    assert (enc.slab[:, :w].cpu().numpy()[live] == s_ref[:, :w][live]).all()
     assert (bits.cpu().numpy().astype(np.uint32) == bits_ref).all()        # getNumBits() after every symbol
     pay = I.compact(enc)
     tdt = {np.uint8: torch.uint8, np.uint16: torch.int16, np.uint32: torch.int32}[dtype]
