@@ -20,6 +20,13 @@ def I():
     return I
 
 
+def same_rows(slab, s_ref, lens):
+    """slab rows equal up to each stream's own length (bytes past it are unspecified)."""
+    w = int(lens.max()) if len(lens) else 0
+    live = np.arange(w)[None, :] < np.asarray(lens)[:, None]
+    return bool((slab[:, :w][live] == s_ref[:, :w][live]).all())
+
+
 def script_to_ops(script, wide=False):
     ep, trm = (O.OP16_EP, O.OP16_TRM) if wide else (O.OP8_EP, O.OP8_TRM)
     ops = []
@@ -110,9 +117,7 @@ def test_random_vs_oracle(I, seed, n_streams, n_ops, n_ctx, p_ep, ragged):
     slab, lens, payload, boff, bins, ok = gpu_roundtrip(I, ops, off, ci, stride=stride)
     s_ref, l_ref = O.encode_ops(ops, off, ci, out_stride=stride, n_threads=8)
     assert (lens == l_ref).all()
-    w = int(l_ref.max())
-    live = np.arange(w)[None, :] < l_ref[:, None]   # bytes past a stream's length are unspecified
-    assert (slab[:, :w][live] == s_ref[:, :w][live]).all()
+    assert same_rows(slab, s_ref, l_ref)
     p_ref, b_ref = O.compact(s_ref, l_ref)
     assert (boff == b_ref).all() and (payload[:len(p_ref)] == p_ref).all()
     assert ok.all() and (bins == (ops & 1)).all()
@@ -131,7 +136,7 @@ def test_many_contexts_global_path(I):
     ci = rng.integers(0, 126, size=(n_streams, n_ctx)).astype(np.uint8)
     slab, lens, payload, boff, b, ok = gpu_roundtrip(I, ops, off, ci, stride=1024)
     s_ref, l_ref = O.encode_ops(ops, off, ci, out_stride=1024, n_threads=8)
-    assert (lens == l_ref).all() and (slab[:, :int(l_ref.max())] == s_ref[:, :int(l_ref.max())]).all()
+    assert (lens == l_ref).all() and same_rows(slab, s_ref, l_ref)
     assert ok.all() and (b == (ops & 1)).all()
 
 
@@ -197,4 +202,4 @@ def test_full_length_streams_roundtrip(I):
     slab, lens, payload, boff, bins, ok = gpu_roundtrip(I, ops, off, ci, stride=16448)
     assert ok.all() and (bins == (ops & 1)).all()
     s_ref, l_ref = O.encode_ops(ops[:64 * 65536], off[:65], ci, out_stride=16448, n_threads=8)
-    assert (lens[:64] == l_ref).all() and (slab[:64, :int(l_ref.max())] == s_ref[:, :int(l_ref.max())]).all()
+    assert (lens[:64] == l_ref).all() and same_rows(slab[:64], s_ref, l_ref)
