@@ -59,6 +59,15 @@ CB_HD uint32_t cb_funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
 #endif
 }
 
+// upper 32 bits of ((hi:lo) << s), 0 <= s < 32
+CB_HD uint32_t cb_funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, s);
+#else
+  return (uint32_t)((((((uint64_t)hi) << 32) | lo) << s) >> 32);
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // tables
 // ---------------------------------------------------------------------------

@@ -1,0 +1,353 @@
+// cabac_wide.cuh -- the wide-window formulation of the per-lane coder (the hot path).
+//
+// Same arithmetic as the reference engine (CABAC_ArithmeticEncoder.cpp:113-178,250-270,
+// 326-412; CABAC_ArithmeticDecoder.cpp:54-190,288-331,423-472), restated so that a lane
+// touches memory once per 32 coded BITS instead of once per byte, and so that the per-bin
+// step is one straight-line sequence with no data-dependent branch:
+//
+//  encoder  The reference keeps `low` in 32 bits and moves one byte out whenever fewer
+//           than 12 free bits remain, parking it in bufferedByte/numBufferedBytes until a
+//           carry can no longer reach it (writeOut, :380-412).  Here the window is 64 bits
+//           (kept as W = 2*low, see below), whole big-endian 32-bit words leave it at fixed
+//           points of the instruction stream (after every 4th bin), and a carry is added to
+//           the previously emitted word, which is still in a register (`pend`); only a carry
+//           into a 0xFFFFFFFF word has to walk back through memory.  Every emitted bit is a
+//           bit >= 9 of the reference's `low`, i.e. one that later bins can only change by
+//           a carry, so the bytes are identical.
+//  decoder  The reference keeps 9+7 bits of `value` plus up to 8 look-ahead bits and reads
+//           one byte whenever they run out (:137-141,156-162,295-299).  Here the window
+//           holds value<<15 followed by up to 47 look-ahead bits and is topped up with one
+//           32-bit word after every 4th bin.  All decisions compare bits the reference has
+//           already read, so the decoded bins are identical; bytes past the end of a stream
+//           read as 0xFF like CABAC_BitstreamFile.cpp:153-158.
+//  bypass   W = 2*low makes encodeBinEP the same expression as the LPS branch of encodeBin:
+//           W' = (W + add) << n with add = bin ? range : 0, n = 1 (context bins: add =
+//           isLPS ? 2*rMPS : 0, n = renorm shift).  A bypass op is therefore coded as a
+//           context bin on a dummy context slot whose state byte is 0x80 (mps bit 0, both
+//           next states 0x80); three selects pick range / 1 / range instead of the
+//           context-path values.  The decoder mirrors this with value - (bin ? range<<21 : 0).
+//
+// Everything is __host__ __device__ so that tests/emul compiles exactly this code with g++.
+#pragma once
+#include "cabac_lane.cuh"
+
+namespace cabac {
+
+constexpr uint32_t kEpState = 128;     // dummy state byte of the bypass slot
+constexpr uint32_t kNumRows = 129;     // fused rows 0..127 + the bypass row
+
+// rows as the wide kernels use them: x = four LPS sub-ranges, y = nextMPS | nextLPS << 8
+CB_HD constexpr uint2 wide_row(uint32_t st) {
+  return st < 128 ? fused_row(st) : uint2{0u, kEpState | (kEpState << 8)};
+}
+
+CB_HD uint32_t cb_bswap(uint32_t x) { return cb_perm(x, 0, 0x0123); }
+
+// ---------------------------------------------------------------------------
+// encoder
+// ---------------------------------------------------------------------------
+struct EncWide {
+  uint64_t W;         // 2 * (the reference's low), bits below the not-yet-emitted point
+  uint32_t range;
+  int32_t n;          // bits shifted in since the last emitted word boundary (reference: 23 - bitsLeft, mod emission)
+  uint32_t pend;      // last emitted word (numeric value), kept for carries
+  uint32_t wi;        // words emitted so far
+  uint32_t cap_words; // slab capacity in words
+  uint32_t overflow;
+  uint32_t* out;      // slab row, 4-byte aligned
+};
+
+CB_HD void encw_start(EncWide& E, uint8_t* out, uint32_t cap_bytes) {  // Encoder.cpp:54-61
+  E.W = 0; E.range = 510; E.n = 0; E.pend = 0; E.wi = 0; E.overflow = 0;
+  E.cap_words = cap_bytes >> 2;
+  E.out = reinterpret_cast<uint32_t*>(out);
+}
+
+// +1 into the words already emitted (replaces Encoder.cpp:394-404 and :76-87).  Rare: about
+// one carry per 1000 bins, and the walk past `pend` needs a 0xFFFFFFFF word.
+CB_HD_NOINLINE uint32_t encw_carry(uint32_t pend, uint32_t wi, uint32_t cap_words, uint32_t* out) {
+  pend += 1u;
+  if (wi == 0) return pend;
+  volatile uint32_t* o = out;
+  if (wi - 1 < cap_words) o[wi - 1] = cb_bswap(pend);
+  if (pend == 0) {
+    for (int64_t i = (int64_t)wi - 2; i >= 0; --i) {
+      if ((uint64_t)i >= cap_words) continue;
+      uint32_t v = cb_bswap(o[i]) + 1u;
+      o[i] = cb_bswap(v);
+      if (v != 0) break;
+    }
+  }
+  return pend;
+}
+
+// Move one 32-bit word out when at least 32 settled bits are waiting.  Emits the bits
+// [n-23, n+8] of the reference's low: the four bytes the reference would hand to
+// writeOut() over its next four calls.
+CB_HD void encw_emit(EncWide& E) {
+  if (E.n >= 32) {
+    const uint32_t sh = (uint32_t)E.n - 22u;  // 10..31
+    const uint64_t t = E.W >> sh;             // 33 bits: word + carry
+    E.W &= (1ull << sh) - 1ull;
+    E.n -= 32;
+    if ((uint32_t)(t >> 32)) E.pend = encw_carry(E.pend, E.wi, E.cap_words, E.out);
+    const uint32_t word = (uint32_t)t;
+    if (E.wi < E.cap_words) E.out[E.wi] = cb_bswap(word);
+    else E.overflow = 1;
+    E.pend = word;
+    E.wi++;
+  }
+}
+
+// One bin, context-coded or bypass (see the file header).  st = state byte of the slot the
+// op addresses (kEpState for a bypass op), row = wide_row(st); returns the new state byte.
+CB_HD uint32_t encw_bin(EncWide& E, uint32_t o, bool is_ep, uint32_t st, uint2 row) {
+  const uint32_t lps = cb_perm(0, row.x, E.range >> 6);
+  const uint32_t rmps = E.range - lps;
+  const uint32_t is_lps = (st ^ o) & 1u;
+  const uint32_t x2 = is_ep ? E.range : 2u * rmps;
+  const uint32_t rsel = is_lps ? lps : rmps;
+  const int nn = cb_clz(rsel | 4u) - 23;     // min(clz(rsel)-23, 6): Encoder.cpp:482-492 incl. the state-63 row
+  const int ns = is_ep ? 1 : nn;
+  E.W = (E.W + (uint64_t)(is_lps ? x2 : 0u)) << ns;
+  E.range = is_ep ? E.range : (rsel << nn);
+  E.n += ns;
+  return cb_perm(row.y, 0, is_lps | 0x4440u);
+}
+
+// encodeBinTrm, Encoder.cpp:326-367 (the only op that is a real branch; a handful per stream)
+CB_HD void encw_trm(EncWide& E, uint32_t bin) {
+  E.range -= 2;
+  if (bin) {
+    E.W = (E.W + 2ull * E.range) << 7;
+    E.range = 256;
+    E.n += 7;
+  } else if (E.range < 256) {
+    E.W <<= 1; E.range <<= 1; E.n += 1;
+  }
+}
+
+// finish, Encoder.cpp:70-105; returns the stream length in bytes
+CB_HD uint32_t encw_finish(EncWide& E) {
+  encw_emit(E);
+  encw_trm(E, 1);
+  encw_emit(E);
+  const uint32_t cbit = (uint32_t)E.n + 10u;            // bit 9+n of low = the carry finish() tests (:76)
+  if ((E.W >> cbit) & 1ull) {
+    E.pend = encw_carry(E.pend, E.wi, E.cap_words, E.out);
+    E.W &= ~(1ull << cbit);
+  }
+  // write(low >> 8, 24 - bitsLeft) = n+1 bits, the stop bit, zero padding (:100-104)
+  const uint32_t tb = (uint32_t)E.n + 2u;               // <= 33
+  const uint64_t tail = ((((E.W >> 9) & ((1ull << (E.n + 1)) - 1ull)) << 1) | 1ull) << (64u - tb);
+  const uint32_t nb = (tb + 7u) >> 3;
+  uint8_t* o8 = reinterpret_cast<uint8_t*>(E.out);
+  const uint32_t base = 4u * E.wi;
+  for (uint32_t j = 0; j < nb; ++j) {
+    if (base + j < 4u * E.cap_words) o8[base + j] = (uint8_t)(tail >> (56u - 8u * j));
+    else E.overflow = 1;
+  }
+  return base + nb;
+}
+
+// ---------------------------------------------------------------------------
+// decoder
+// ---------------------------------------------------------------------------
+// Window R = hi:lo.  Stream byte m sits at bits [55-8m+s, 62-8m+s] after s shifts, so the
+// reference's 16+ bit `value` is hi >> 15.  f = number of low bits of R not yet filled;
+// with p = stream bytes loaded so far, f = 63 + s - 8p, which also gives the total shift
+// count s back for finish().
+struct DecWide {
+  uint32_t lo, hi;
+  uint32_t range;
+  int32_t f;
+  uint32_t p;            // stream bytes loaded into the window (3 mod 4 after start)
+  uint32_t len;          // stream length in bytes
+  uint32_t cur;          // aligned little-endian word that holds stream byte p (and up to 3 earlier ones)
+  uint32_t sel;          // byte selector turning {cur,next} into the big-endian word of stream bytes p..p+3
+  const uint32_t* wp;    // address of the aligned word after `cur`
+  const uint8_t* in;     // first byte of the stream
+};
+
+// big-endian word of stream bytes p..p+3, 0xFF past the end (BitstreamFile.cpp:153-158)
+CB_HD uint32_t decw_fetch(DecWide& D) {
+  uint32_t w;
+  if (D.p < D.len) {
+    // the second aligned word is only touched when the stream really extends into it
+    const uint32_t k = D.sel >> 12;                       // offset of byte p inside cur
+    const uint32_t nxt = (D.p + (4u - k) < D.len) ? *D.wp : 0u;
+    w = cb_perm(D.cur, nxt, D.sel);
+    D.cur = nxt;
+    D.wp++;
+    const uint32_t rem = D.len - D.p;
+    if (rem < 4u) w |= 0xffffffffu >> (8u * rem);
+  } else {
+    w = 0xffffffffu;
+  }
+  D.p += 4u;
+  return w;
+}
+
+CB_HD void decw_refill(DecWide& D) {
+  if (D.f >= 32) {
+    const uint32_t w = decw_fetch(D);
+    const uint32_t k = (uint32_t)D.f - 32u;                // 0..23
+    D.lo |= w << k;
+    D.hi |= cb_funnel_l(w, 0u, k);                         // w >> (32-k), 0 when k == 0
+    D.f -= 32;
+  }
+}
+
+// start, Decoder.cpp:54-60: the reference reads two bytes; here the first seven go in.
+CB_HD void decw_start(DecWide& D, const uint8_t* in, uint32_t len) {
+  D.in = in; D.len = len; D.range = 510;
+  const uint32_t b0 = len > 0 ? in[0] : 0xffu, b1 = len > 1 ? in[1] : 0xffu, b2 = len > 2 ? in[2] : 0xffu;
+  D.hi = ((b0 << 24) | (b1 << 16) | (b2 << 8)) >> 1;
+  D.lo = 0;
+  D.p = 3; D.f = 63 - 24;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(in) + 3u;
+  const uint32_t k = (uint32_t)(a & 3u);
+  D.sel = (k + 3u) | ((k + 2u) << 4) | ((k + 1u) << 8) | (k << 12);
+  const uint32_t* w0 = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  D.cur = (D.p < len) ? *w0 : 0u;
+  D.wp = w0 + 1;
+  decw_refill(D);   // bytes 3..6
+}
+
+// One bin, context-coded or bypass; returns the bin, st is updated in place.
+CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, uint32_t& st, uint2 row) {
+  const uint32_t lps = cb_perm(0, row.x, D.range >> 6);
+  const uint32_t rmps = D.range - lps;
+  const uint32_t x2 = is_ep ? D.range : 2u * rmps;
+  const uint32_t scaled = x2 << 21;                        // reference: scaledRange << 15 (bypass: compare before the shift)
+  const uint32_t is_lps = D.hi >= scaled ? 1u : 0u;
+  const uint32_t rsel = is_lps ? lps : rmps;
+  const int nn = cb_clz(rsel | 4u) - 23;
+  const int ns = is_ep ? 1 : nn;
+  const uint32_t h = D.hi - (is_lps ? scaled : 0u);
+  D.hi = cb_funnel_l(D.lo, h, (uint32_t)ns);                // (h:lo) << ns, ns in 0..6
+  D.lo <<= ns;
+  D.range = is_ep ? D.range : (rsel << nn);
+  D.f += ns;
+  const uint32_t bin = (st ^ is_lps) & 1u;
+  st = cb_perm(row.y, 0, is_lps | 0x4440u);
+  return bin;
+}
+
+// decodeBinTrm, Decoder.cpp:423-472
+CB_HD uint32_t decw_trm(DecWide& D) {
+  D.range -= 2;
+  const uint32_t scaled = D.range << 22;
+  if (D.hi >= scaled) return 1u;
+  if (D.range < 256u) {
+    D.range <<= 1;
+    D.hi = (D.hi << 1) | (D.lo >> 31);
+    D.lo <<= 1;
+    D.f += 1;
+  }
+  return 0u;
+}
+
+// finish, Decoder.cpp:73-85: terminate bin must be 1 and the unread part of the last byte
+// the reference would have read must be the stop bit followed by zeros.
+CB_HD uint32_t decw_finish(DecWide& D) {
+  const uint32_t t = decw_trm(D);
+  const uint32_t s = (uint32_t)(D.f + 8 * (int32_t)D.p - 63);   // total shift count
+  const uint32_t idx = 1u + (s >> 3);                           // last byte the reference has read
+  const uint32_t last = idx < D.len ? D.in[idx] : 0xffu;
+  const uint32_t stop = ((last << (s & 7u)) & 0xffu) == 0x80u;
+  return (t == 1u && stop) ? 1u : 0u;
+}
+
+// ---------------------------------------------------------------------------
+// op blocks: the schedule both kernels and the host emulation follow
+// ---------------------------------------------------------------------------
+// u8 op format: op = code << 1 | bin, code 0..124 context, 125 terminate, 126 bypass.
+constexpr uint32_t kOpEpByte = 126u << 1;   // op bytes >= this are bypass ops
+constexpr uint32_t kOpTrmCode = 125u;
+
+// true when one of the 16 op bytes of a block may be a terminate op (false positives are
+// possible -- never false negatives -- and only send the block down the general path)
+CB_HD bool block_has_trm(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  // code bytes are <= 0x7f, so "byte == 0" <=> borrow into bit 7 of (x - 0x01): exact for the
+  // lowest zero byte, possibly a false positive above it
+  const uint32_t h0 = (((w0 >> 1) & 0x7f7f7f7fu) ^ 0x7d7d7d7du) - 0x01010101u;
+  const uint32_t h1 = (((w1 >> 1) & 0x7f7f7f7fu) ^ 0x7d7d7d7du) - 0x01010101u;
+  const uint32_t h2 = (((w2 >> 1) & 0x7f7f7f7fu) ^ 0x7d7d7d7du) - 0x01010101u;
+  const uint32_t h3 = (((w3 >> 1) & 0x7f7f7f7fu) ^ 0x7d7d7d7du) - 0x01010101u;
+  return ((h0 | h1 | h2 | h3) & 0x80808080u) != 0u;
+}
+
+// Context storage as the kernels see it: slot c of this lane, c == n_ctx is the bypass slot.
+// Tab::row(st) returns wide_row(st).
+template <class Ctx, class Tab>
+CB_HD void encw_op(EncWide& E, uint32_t o, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
+  const bool is_ep = o >= kOpEpByte;
+  const uint32_t c = (o >> 1) < n_ctx ? (o >> 1) : n_ctx;
+  const uint32_t st = ctx.load(c);
+  ctx.store(c, encw_bin(E, o, is_ep, st, tab.row(st)));
+}
+
+// 16 ops without a terminate op: 4 x (4 bins, emit).  Worst case 6 bits per bin: n <= 31
+// after an emit, <= 49 after three more bins; the window holds n <= 53, so one early emit is
+// needed only when n > 47 before the fourth bin (never seen outside adversarial inputs).
+template <class Ctx, class Tab>
+CB_HD void encw_block16(EncWide& E, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+                        const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
+  const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (b == 3 && E.n > 47) encw_emit(E);
+      encw_op(E, (w[g] >> (8 * b)) & 0xffu, ctx, tab, n_ctx);
+    }
+    encw_emit(E);
+  }
+}
+
+// general path: any op kind, any count (stream heads up to the 16-byte boundary, tails,
+// blocks with terminate ops)
+template <class Ctx, class Tab>
+CB_HD void encw_general(EncWide& E, uint32_t o, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
+  if ((o >> 1) == kOpTrmCode) encw_trm(E, o & 1u);
+  else encw_op(E, o, ctx, tab, n_ctx);
+  encw_emit(E);
+}
+
+template <class Ctx, class Tab>
+CB_HD uint32_t decw_op(DecWide& D, uint32_t o, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
+  const bool is_ep = o >= kOpEpByte;
+  const uint32_t c = (o >> 1) < n_ctx ? (o >> 1) : n_ctx;
+  uint32_t st = ctx.load(c);
+  const uint32_t bin = decw_bin(D, is_ep, st, tab.row(st));
+  ctx.store(c, st);
+  return bin;
+}
+
+// 16 ops without a terminate op -> 16 bins packed one per byte (little-endian in r[0..3]).
+// f <= 31 after a refill and <= 49 before the fourth bin; decisions need f <= 53.
+template <class Ctx, class Tab>
+CB_HD void decw_block16(DecWide& D, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t r[4],
+                        const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
+  const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc |= decw_op(D, (w[g] >> (8 * b)) & 0xffu, ctx, tab, n_ctx) << (8 * b);
+    r[g] = acc;
+    decw_refill(D);
+  }
+}
+
+template <class Ctx, class Tab>
+CB_HD uint32_t decw_general(DecWide& D, uint32_t o, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
+  uint32_t bin;
+  if ((o >> 1) == kOpTrmCode) bin = decw_trm(D);
+  else bin = decw_op(D, o, ctx, tab, n_ctx);
+  decw_refill(D);
+  return bin;
+}
+
+}  // namespace cabac

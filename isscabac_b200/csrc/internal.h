@@ -10,6 +10,7 @@ extern thread_local char g_err[512];
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 size_t smem_limit();
+int sm_count();
 // out[0..n] = exclusive scan of in[0..n) (out[n] = total); scratch: cabac_compact_scratch_bytes(n)
 int exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, void* d_scratch, cudaStream_t st);
 }  // namespace isscabac_internal

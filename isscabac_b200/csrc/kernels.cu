@@ -20,6 +20,7 @@
 
 #include "../../include/isscabac.h"
 #include "cabac_lane.cuh"
+#include "cabac_wide.cuh"
 #include "internal.h"
 
 using namespace cabac;
@@ -326,6 +327,152 @@ __global__ void __launch_bounds__(NT) k_decode_ops(CodecParams P) {
 }
 
 // ---------------------------------------------------------------------------
+// wide-window kernels (cabac_wide.cuh): the hot path for the u8 op format
+// ---------------------------------------------------------------------------
+// One WARP per tile of 32 streams, NW warps per CTA (NW chosen by the host so that the tiles
+// spread evenly over the SMs: 65,536 streams = 2,048 tiles = 14 warps on each of 147 SMs).
+// Shared memory per CTA:
+//   tab  [129][32] uint2   fused state rows, replicated per lane: row st of lane l at
+//                          tab[st*32 + l] -> the 32 lanes always hit 32 distinct bank pairs
+//   ctx  [NW][n_ctx+1][32] u32   context state bytes, one word per (warp, context, lane);
+//                          slot n_ctx is the bypass slot (state 0x80)
+// Per lane and 16 ops: one 16-byte op load (next block prefetched), 16 branch-free bin steps,
+// 4 word emissions (encode) or refills (decode), one 16-byte store of the bins (decode).
+constexpr int WIDE_MAX_WARPS = 16;
+constexpr size_t WIDE_TAB_BYTES = (size_t)kNumRows * 32 * sizeof(uint2);
+
+struct WideRowTable {
+  uint2 r[kNumRows];
+  constexpr WideRowTable() : r{} {
+    for (uint32_t i = 0; i < kNumRows; ++i) r[i] = wide_row(i);
+  }
+};
+__constant__ WideRowTable c_wide_rows = WideRowTable();
+
+struct WCtx {
+  uint32_t* p;  // this lane's column of this warp's context block
+  __device__ __forceinline__ uint32_t load(uint32_t c) const { return p[c * 32]; }
+  __device__ __forceinline__ void store(uint32_t c, uint32_t v) const { p[c * 32] = v; }
+};
+struct WTab {
+  const uint2* p;  // this lane's column of the table
+  __device__ __forceinline__ uint2 row(uint32_t st) const { return p[st * 32]; }
+};
+
+// fills the table, initialises this warp's context block; returns false for lanes without a stream
+__device__ __forceinline__ bool wide_setup(const CodecParams& P, uint8_t* smem, uint32_t& s, WCtx& ctx, WTab& tab) {
+  uint2* t = reinterpret_cast<uint2*>(smem);
+  for (uint32_t i = threadIdx.x; i < kNumRows * 32; i += blockDim.x) t[i] = c_wide_rows.r[i >> 5];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t nw = blockDim.x >> 5;
+  s = (blockIdx.x * nw + warp) * 32 + lane;
+  const bool valid = s < P.n_streams;
+  uint32_t* c0 = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + (size_t)warp * (P.n_ctx + 1) * 32 + lane;
+  const uint8_t* init = P.ctx_init + (P.per_stream_init && valid ? (uint64_t)s * P.n_ctx : 0);
+  for (uint32_t c = 0; c < P.n_ctx; ++c) c0[c * 32] = init[c] & 127u;
+  c0[P.n_ctx * 32] = kEpState;
+  ctx.p = c0;
+  tab.p = t + lane;
+  __syncthreads();
+  return valid;
+}
+
+__global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_ops_wide(CodecParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint32_t s;
+  WCtx ctx;
+  WTab tab;
+  if (!wide_setup(P, smem, s, ctx, tab)) return;
+  const uint32_t n_ctx = P.n_ctx;
+  const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(P.ops) + o0;
+  const uint64_t n = o1 - o0;
+
+  EncWide E;
+  const uint32_t cap = (uint32_t)(P.slab_stride > 0xfffffffcull ? 0xfffffffcull : P.slab_stride);
+  encw_start(E, P.slab + (uint64_t)s * P.slab_stride, cap);
+
+  // head: general path up to the first 16-byte boundary of this lane's op array
+  uint64_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u;
+  if (head > n) head = n;
+  for (uint64_t i = 0; i < head; ++i) encw_general(E, p[i], ctx, tab, n_ctx);
+  p += head;
+  const uint64_t nblk = (n - head) >> 4;
+  const uint32_t tail = (uint32_t)((n - head) & 15u);
+  // body: 16 ops per load, next block prefetched while this one is coded
+  if (nblk) {
+    uint4 cur = __ldg(reinterpret_cast<const uint4*>(p));
+    for (uint64_t b = 0; b < nblk; ++b) {
+      uint4 nxt = cur;
+      if (b + 1 < nblk) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
+      if (block_has_trm(cur.x, cur.y, cur.z, cur.w)) {
+        for (int k = 0; k < 16; ++k) encw_general(E, p[k], ctx, tab, n_ctx);
+      } else {
+        encw_block16(E, cur.x, cur.y, cur.z, cur.w, ctx, tab, n_ctx);
+      }
+      cur = nxt;
+      p += 16;
+    }
+  }
+  for (uint32_t i = 0; i < tail; ++i) encw_general(E, p[i], ctx, tab, n_ctx);
+
+  const uint32_t len = encw_finish(E);
+  P.lengths[s] = len;
+  if ((E.overflow || len > cap) && P.overflow) atomicOr(P.overflow, 1u);
+}
+
+__global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_ops_wide(CodecParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint32_t s;
+  WCtx ctx;
+  WTab tab;
+  if (!wide_setup(P, smem, s, ctx, tab)) return;
+  const uint32_t n_ctx = P.n_ctx;
+  const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(P.ops) + o0;
+  uint8_t* q = P.bins + o0;
+  const uint64_t n = o1 - o0;
+  const uint64_t b0 = P.byte_off[s], b1 = P.byte_off[s + 1];
+
+  DecWide D;
+  decw_start(D, P.bytes + b0, (uint32_t)(b1 - b0));
+
+  uint64_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u;
+  if (head > n) head = n;
+  for (uint64_t i = 0; i < head; ++i) q[i] = (uint8_t)decw_general(D, p[i], ctx, tab, n_ctx);
+  p += head;
+  q += head;
+  const uint64_t nblk = (n - head) >> 4;
+  const uint32_t tail = (uint32_t)((n - head) & 15u);
+  const bool out_vec = (reinterpret_cast<uintptr_t>(q) & 15u) == 0;  // true whenever ops and bins share their alignment
+  if (nblk) {
+    uint4 cur = __ldg(reinterpret_cast<const uint4*>(p));
+    for (uint64_t b = 0; b < nblk; ++b) {
+      uint4 nxt = cur;
+      if (b + 1 < nblk) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
+      if (block_has_trm(cur.x, cur.y, cur.z, cur.w)) {
+        for (int k = 0; k < 16; ++k) q[k] = (uint8_t)decw_general(D, p[k], ctx, tab, n_ctx);
+      } else {
+        uint32_t r[4];
+        decw_block16(D, cur.x, cur.y, cur.z, cur.w, r, ctx, tab, n_ctx);
+        if (out_vec) {
+          *reinterpret_cast<uint4*>(q) = make_uint4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) q[k] = (uint8_t)(r[k >> 2] >> (8 * (k & 3)));
+        }
+      }
+      cur = nxt;
+      p += 16;
+      q += 16;
+    }
+  }
+  for (uint32_t i = 0; i < tail; ++i) q[i] = (uint8_t)decw_general(D, p[i], ctx, tab, n_ctx);
+
+  if (P.finish_ok) P.finish_ok[s] = (uint8_t)decw_finish(D);
+}
+
+// ---------------------------------------------------------------------------
 // device-wide exclusive scan (u32 -> u64), single pass, decoupled look-back
 // ---------------------------------------------------------------------------
 // Tiles of SCAN_TILE elements; tile order is taken from an atomic ticket so a tile only
@@ -467,6 +614,17 @@ int cuda_fail(cudaError_t e, const char* what) {
   return ISSCABAC_ERR_CUDA;
 }
 
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+      n = v;
+  }
+  return n > 0 ? n : 1;
+}
+
 size_t smem_limit() {
   static size_t lim = 0;
   if (!lim) {
@@ -506,6 +664,28 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   const size_t smem_ctx = tab_bytes + (size_t)P.n_ctx * NT * 4;
   const size_t lim = smem_limit();
   if (!lim) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
+  // hot path: u8 ops, context block of one warp fits shared memory next to the table
+  const size_t warp_ctx = ((size_t)P.n_ctx + 1) * 32 * 4;
+  if (op_width == 1 && P.n_ctx <= 125 && WIDE_TAB_BYTES + warp_ctx <= lim) {
+    const uint32_t sms = (uint32_t)sm_count();
+    const uint32_t tiles = (P.n_streams + 31) / 32;
+    // warps per CTA: spread the tiles evenly over the SMs (whole CTAs per SM), at most 16
+    uint32_t ctas_per_sm = (tiles + sms * WIDE_MAX_WARPS - 1) / (sms * WIDE_MAX_WARPS);
+    uint32_t nw = (tiles + sms * ctas_per_sm - 1) / (sms * ctas_per_sm);
+    const uint32_t nw_smem = (uint32_t)((lim - WIDE_TAB_BYTES) / warp_ctx);
+    if (nw > nw_smem) nw = nw_smem;
+    if (nw > WIDE_MAX_WARPS) nw = WIDE_MAX_WARPS;
+    if (nw < 1) nw = 1;
+    const size_t smem = WIDE_TAB_BYTES + warp_ctx * nw;
+    auto kernel = ENC ? k_encode_ops_wide : k_decode_ops_wide;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    }
+    kernel<<<(tiles + nw - 1) / nw, nw * 32, smem, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, ENC ? "k_encode_ops_wide" : "k_decode_ops_wide");
+  }
   // keep at least 2 CTAs per SM resident on the shared-memory path
   const bool use_smem = smem_ctx <= lim / 2;
   int rc;

@@ -105,3 +105,91 @@ int emul_decode_symbols(const int32_t* cfgv, const uint8_t* bytes, uint32_t len,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// wide-window formulation (cabac_wide.cuh), driven with the kernels' schedule:
+// general path up to the first 16-byte boundary of the op array, 16-op blocks, general tail
+// ---------------------------------------------------------------------------
+#include "../../isscabac_b200/csrc/cabac_wide.cuh"
+
+namespace {
+struct HostCtx {
+  uint32_t* p;
+  uint32_t load(uint32_t c) const { return p[c]; }
+  void store(uint32_t c, uint32_t v) const { p[c] = v; }
+};
+struct HostTab {
+  uint2 row(uint32_t st) const { return wide_row(st); }
+};
+inline uint32_t ld32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+}  // namespace
+
+extern "C" {
+
+int emul_encode_ops_wide(uint32_t n_streams, const uint64_t* op_off, const uint8_t* ops,
+                         const uint8_t* ctx_init, uint32_t n_ctx, int per_stream,
+                         uint8_t* slab, uint64_t stride, uint32_t* lens) {
+  std::vector<uint32_t> cs(n_ctx + 1);
+  int ovf = 0;
+  for (uint32_t s = 0; s < n_streams; ++s) {
+    for (uint32_t c = 0; c < n_ctx; ++c) cs[c] = ctx_init[(per_stream ? (uint64_t)s * n_ctx : 0) + c] & 127u;
+    cs[n_ctx] = kEpState;
+    HostCtx ctx{cs.data()};
+    HostTab tab;
+    EncWide E;
+    encw_start(E, slab + s * stride, (uint32_t)stride);
+    const uint8_t* p = ops + op_off[s];
+    uint64_t n = op_off[s + 1] - op_off[s], i = 0;
+    uint64_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+    if (head > n) head = n;
+    for (; i < head; ++i) encw_general(E, p[i], ctx, tab, n_ctx);
+    for (; i + 16 <= n; i += 16) {
+      uint32_t w0 = ld32(p + i), w1 = ld32(p + i + 4), w2 = ld32(p + i + 8), w3 = ld32(p + i + 12);
+      if (block_has_trm(w0, w1, w2, w3)) {
+        for (int k = 0; k < 16; ++k) encw_general(E, p[i + k], ctx, tab, n_ctx);
+      } else {
+        encw_block16(E, w0, w1, w2, w3, ctx, tab, n_ctx);
+      }
+    }
+    for (; i < n; ++i) encw_general(E, p[i], ctx, tab, n_ctx);
+    lens[s] = encw_finish(E);
+    ovf |= E.overflow;
+  }
+  return ovf;
+}
+
+int emul_decode_ops_wide(uint32_t n_streams, const uint64_t* byte_off, const uint8_t* bytes,
+                         const uint64_t* op_off, const uint8_t* ops,
+                         const uint8_t* ctx_init, uint32_t n_ctx, int per_stream,
+                         uint8_t* bins, uint8_t* ok) {
+  std::vector<uint32_t> cs(n_ctx + 1);
+  for (uint32_t s = 0; s < n_streams; ++s) {
+    for (uint32_t c = 0; c < n_ctx; ++c) cs[c] = ctx_init[(per_stream ? (uint64_t)s * n_ctx : 0) + c] & 127u;
+    cs[n_ctx] = kEpState;
+    HostCtx ctx{cs.data()};
+    HostTab tab;
+    DecWide D;
+    decw_start(D, bytes + byte_off[s], (uint32_t)(byte_off[s + 1] - byte_off[s]));
+    const uint8_t* p = ops + op_off[s];
+    uint8_t* q = bins + op_off[s];
+    uint64_t n = op_off[s + 1] - op_off[s], i = 0;
+    uint64_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+    if (head > n) head = n;
+    for (; i < head; ++i) q[i] = (uint8_t)decw_general(D, p[i], ctx, tab, n_ctx);
+    for (; i + 16 <= n; i += 16) {
+      uint32_t w0 = ld32(p + i), w1 = ld32(p + i + 4), w2 = ld32(p + i + 8), w3 = ld32(p + i + 12);
+      if (block_has_trm(w0, w1, w2, w3)) {
+        for (int k = 0; k < 16; ++k) q[i + k] = (uint8_t)decw_general(D, p[i + k], ctx, tab, n_ctx);
+      } else {
+        uint32_t r[4];
+        decw_block16(D, w0, w1, w2, w3, r, ctx, tab, n_ctx);
+        memcpy(q + i, r, 16);
+      }
+    }
+    for (; i < n; ++i) q[i] = (uint8_t)decw_general(D, p[i], ctx, tab, n_ctx);
+    ok[s] = (uint8_t)decw_finish(D);
+  }
+  return 0;
+}
+
+}  // extern "C"
