@@ -59,6 +59,41 @@ CB_HD uint32_t cb_funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
 #endif
 }
 
+// cb_perm without the selector sanitising of __byte_perm: every selector nibble must be 0..7
+CB_HD uint32_t cb_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+#else
+  return cb_perm(a, b, sel);
+#endif
+}
+// makes a value opaque to the optimiser (keeps an address in registers instead of having it
+// recomputed from the kernel parameters at every use)
+template <class T>
+CB_HD T* cb_keep(T* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+l"(p));
+#endif
+  return p;
+}
+CB_HD uint32_t cb_keep32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+r"(v));
+#endif
+  return v;
+}
+// acc + a * b with a 32x32 -> 64 bit product (one IMAD.WIDE)
+CB_HD uint64_t cb_mad_wide(uint32_t a, uint32_t b, uint64_t acc) {
+#if defined(__CUDA_ARCH__)
+  uint64_t d;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(acc));
+  return d;
+#else
+  return acc + (uint64_t)a * b;
+#endif
+}
 // upper 32 bits of ((hi:lo) << s), 0 <= s < 32
 CB_HD uint32_t cb_funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {
 #if defined(__CUDA_ARCH__)

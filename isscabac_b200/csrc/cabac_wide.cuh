@@ -51,16 +51,15 @@ struct EncWide {
   uint32_t range;
   int32_t n;          // bits shifted in since the last emitted word boundary (reference: 23 - bitsLeft, mod emission)
   uint32_t pend;      // last emitted word (numeric value), kept for carries
-  uint32_t wi;        // words emitted so far
+  uint32_t wi;        // words emitted so far (keeps counting past the capacity: the caller sees len > cap)
   uint32_t cap_words; // slab capacity in words
-  uint32_t overflow;
   uint32_t* out;      // slab row, 4-byte aligned
 };
 
 CB_HD void encw_start(EncWide& E, uint8_t* out, uint32_t cap_bytes) {  // Encoder.cpp:54-61
-  E.W = 0; E.range = 510; E.n = 0; E.pend = 0; E.wi = 0; E.overflow = 0;
+  E.W = 0; E.range = 510; E.n = 0; E.pend = 0; E.wi = 0;
   E.cap_words = cap_bytes >> 2;
-  E.out = reinterpret_cast<uint32_t*>(out);
+  E.out = cb_keep(reinterpret_cast<uint32_t*>(out));
 }
 
 // +1 into the words already emitted (replaces Encoder.cpp:394-404 and :76-87).  Rare: about
@@ -87,13 +86,13 @@ CB_HD_NOINLINE uint32_t encw_carry(uint32_t pend, uint32_t wi, uint32_t cap_word
 CB_HD void encw_emit(EncWide& E) {
   if (E.n >= 32) {
     const uint32_t sh = (uint32_t)E.n - 22u;  // 10..31
-    const uint64_t t = E.W >> sh;             // 33 bits: word + carry
-    E.W &= (1ull << sh) - 1ull;
+    const uint32_t lo = (uint32_t)E.W, hi = (uint32_t)(E.W >> 32);
+    const uint32_t word = cb_funnel_r(lo, hi, sh);
+    const uint32_t carry = hi >> sh;          // W < 2^(n+11): one carry bit above the word
+    E.W = lo & ~(0xffffffffu << sh);
     E.n -= 32;
-    if ((uint32_t)(t >> 32)) E.pend = encw_carry(E.pend, E.wi, E.cap_words, E.out);
-    const uint32_t word = (uint32_t)t;
+    if (carry) E.pend = encw_carry(E.pend, E.wi, E.cap_words, E.out);
     if (E.wi < E.cap_words) E.out[E.wi] = cb_bswap(word);
-    else E.overflow = 1;
     E.pend = word;
     E.wi++;
   }
@@ -102,17 +101,17 @@ CB_HD void encw_emit(EncWide& E) {
 // One bin, context-coded or bypass (see the file header).  st = state byte of the slot the
 // op addresses (kEpState for a bypass op), row = wide_row(st); returns the new state byte.
 CB_HD uint32_t encw_bin(EncWide& E, uint32_t o, bool is_ep, uint32_t st, uint2 row) {
-  const uint32_t lps = cb_perm(0, row.x, E.range >> 6);
+  const uint32_t lps = cb_prmt(0, row.x, E.range >> 6);   // selector 4..7 = row.x byte q (range is 256..510)
   const uint32_t rmps = E.range - lps;
   const uint32_t is_lps = (st ^ o) & 1u;
   const uint32_t x2 = is_ep ? E.range : 2u * rmps;
   const uint32_t rsel = is_lps ? lps : rmps;
   const int nn = cb_clz(rsel | 4u) - 23;     // min(clz(rsel)-23, 6): Encoder.cpp:482-492 incl. the state-63 row
   const int ns = is_ep ? 1 : nn;
-  E.W = (E.W + (uint64_t)(is_lps ? x2 : 0u)) << ns;
+  E.W = cb_mad_wide(is_lps, x2, E.W) << ns;  // one 32x32+64 multiply-add: select, add and carry in one
   E.range = is_ep ? E.range : (rsel << nn);
   E.n += ns;
-  return cb_perm(row.y, 0, is_lps | 0x4440u);
+  return cb_prmt(row.y, 0, is_lps | 0x4440u);
 }
 
 // encodeBinTrm, Encoder.cpp:326-367 (the only op that is a real branch; a handful per stream)
@@ -143,10 +142,8 @@ CB_HD uint32_t encw_finish(EncWide& E) {
   const uint32_t nb = (tb + 7u) >> 3;
   uint8_t* o8 = reinterpret_cast<uint8_t*>(E.out);
   const uint32_t base = 4u * E.wi;
-  for (uint32_t j = 0; j < nb; ++j) {
+  for (uint32_t j = 0; j < nb; ++j)
     if (base + j < 4u * E.cap_words) o8[base + j] = (uint8_t)(tail >> (56u - 8u * j));
-    else E.overflow = 1;
-  }
   return base + nb;
 }
 
@@ -157,32 +154,36 @@ CB_HD uint32_t encw_finish(EncWide& E) {
 // reference's 16+ bit `value` is hi >> 15.  f = number of low bits of R not yet filled;
 // with p = stream bytes loaded so far, f = 63 + s - 8p, which also gives the total shift
 // count s back for finish().
+// Input: aligned 32-bit words of the payload, two of them always in flight (cur, nxt) so that a
+// refill never waits for memory; PRMT with a per-stream selector turns {cur,nxt} into the
+// big-endian word of the next four stream bytes whatever the stream's byte alignment.
 struct DecWide {
   uint32_t lo, hi;
   uint32_t range;
   int32_t f;
   uint32_t p;            // stream bytes loaded into the window (3 mod 4 after start)
   uint32_t len;          // stream length in bytes
-  uint32_t cur;          // aligned little-endian word that holds stream byte p (and up to 3 earlier ones)
-  uint32_t sel;          // byte selector turning {cur,next} into the big-endian word of stream bytes p..p+3
-  const uint32_t* wp;    // address of the aligned word after `cur`
+  uint32_t cur, nxt;     // aligned little-endian words: cur holds stream byte p
+  uint32_t sel;          // byte selector for {cur,nxt} -> big-endian word of stream bytes p..p+3
+  uint32_t widx, wcnt;   // next aligned word to load / number of aligned words that hold stream bytes
+  const uint32_t* wbase; // aligned word that holds stream byte 3
   const uint8_t* in;     // first byte of the stream
 };
 
+CB_HD uint32_t decw_load(DecWide& D) {
+  const uint32_t v = D.widx < D.wcnt ? D.wbase[D.widx] : 0u;
+  D.widx++;
+  return v;
+}
+
 // big-endian word of stream bytes p..p+3, 0xFF past the end (BitstreamFile.cpp:153-158)
 CB_HD uint32_t decw_fetch(DecWide& D) {
-  uint32_t w;
-  if (D.p < D.len) {
-    // the second aligned word is only touched when the stream really extends into it
-    const uint32_t k = D.sel >> 12;                       // offset of byte p inside cur
-    const uint32_t nxt = (D.p + (4u - k) < D.len) ? *D.wp : 0u;
-    w = cb_perm(D.cur, nxt, D.sel);
-    D.cur = nxt;
-    D.wp++;
-    const uint32_t rem = D.len - D.p;
-    if (rem < 4u) w |= 0xffffffffu >> (8u * rem);
-  } else {
-    w = 0xffffffffu;
+  uint32_t w = cb_prmt(D.cur, D.nxt, D.sel);
+  D.cur = D.nxt;
+  D.nxt = decw_load(D);                       // needed two refills from now
+  if (D.p + 4u > D.len) {                     // only at the very end of a stream
+    const uint32_t rem = D.len > D.p ? D.len - D.p : 0u;
+    w = rem ? (w | (0xffffffffu >> (8u * rem))) : 0xffffffffu;
   }
   D.p += 4u;
   return w;
@@ -208,15 +209,18 @@ CB_HD void decw_start(DecWide& D, const uint8_t* in, uint32_t len) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(in) + 3u;
   const uint32_t k = (uint32_t)(a & 3u);
   D.sel = (k + 3u) | ((k + 2u) << 4) | ((k + 1u) << 8) | (k << 12);
-  const uint32_t* w0 = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  D.cur = (D.p < len) ? *w0 : 0u;
-  D.wp = w0 + 1;
+  D.wbase = cb_keep(reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3));
+  // aligned words from the one holding byte 3 to the one holding byte len-1
+  D.wcnt = len > 3 ? (uint32_t)(((a + (len - 4u)) >> 2) - (a >> 2)) + 1u : 0u;
+  D.widx = 0;
+  D.cur = decw_load(D);
+  D.nxt = decw_load(D);
   decw_refill(D);   // bytes 3..6
 }
 
 // One bin, context-coded or bypass; returns the bin, st is updated in place.
 CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, uint32_t& st, uint2 row) {
-  const uint32_t lps = cb_perm(0, row.x, D.range >> 6);
+  const uint32_t lps = cb_prmt(0, row.x, D.range >> 6);
   const uint32_t rmps = D.range - lps;
   const uint32_t x2 = is_ep ? D.range : 2u * rmps;
   const uint32_t scaled = x2 << 21;                        // reference: scaledRange << 15 (bypass: compare before the shift)
@@ -230,7 +234,7 @@ CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, uint32_t& st, uint2 row) {
   D.range = is_ep ? D.range : (rsel << nn);
   D.f += ns;
   const uint32_t bin = (st ^ is_lps) & 1u;
-  st = cb_perm(row.y, 0, is_lps | 0x4440u);
+  st = cb_prmt(row.y, 0, is_lps | 0x4440u);
   return bin;
 }
 

@@ -359,18 +359,23 @@ struct WTab {
   __device__ __forceinline__ uint2 row(uint32_t st) const { return p[st * 32]; }
 };
 
-// fills the table, initialises this warp's context block; returns false for lanes without a stream
-__device__ __forceinline__ bool wide_setup(const CodecParams& P, uint8_t* smem, uint32_t& s, WCtx& ctx, WTab& tab) {
+// fills the table, initialises this warp's context block; returns false for lanes without a stream.
+// The per-lane offsets are made opaque so that they stay in registers (the optimiser otherwise
+// recomputes them from threadIdx at every table access).
+__device__ __forceinline__ bool wide_setup(const CodecParams& P, uint8_t* smem, uint32_t& s, WCtx& ctx, WTab& tab,
+                                           uint32_t& n_ctx) {
   uint2* t = reinterpret_cast<uint2*>(smem);
   for (uint32_t i = threadIdx.x; i < kNumRows * 32; i += blockDim.x) t[i] = c_wide_rows.r[i >> 5];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5, lane = cb_keep32(threadIdx.x & 31);
   const uint32_t nw = blockDim.x >> 5;
+  n_ctx = cb_keep32(P.n_ctx);
   s = (blockIdx.x * nw + warp) * 32 + lane;
   const bool valid = s < P.n_streams;
-  uint32_t* c0 = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + (size_t)warp * (P.n_ctx + 1) * 32 + lane;
-  const uint8_t* init = P.ctx_init + (P.per_stream_init && valid ? (uint64_t)s * P.n_ctx : 0);
-  for (uint32_t c = 0; c < P.n_ctx; ++c) c0[c * 32] = init[c] & 127u;
-  c0[P.n_ctx * 32] = kEpState;
+  const uint32_t coff = cb_keep32(warp * (n_ctx + 1) * 32 + lane);
+  uint32_t* c0 = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + coff;
+  const uint8_t* init = P.ctx_init + (P.per_stream_init && valid ? (uint64_t)s * n_ctx : 0);
+  for (uint32_t c = 0; c < n_ctx; ++c) c0[c * 32] = init[c] & 127u;
+  c0[n_ctx * 32] = kEpState;
   ctx.p = c0;
   tab.p = t + lane;
   __syncthreads();
@@ -382,8 +387,8 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_ops_wide(CodecPa
   uint32_t s;
   WCtx ctx;
   WTab tab;
-  if (!wide_setup(P, smem, s, ctx, tab)) return;
-  const uint32_t n_ctx = P.n_ctx;
+  uint32_t n_ctx;
+  if (!wide_setup(P, smem, s, ctx, tab, n_ctx)) return;
   const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
   const uint8_t* p = reinterpret_cast<const uint8_t*>(P.ops) + o0;
   const uint64_t n = o1 - o0;
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_ops_wide(CodecPa
 
   const uint32_t len = encw_finish(E);
   P.lengths[s] = len;
-  if ((E.overflow || len > cap) && P.overflow) atomicOr(P.overflow, 1u);
+  if (len > cap && P.overflow) atomicOr(P.overflow, 1u);
 }
 
 __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_ops_wide(CodecParams P) {
@@ -426,8 +431,8 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_ops_wide(CodecPa
   uint32_t s;
   WCtx ctx;
   WTab tab;
-  if (!wide_setup(P, smem, s, ctx, tab)) return;
-  const uint32_t n_ctx = P.n_ctx;
+  uint32_t n_ctx;
+  if (!wide_setup(P, smem, s, ctx, tab, n_ctx)) return;
   const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
   const uint8_t* p = reinterpret_cast<const uint8_t*>(P.ops) + o0;
   uint8_t* q = P.bins + o0;

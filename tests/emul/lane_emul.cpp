@@ -153,7 +153,7 @@ int emul_encode_ops_wide(uint32_t n_streams, const uint64_t* op_off, const uint8
     }
     for (; i < n; ++i) encw_general(E, p[i], ctx, tab, n_ctx);
     lens[s] = encw_finish(E);
-    ovf |= E.overflow;
+    ovf |= lens[s] > stride;
   }
   return ovf;
 }

@@ -21,8 +21,8 @@ u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uin
 def emul():
     src = os.path.join(HERE, "emul", "lane_emul.cpp")
     so = os.path.join(HERE, "emul", "liblane_emul.so")
-    hdr = os.path.join(HERE, "..", "isscabac_b200", "csrc", "cabac_lane.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(HERE, "..", "isscabac_b200", "csrc", h) for h in ("cabac_lane.cuh", "cabac_wide.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src], check=True)
     L = C.CDLL(so)
     L.emul_symbols_to_ops.restype = C.c_uint64
