@@ -78,6 +78,16 @@ CB_HD T* cb_keep(T* p) {
 #endif
   return p;
 }
+// (a ^ b) & 1 as ONE three-input logic op
+CB_HD uint32_t cb_xor_and1(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, 1, 0x28;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+#else
+  return (a ^ b) & 1u;
+#endif
+}
 CB_HD uint32_t cb_keep32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
   asm volatile("" : "+r"(v));

@@ -50,8 +50,8 @@ struct EncWide {
   uint64_t W;         // 2 * (the reference's low), bits below the not-yet-emitted point
   uint32_t range;
   int32_t n;          // bits shifted in since the last emitted word boundary (reference: 23 - bitsLeft, mod emission)
-  uint32_t pend;      // last emitted word (numeric value), kept for carries
-  uint32_t wi;        // words emitted so far (keeps counting past the capacity: the caller sees len > cap)
+  uint32_t pend;      // last emitted word (numeric value): still in a register so that a carry is one add
+  uint32_t wi;        // words emitted so far, the pending one included (keeps counting past the capacity)
   uint32_t cap_words; // slab capacity in words
   uint32_t* out;      // slab row, 4-byte aligned
 };
@@ -62,27 +62,23 @@ CB_HD void encw_start(EncWide& E, uint8_t* out, uint32_t cap_bytes) {  // Encode
   E.out = cb_keep(reinterpret_cast<uint32_t*>(out));
 }
 
-// +1 into the words already emitted (replaces Encoder.cpp:394-404 and :76-87).  Rare: about
-// one carry per 1000 bins, and the walk past `pend` needs a 0xFFFFFFFF word.
-CB_HD_NOINLINE uint32_t encw_carry(uint32_t pend, uint32_t wi, uint32_t cap_words, uint32_t* out) {
-  pend += 1u;
-  if (wi == 0) return pend;
+// A carry out of a pending word that was 0xFFFFFFFF: +1 into the words already stored
+// (indices < wi-1).  Needs 32 one-bits in a row, i.e. practically never; replaces the
+// buffered-0xFF-run handling of Encoder.cpp:394-404 and :76-87.
+CB_HD_NOINLINE void encw_carry_walk(uint32_t wi, uint32_t cap_words, uint32_t* out) {
   volatile uint32_t* o = out;
-  if (wi - 1 < cap_words) o[wi - 1] = cb_bswap(pend);
-  if (pend == 0) {
-    for (int64_t i = (int64_t)wi - 2; i >= 0; --i) {
-      if ((uint64_t)i >= cap_words) continue;
-      uint32_t v = cb_bswap(o[i]) + 1u;
-      o[i] = cb_bswap(v);
-      if (v != 0) break;
-    }
+  for (int64_t i = (int64_t)wi - 2; i >= 0; --i) {
+    if ((uint64_t)i >= cap_words) continue;
+    uint32_t v = cb_bswap(o[i]) + 1u;
+    o[i] = cb_bswap(v);
+    if (v != 0) break;
   }
-  return pend;
 }
 
 // Move one 32-bit word out when at least 32 settled bits are waiting.  Emits the bits
 // [n-23, n+8] of the reference's low: the four bytes the reference would hand to
-// writeOut() over its next four calls.
+// writeOut() over its next four calls.  The word stays in `pend`; what is stored is the
+// PREVIOUS word, after the carry of this emission has been added to it.
 CB_HD void encw_emit(EncWide& E) {
   if (E.n >= 32) {
     const uint32_t sh = (uint32_t)E.n - 22u;  // 10..31
@@ -91,8 +87,9 @@ CB_HD void encw_emit(EncWide& E) {
     const uint32_t carry = hi >> sh;          // W < 2^(n+11): one carry bit above the word
     E.W = lo & ~(0xffffffffu << sh);
     E.n -= 32;
-    if (carry) E.pend = encw_carry(E.pend, E.wi, E.cap_words, E.out);
-    if (E.wi < E.cap_words) E.out[E.wi] = cb_bswap(word);
+    const uint32_t prev = E.pend + carry;
+    if (carry > prev) encw_carry_walk(E.wi, E.cap_words, E.out);   // prev wrapped to 0
+    if (E.wi - 1u < E.cap_words) E.out[E.wi - 1u] = cb_bswap(prev);  // false for wi == 0: nothing pending yet
     E.pend = word;
     E.wi++;
   }
@@ -103,12 +100,14 @@ CB_HD void encw_emit(EncWide& E) {
 CB_HD uint32_t encw_bin(EncWide& E, uint32_t o, bool is_ep, uint32_t st, uint2 row) {
   const uint32_t lps = cb_prmt(0, row.x, E.range >> 6);   // selector 4..7 = row.x byte q (range is 256..510)
   const uint32_t rmps = E.range - lps;
-  const uint32_t is_lps = (st ^ o) & 1u;
+  const uint32_t is_lps = cb_xor_and1(st, o);
   const uint32_t x2 = is_ep ? E.range : 2u * rmps;
   const uint32_t rsel = is_lps ? lps : rmps;
   const int nn = cb_clz(rsel | 4u) - 23;     // min(clz(rsel)-23, 6): Encoder.cpp:482-492 incl. the state-63 row
   const int ns = is_ep ? 1 : nn;
-  E.W = cb_mad_wide(is_lps, x2, E.W) << ns;  // one 32x32+64 multiply-add: select, add and carry in one
+  uint64_t W = E.W;
+  if (is_lps) W += x2;                       // predicated 64-bit add
+  E.W = W << ns;
   E.range = is_ep ? E.range : (rsel << nn);
   E.n += ns;
   return cb_prmt(row.y, 0, is_lps | 0x4440u);
@@ -132,10 +131,12 @@ CB_HD uint32_t encw_finish(EncWide& E) {
   encw_trm(E, 1);
   encw_emit(E);
   const uint32_t cbit = (uint32_t)E.n + 10u;            // bit 9+n of low = the carry finish() tests (:76)
-  if ((E.W >> cbit) & 1ull) {
-    E.pend = encw_carry(E.pend, E.wi, E.cap_words, E.out);
-    E.W &= ~(1ull << cbit);
-  }
+  const uint32_t carry = (uint32_t)(E.W >> cbit) & 1u;
+  E.W &= ~(1ull << cbit);
+  // the pending word goes out now, with the final carry
+  const uint32_t prev = E.pend + carry;
+  if (carry > prev) encw_carry_walk(E.wi, E.cap_words, E.out);
+  if (E.wi - 1u < E.cap_words) E.out[E.wi - 1u] = cb_bswap(prev);
   // write(low >> 8, 24 - bitsLeft) = n+1 bits, the stop bit, zero padding (:100-104)
   const uint32_t tb = (uint32_t)E.n + 2u;               // <= 33
   const uint64_t tail = ((((E.W >> 9) & ((1ull << (E.n + 1)) - 1ull)) << 1) | 1ull) << (64u - tb);
@@ -267,7 +268,6 @@ CB_HD uint32_t decw_finish(DecWide& D) {
 // op blocks: the schedule both kernels and the host emulation follow
 // ---------------------------------------------------------------------------
 // u8 op format: op = code << 1 | bin, code 0..124 context, 125 terminate, 126 bypass.
-constexpr uint32_t kOpEpByte = 126u << 1;   // op bytes >= this are bypass ops
 constexpr uint32_t kOpTrmCode = 125u;
 
 // true when one of the 16 op bytes of a block may be a terminate op (false positives are
@@ -283,13 +283,13 @@ CB_HD bool block_has_trm(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
 }
 
 // Context storage as the kernels see it: slot c of this lane, c == n_ctx is the bypass slot.
-// Tab::row(st) returns wide_row(st).
+// Tab::row(st) returns wide_row(st).  `code` = op >> 1, `ob` = any word whose bit 0 is the bin.
 template <class Ctx, class Tab>
-CB_HD void encw_op(EncWide& E, uint32_t o, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
-  const bool is_ep = o >= kOpEpByte;
-  const uint32_t c = (o >> 1) < n_ctx ? (o >> 1) : n_ctx;
+CB_HD void encw_op(EncWide& E, uint32_t code, uint32_t ob, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
+  const bool is_ep = code > kOpTrmCode;
+  const uint32_t c = code < n_ctx ? code : n_ctx;
   const uint32_t st = ctx.load(c);
-  ctx.store(c, encw_bin(E, o, is_ep, st, tab.row(st)));
+  ctx.store(c, encw_bin(E, ob, is_ep, st, tab.row(st)));
 }
 
 // 16 ops without a terminate op: 4 x (4 bins, emit).  Worst case 6 bits per bin: n <= 31
@@ -301,10 +301,11 @@ CB_HD void encw_block16(EncWide& E, uint32_t w0, uint32_t w1, uint32_t w2, uint3
   const uint32_t w[4] = {w0, w1, w2, w3};
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
+    const uint32_t codes = (w[g] >> 1) & 0x7f7f7f7fu;   // the four op codes, one per byte
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       if (b == 3 && E.n > 47) encw_emit(E);
-      encw_op(E, (w[g] >> (8 * b)) & 0xffu, ctx, tab, n_ctx);
+      encw_op(E, cb_prmt(codes, 0, 0x4440u + b), w[g] >> (8 * b), ctx, tab, n_ctx);
     }
     encw_emit(E);
   }
@@ -315,14 +316,14 @@ CB_HD void encw_block16(EncWide& E, uint32_t w0, uint32_t w1, uint32_t w2, uint3
 template <class Ctx, class Tab>
 CB_HD void encw_general(EncWide& E, uint32_t o, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
   if ((o >> 1) == kOpTrmCode) encw_trm(E, o & 1u);
-  else encw_op(E, o, ctx, tab, n_ctx);
+  else encw_op(E, o >> 1, o, ctx, tab, n_ctx);
   encw_emit(E);
 }
 
 template <class Ctx, class Tab>
-CB_HD uint32_t decw_op(DecWide& D, uint32_t o, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
-  const bool is_ep = o >= kOpEpByte;
-  const uint32_t c = (o >> 1) < n_ctx ? (o >> 1) : n_ctx;
+CB_HD uint32_t decw_op(DecWide& D, uint32_t code, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
+  const bool is_ep = code > kOpTrmCode;
+  const uint32_t c = code < n_ctx ? code : n_ctx;
   uint32_t st = ctx.load(c);
   const uint32_t bin = decw_bin(D, is_ep, st, tab.row(st));
   ctx.store(c, st);
@@ -337,9 +338,10 @@ CB_HD void decw_block16(DecWide& D, uint32_t w0, uint32_t w1, uint32_t w2, uint3
   const uint32_t w[4] = {w0, w1, w2, w3};
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
+    const uint32_t codes = (w[g] >> 1) & 0x7f7f7f7fu;
     uint32_t acc = 0;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc |= decw_op(D, (w[g] >> (8 * b)) & 0xffu, ctx, tab, n_ctx) << (8 * b);
+    for (int b = 0; b < 4; ++b) acc |= decw_op(D, cb_prmt(codes, 0, 0x4440u + b), ctx, tab, n_ctx) << (8 * b);
     r[g] = acc;
     decw_refill(D);
   }
@@ -349,7 +351,7 @@ template <class Ctx, class Tab>
 CB_HD uint32_t decw_general(DecWide& D, uint32_t o, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
   uint32_t bin;
   if ((o >> 1) == kOpTrmCode) bin = decw_trm(D);
-  else bin = decw_op(D, o, ctx, tab, n_ctx);
+  else bin = decw_op(D, o >> 1, ctx, tab, n_ctx);
   decw_refill(D);
   return bin;
 }
