@@ -78,6 +78,14 @@ CB_HD T* cb_keep(T* p) {
 #endif
   return p;
 }
+// 32-bit store to global memory (keeps the STG form when the pointer came through cb_keep)
+CB_HD void cb_stg32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+  *p = v;
+#endif
+}
 // (a ^ b) & 1 as ONE three-input logic op
 CB_HD uint32_t cb_xor_and1(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)

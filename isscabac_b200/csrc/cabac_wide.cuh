@@ -51,28 +51,36 @@ struct EncWide {
   uint32_t range;
   int32_t n;          // bits shifted in since the last emitted word boundary (reference: 23 - bitsLeft, mod emission)
   uint32_t pend;      // last emitted word (numeric value): still in a register so that a carry is one add
-  uint32_t wi;        // words emitted so far, the pending one included (keeps counting past the capacity)
+  uint32_t wp;        // index of the pending word = words emitted - 1 (0xffffffff before the first one);
+                      // keeps counting past the capacity so that the caller sees len > cap
   uint32_t cap_words; // slab capacity in words
-  uint32_t* out;      // slab row, 4-byte aligned
+  uint32_t* slot;     // where the pending word will be stored (row + wp)
 };
 
 CB_HD void encw_start(EncWide& E, uint8_t* out, uint32_t cap_bytes) {  // Encoder.cpp:54-61
-  E.W = 0; E.range = 510; E.n = 0; E.pend = 0; E.wi = 0;
+  E.W = 0; E.range = 510; E.n = 0; E.pend = 0; E.wp = 0xffffffffu;
   E.cap_words = cap_bytes >> 2;
-  E.out = cb_keep(reinterpret_cast<uint32_t*>(out));
+  E.slot = cb_keep(reinterpret_cast<uint32_t*>(out) - 1);
 }
 
 // A carry out of a pending word that was 0xFFFFFFFF: +1 into the words already stored
-// (indices < wi-1).  Needs 32 one-bits in a row, i.e. practically never; replaces the
-// buffered-0xFF-run handling of Encoder.cpp:394-404 and :76-87.
-CB_HD_NOINLINE void encw_carry_walk(uint32_t wi, uint32_t cap_words, uint32_t* out) {
-  volatile uint32_t* o = out;
-  for (int64_t i = (int64_t)wi - 2; i >= 0; --i) {
+// (those before the pending one).  Needs 32 one-bits in a row, i.e. practically never;
+// replaces the buffered-0xFF-run handling of Encoder.cpp:394-404 and :76-87.
+CB_HD_NOINLINE void encw_carry_walk(uint32_t wp, uint32_t cap_words, uint32_t* slot) {
+  volatile uint32_t* o = slot - wp;   // row start
+  for (int64_t i = (int64_t)wp - 1; i >= 0; --i) {
     if ((uint64_t)i >= cap_words) continue;
     uint32_t v = cb_bswap(o[i]) + 1u;
     o[i] = cb_bswap(v);
     if (v != 0) break;
   }
+}
+
+// the pending word leaves for memory, `carry` (0/1) added
+CB_HD void encw_retire(EncWide& E, uint32_t carry) {
+  const uint32_t prev = E.pend + carry;
+  if (carry > prev && E.wp != 0xffffffffu) encw_carry_walk(E.wp, E.cap_words, E.slot);   // prev wrapped to 0
+  if (E.wp < E.cap_words) cb_stg32(E.slot, cb_bswap(prev));   // false while nothing is pending (wp = 0xffffffff)
 }
 
 // Move one 32-bit word out when at least 32 settled bits are waiting.  Emits the bits
@@ -87,11 +95,10 @@ CB_HD void encw_emit(EncWide& E) {
     const uint32_t carry = hi >> sh;          // W < 2^(n+11): one carry bit above the word
     E.W = lo & ~(0xffffffffu << sh);
     E.n -= 32;
-    const uint32_t prev = E.pend + carry;
-    if (carry > prev) encw_carry_walk(E.wi, E.cap_words, E.out);   // prev wrapped to 0
-    if (E.wi - 1u < E.cap_words) E.out[E.wi - 1u] = cb_bswap(prev);  // false for wi == 0: nothing pending yet
+    encw_retire(E, carry);
     E.pend = word;
-    E.wi++;
+    E.wp++;
+    E.slot++;
   }
 }
 
@@ -133,18 +140,15 @@ CB_HD uint32_t encw_finish(EncWide& E) {
   const uint32_t cbit = (uint32_t)E.n + 10u;            // bit 9+n of low = the carry finish() tests (:76)
   const uint32_t carry = (uint32_t)(E.W >> cbit) & 1u;
   E.W &= ~(1ull << cbit);
-  // the pending word goes out now, with the final carry
-  const uint32_t prev = E.pend + carry;
-  if (carry > prev) encw_carry_walk(E.wi, E.cap_words, E.out);
-  if (E.wi - 1u < E.cap_words) E.out[E.wi - 1u] = cb_bswap(prev);
+  encw_retire(E, carry);                                // the pending word goes out now, with the final carry
   // write(low >> 8, 24 - bitsLeft) = n+1 bits, the stop bit, zero padding (:100-104)
   const uint32_t tb = (uint32_t)E.n + 2u;               // <= 33
   const uint64_t tail = ((((E.W >> 9) & ((1ull << (E.n + 1)) - 1ull)) << 1) | 1ull) << (64u - tb);
   const uint32_t nb = (tb + 7u) >> 3;
-  uint8_t* o8 = reinterpret_cast<uint8_t*>(E.out);
-  const uint32_t base = 4u * E.wi;
+  uint8_t* o8 = reinterpret_cast<uint8_t*>(E.slot + 1);
+  const uint32_t base = 4u * (E.wp + 1u);
   for (uint32_t j = 0; j < nb; ++j)
-    if (base + j < 4u * E.cap_words) o8[base + j] = (uint8_t)(tail >> (56u - 8u * j));
+    if (base + j < 4u * E.cap_words) o8[j] = (uint8_t)(tail >> (56u - 8u * j));
   return base + nb;
 }
 
@@ -270,15 +274,18 @@ CB_HD uint32_t decw_finish(DecWide& D) {
 // u8 op format: op = code << 1 | bin, code 0..124 context, 125 terminate, 126 bypass.
 constexpr uint32_t kOpTrmCode = 125u;
 
-// true when one of the 16 op bytes of a block may be a terminate op (false positives are
+// the four op codes of a word of ops, one per byte
+CB_HD uint32_t op_codes4(uint32_t w) { return (w >> 1) & 0x7f7f7f7fu; }
+
+// true when one of the 16 op codes of a block may be a terminate op (false positives are
 // possible -- never false negatives -- and only send the block down the general path)
-CB_HD bool block_has_trm(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+CB_HD bool block_has_trm(const uint32_t cw[4]) {
   // code bytes are <= 0x7f, so "byte == 0" <=> borrow into bit 7 of (x - 0x01): exact for the
   // lowest zero byte, possibly a false positive above it
-  const uint32_t h0 = (((w0 >> 1) & 0x7f7f7f7fu) ^ 0x7d7d7d7du) - 0x01010101u;
-  const uint32_t h1 = (((w1 >> 1) & 0x7f7f7f7fu) ^ 0x7d7d7d7du) - 0x01010101u;
-  const uint32_t h2 = (((w2 >> 1) & 0x7f7f7f7fu) ^ 0x7d7d7d7du) - 0x01010101u;
-  const uint32_t h3 = (((w3 >> 1) & 0x7f7f7f7fu) ^ 0x7d7d7d7du) - 0x01010101u;
+  const uint32_t h0 = (cw[0] ^ 0x7d7d7d7du) - 0x01010101u;
+  const uint32_t h1 = (cw[1] ^ 0x7d7d7d7du) - 0x01010101u;
+  const uint32_t h2 = (cw[2] ^ 0x7d7d7d7du) - 0x01010101u;
+  const uint32_t h3 = (cw[3] ^ 0x7d7d7d7du) - 0x01010101u;
   return ((h0 | h1 | h2 | h3) & 0x80808080u) != 0u;
 }
 
@@ -296,12 +303,11 @@ CB_HD void encw_op(EncWide& E, uint32_t code, uint32_t ob, const Ctx& ctx, const
 // after an emit, <= 49 after three more bins; the window holds n <= 53, so one early emit is
 // needed only when n > 47 before the fourth bin (never seen outside adversarial inputs).
 template <class Ctx, class Tab>
-CB_HD void encw_block16(EncWide& E, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+CB_HD void encw_block16(EncWide& E, const uint32_t w[4], const uint32_t cw[4],
                         const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
-  const uint32_t w[4] = {w0, w1, w2, w3};
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const uint32_t codes = (w[g] >> 1) & 0x7f7f7f7fu;   // the four op codes, one per byte
+    const uint32_t codes = cw[g];   // the four op codes, one per byte
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       if (b == 3 && E.n > 47) encw_emit(E);
@@ -333,12 +339,11 @@ CB_HD uint32_t decw_op(DecWide& D, uint32_t code, const Ctx& ctx, const Tab& tab
 // 16 ops without a terminate op -> 16 bins packed one per byte (little-endian in r[0..3]).
 // f <= 31 after a refill and <= 49 before the fourth bin; decisions need f <= 53.
 template <class Ctx, class Tab>
-CB_HD void decw_block16(DecWide& D, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t r[4],
+CB_HD void decw_block16(DecWide& D, const uint32_t cw[4], uint32_t r[4],
                         const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
-  const uint32_t w[4] = {w0, w1, w2, w3};
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const uint32_t codes = (w[g] >> 1) & 0x7f7f7f7fu;
+    const uint32_t codes = cw[g];
     uint32_t acc = 0;
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc |= decw_op(D, cb_prmt(codes, 0, 0x4440u + b), ctx, tab, n_ctx) << (8 * b);

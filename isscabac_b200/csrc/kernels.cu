@@ -407,13 +407,15 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_ops_wide(CodecPa
   // body: 16 ops per load, next block prefetched while this one is coded
   if (nblk) {
     uint4 cur = __ldg(reinterpret_cast<const uint4*>(p));
-    for (uint64_t b = 0; b < nblk; ++b) {
+    for (uint64_t b = nblk; b != 0; --b) {
       uint4 nxt = cur;
-      if (b + 1 < nblk) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
-      if (block_has_trm(cur.x, cur.y, cur.z, cur.w)) {
+      if (b > 1) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
+      const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+      const uint32_t cw[4] = {op_codes4(cur.x), op_codes4(cur.y), op_codes4(cur.z), op_codes4(cur.w)};
+      if (block_has_trm(cw)) {
         for (int k = 0; k < 16; ++k) encw_general(E, p[k], ctx, tab, n_ctx);
       } else {
-        encw_block16(E, cur.x, cur.y, cur.z, cur.w, ctx, tab, n_ctx);
+        encw_block16(E, w, cw, ctx, tab, n_ctx);
       }
       cur = nxt;
       p += 16;
@@ -452,14 +454,15 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_ops_wide(CodecPa
   const bool out_vec = (reinterpret_cast<uintptr_t>(q) & 15u) == 0;  // true whenever ops and bins share their alignment
   if (nblk) {
     uint4 cur = __ldg(reinterpret_cast<const uint4*>(p));
-    for (uint64_t b = 0; b < nblk; ++b) {
+    for (uint64_t b = nblk; b != 0; --b) {
       uint4 nxt = cur;
-      if (b + 1 < nblk) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
-      if (block_has_trm(cur.x, cur.y, cur.z, cur.w)) {
+      if (b > 1) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
+      const uint32_t cw[4] = {op_codes4(cur.x), op_codes4(cur.y), op_codes4(cur.z), op_codes4(cur.w)};
+      if (block_has_trm(cw)) {
         for (int k = 0; k < 16; ++k) q[k] = (uint8_t)decw_general(D, p[k], ctx, tab, n_ctx);
       } else {
         uint32_t r[4];
-        decw_block16(D, cur.x, cur.y, cur.z, cur.w, r, ctx, tab, n_ctx);
+        decw_block16(D, cw, r, ctx, tab, n_ctx);
         if (out_vec) {
           *reinterpret_cast<uint4*>(q) = make_uint4(r[0], r[1], r[2], r[3]);
         } else {

@@ -144,11 +144,12 @@ int emul_encode_ops_wide(uint32_t n_streams, const uint64_t* op_off, const uint8
     if (head > n) head = n;
     for (; i < head; ++i) encw_general(E, p[i], ctx, tab, n_ctx);
     for (; i + 16 <= n; i += 16) {
-      uint32_t w0 = ld32(p + i), w1 = ld32(p + i + 4), w2 = ld32(p + i + 8), w3 = ld32(p + i + 12);
-      if (block_has_trm(w0, w1, w2, w3)) {
+      const uint32_t w[4] = {ld32(p + i), ld32(p + i + 4), ld32(p + i + 8), ld32(p + i + 12)};
+      const uint32_t cw[4] = {op_codes4(w[0]), op_codes4(w[1]), op_codes4(w[2]), op_codes4(w[3])};
+      if (block_has_trm(cw)) {
         for (int k = 0; k < 16; ++k) encw_general(E, p[i + k], ctx, tab, n_ctx);
       } else {
-        encw_block16(E, w0, w1, w2, w3, ctx, tab, n_ctx);
+        encw_block16(E, w, cw, ctx, tab, n_ctx);
       }
     }
     for (; i < n; ++i) encw_general(E, p[i], ctx, tab, n_ctx);
@@ -177,12 +178,13 @@ int emul_decode_ops_wide(uint32_t n_streams, const uint64_t* byte_off, const uin
     if (head > n) head = n;
     for (; i < head; ++i) q[i] = (uint8_t)decw_general(D, p[i], ctx, tab, n_ctx);
     for (; i + 16 <= n; i += 16) {
-      uint32_t w0 = ld32(p + i), w1 = ld32(p + i + 4), w2 = ld32(p + i + 8), w3 = ld32(p + i + 12);
-      if (block_has_trm(w0, w1, w2, w3)) {
+      const uint32_t cw[4] = {op_codes4(ld32(p + i)), op_codes4(ld32(p + i + 4)), op_codes4(ld32(p + i + 8)),
+                              op_codes4(ld32(p + i + 12))};
+      if (block_has_trm(cw)) {
         for (int k = 0; k < 16; ++k) q[i + k] = (uint8_t)decw_general(D, p[i + k], ctx, tab, n_ctx);
       } else {
         uint32_t r[4];
-        decw_block16(D, w0, w1, w2, w3, r, ctx, tab, n_ctx);
+        decw_block16(D, cw, r, ctx, tab, n_ctx);
         memcpy(q + i, r, 16);
       }
     }
@@ -191,5 +193,8 @@ int emul_decode_ops_wide(uint32_t n_streams, const uint64_t* byte_off, const uin
   }
   return 0;
 }
+
+// direct hook for the (practically unreachable) carry walk past a 0xFFFFFFFF pending word
+void emul_carry_walk(uint32_t* row, uint32_t wp, uint32_t cap_words) { encw_carry_walk(wp, cap_words, row + wp); }
 
 }  // extern "C"

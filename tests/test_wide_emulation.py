@@ -182,3 +182,16 @@ def test_wide_decoder_reads_ff_past_the_end(emul):
         want, _ = O.decode_ops(data if cut else np.zeros(1, np.uint8), np.array([0, cut], dtype=np.uint64), ops, off, ci, n_threads=1)
         got, _ = wide_decode(emul, data, [0, cut], ops, off, ci, pay_misalign=cut % 4)
         assert (got == want).all(), cut
+
+
+def test_wide_carry_walk(emul):
+    """The carry past a 0xFFFFFFFF pending word (needs 32 one-bits in a row at a word boundary, so
+    no random stream reaches it): +1 ripples through the big-endian words already stored."""
+    def be(words):
+        return np.array(words, dtype=">u4").view(np.uint8).view("<u4").copy()
+    row = be([0x12345678, 0x00FFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xAAAAAAAA])
+    emul.emul_carry_walk(p(row, u32p), C.c_uint32(4), C.c_uint32(16))      # pending word index 4: words 0..3 are stored
+    assert list(row.view(np.uint8).view(">u4")) == [0x12345678, 0x01000000, 0, 0, 0xAAAAAAAA]
+    row = be([0xFFFFFFFF, 0xFFFFFFFF, 7])
+    emul.emul_carry_walk(p(row, u32p), C.c_uint32(2), C.c_uint32(1))       # capacity 1 word: word 1 is not in memory
+    assert list(row.view(np.uint8).view(">u4")) == [0, 0xFFFFFFFF, 7]
