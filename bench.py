@@ -40,7 +40,7 @@ P_EP = 0.25
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=65536, help="streams per GPU")
@@ -99,6 +99,8 @@ def gen_ops_device(torch, seed, n_streams, n_bins, device):
 # clocks
 # ---------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms in the background; every row is
+    stamped on arrival so that only the rows inside the timed region are summarised."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -108,7 +110,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -116,7 +118,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
 
     def stop(self):
         if self.proc:
@@ -125,21 +132,28 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+
+    def summary(self, t0, t1):
+        sm, mx, pw, reasons, n_all = [], 0, [], set(), 0
+        for ts, r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
+                continue
+            n_all += 1
+            if not (t0 - 0.02 <= ts <= t1 + 0.05):
                 continue
             try:
                 sm.append(float(f[0]))
                 mx = max(mx, float(f[1]))
+                pw.append(float(f[2]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons),
+                "samples": len(sm), "samples_total": n_all}
 
 
 # ---------------------------------------------------------------------------------------
@@ -253,6 +267,9 @@ def run_b200(a):
             e[3].record()
             marks.append(e)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(a.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -262,21 +279,26 @@ def run_b200(a):
     assert bool(((ops & 1) == bins).all().item()), "decoded bins differ from the encoded ones"
     payload_bytes = int(byte_off[-1].item())
 
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.wait_first()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t_start, t_end = ev(), ev()
+    wall0 = time.time()
     t_start.record()
     for _ in range(a.steps):
         step(record=True)
     t_end.record()
     torch.cuda.synchronize()
+    wall1 = time.time()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        time.sleep(0.05)
+        sampler.stop()
+        clocks = sampler.summary(wall0, wall1)
     ms = t_start.elapsed_time(t_end)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -359,9 +381,21 @@ def run_b200(a):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     enc_bytes = total_bins + payload_bytes + 4 * S          # 1 B/bin in + payload out + 4 B/stream
     dec_bytes = total_bins + payload_bytes + total_bins + S  # kinds in + payload in + 1 B/bin out + flag
-    dom = "k_encode_ops" if ms_enc >= ms_dec else "k_decode_ops"
-    dom_ms, dom_bytes = (ms_enc, enc_bytes) if dom == "k_encode_ops" else (ms_dec, dec_bytes)
+    dom = "k_encode_ops_wide" if ms_enc >= ms_dec else "k_decode_ops_wide"
+    dom_ms, dom_bytes = (ms_enc, enc_bytes) if dom == "k_encode_ops_wide" else (ms_dec, dec_bytes)
     ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+    # DRAM traffic of that kernel per launch, from the committed ncu --set full capture
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)[dom]
+        traffic = float(tj["dram_bytes_per_launch"])
+        traffic_src = tj["source"]
+        if int(tj["bins_per_launch"]) != total_bins:   # captured at another size: bytes scale with the bins
+            traffic *= total_bins / float(tj["bins_per_launch"])
+            traffic_src += f" (scaled from {tj['bins_per_launch']} bins per launch)"
+    except Exception:
+        pass
     # integer-issue roofline (the binding one): algorithmic int32 ops
     sm, _, _ = (torch.cuda.get_device_properties(dev).multi_processor_count, 0, 0)
     f_sm = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
@@ -384,13 +418,14 @@ def run_b200(a):
                    "step": "encode + length scan + compaction + decode" + (" + all-gather of lengths" if world > 1 else "")},
         "encode_gbins": total_bins * world / (ms_enc * 1e-3) / 1e9,
         "decode_gbins": total_bins * world / (ms_dec * 1e-3) / 1e9,
-        "kernel_ms": {"k_encode_ops": ms_enc, "scan+k_compact_copy": ms_cmp, "k_decode_ops": ms_dec},
+        "kernel_ms": {"k_encode_ops_wide": ms_enc, "k_scan_init+k_scan_u32_u64+k_compact_copy": ms_cmp, "k_decode_ops_wide": ms_dec},
         "payload_bytes_per_gpu": payload_bytes, "bits_per_bin": 8.0 * payload_bytes / total_bins,
         "gpu_launches": 5 * a.steps,
         "clocks": clocks,
         "e2e": e2e,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
                      "note": "the path is integer-issue bound, not HBM bound: see roofline_int"},
         "roofline_int": roof_int,
         "cpu_baseline": cpu,
