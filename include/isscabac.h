@@ -155,6 +155,23 @@ int cabac_decode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const u
                          const uint8_t* d_ctx_init, uint32_t n_ctx, int per_stream_init,
                          void* d_symbols, int sym_width, uint8_t* d_finish_ok, void* stream);
 
+/* ---- ISS context-init statistics (ISS/+coder/cabacInitContextModel.m:15-129) -- */
+/* Device-side reduction of the per-context zero counts over the binarised symbols of every
+ * stream (ISS layout: column-major with cfg->rows rows; the up neighbour of a symbol is the
+ * previous one of the same column).  Streams are pooled in groups of streams_per_group
+ * consecutive streams (1 = statistics per stream; the 20 column streams of one matrix = 20).
+ * d_counters: n_groups * cabac_iss_num_counters(Nlbp) u64, zeroed by the call. */
+int cabac_iss_num_counters(int Nlbp);
+int cabac_iss_ctx_stats(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_sym_off,
+                        const void* d_symbols, int sym_width, uint64_t n_symbols, uint32_t streams_per_group,
+                        uint64_t* d_counters, void* stream);
+/* Host: counters -> p(0) per context (7*Nlbp+2 per group), the uint8 side information
+ * uint8(p*255) of cabacEncode.m:30 and the context state bytes initByProb derives from
+ * q/255 (cabacEncode.m:31, CABAC_ContextModelsInit.cpp:124-148).  equal_prob mirrors
+ * param.equalProb (cabacEncode.m:25-27).  Output pointers may be NULL. */
+int cabac_iss_ctx_from_counters(const isscabac_symcfg* cfg, const uint64_t* h_counters, uint32_t n_groups,
+                                int equal_prob, double* h_p0, uint8_t* h_ctx_quant, uint8_t* h_ctx_state);
+
 /* ---- host-buffer API (what a reference-side caller binds) ------------------ */
 /* Same semantics with HOST pointers; all host<->device copies happen inside the call.
  * Encode returns the compacted payload and the offset table: h_payload (capacity

@@ -1,0 +1,211 @@
+// iss_stats.cu -- the step right before encode in the ISS flow: empirical p(0) per context
+// from the binarised matrix (ISS/+coder/cabacInitContextModel.m:15-129), as a device-side
+// reduction + a host-side finalisation in double precision (cabacEncode.m:23-31: statistics,
+// `equalProb`, uint8(ctxInit*255) side-info quantisation, /255, initByProb's state mapping).
+//
+// Every counter of the MATLAB code is a sum over symbols of a 0/1 term that depends only on
+// the symbol's own bin string and on the string of the symbol above it in the same column
+// (Gbin_up1, :16), so one thread per symbol evaluates the terms from the closed-form codes
+// (sym_code / sym_bin) and the warp adds them up with REDUX before touching global memory.
+// Quirks kept on purpose: the first row's neighbour is a NaN cell of length 1 with np = 0
+// (:16,:21,:23), so it takes part in the conds0/conds1 denominators for n = 1; the conds
+// normalisers index the neighbour at the absolute position n, not n + np_up1 (:90,:102); the
+// "rest" suffix statistic starts at the absolute bin position Nlbp+1 (:121-126).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/isscabac.h"
+#include "cabac_lane.cuh"
+#include "internal.h"
+
+using namespace cabac;
+using namespace isscabac_internal;
+
+namespace {
+
+// counters per modelled bin position n (1..Nlbp), then 4 for the two "rest" contexts
+enum { PRE_HIT, PRE_TOT, C_TOT, C0_HIT, C0N_HIT, C1_HIT, C1N_HIT, BL_TOT, BL_HIT, BLN_HIT,
+       SUF_HIT, SUF_TOT, CS_TOT, S0_HIT, S0N_HIT, S1_HIT, S1N_HIT, PER_N };
+enum { RP_HIT, RP_TOT, RS_HIT, RS_TOT, N_REST };
+constexpr int MAX_NLBP = 8;
+
+__device__ __forceinline__ uint32_t load_sym(const void* p, int width, uint64_t i) {
+  if (width == 1) return static_cast<const uint8_t*>(p)[i];
+  if (width == 2) return static_cast<const uint16_t*>(p)[i];
+  return static_cast<const uint32_t*>(p)[i];
+}
+
+__device__ __forceinline__ void add_counter(unsigned long long* dst, uint32_t v, bool uniform) {
+  if (uniform) {
+    const uint32_t s = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst, (unsigned long long)s);
+  } else if (v) {
+    atomicAdd(dst, (unsigned long long)v);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_iss_ctx_stats(isscabac_symcfg c, const void* sym, int width, uint64_t n_sym,
+                                                        const uint64_t* sym_off, uint32_t n_streams, uint32_t per_group,
+                                                        unsigned long long* counters) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n_sym;
+  const int N = c.Nlbp;
+  const uint32_t K = (uint32_t)(PER_N * N + N_REST);
+  uint32_t group = 0xffffffffu;
+  SymCode x = {0, 0, 0}, u = {0, 0, 0};
+  bool hasup = false;
+  if (live) {
+    uint32_t lo = 0, hi = n_streams;   // stream of symbol i: last s with sym_off[s] <= i
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (sym_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    group = lo / per_group;
+    const uint64_t in_stream = i - sym_off[lo];
+    hasup = c.rows ? (in_stream % c.rows) != 0 : in_stream > 0;
+    x = sym_code(load_sym(sym, width, i), c.Nq, c.method);
+    if (hasup) u = sym_code(load_sym(sym, width, i - 1), c.Nq, c.method);
+  }
+  // whole warp in one group -> warp-aggregated adds (dead lanes contribute zeros)
+  const uint32_t g0 = __shfl_sync(0xffffffffu, group, 0);
+  const bool uniform = __all_sync(0xffffffffu, group == g0 || !live) && g0 != 0xffffffffu;
+  if (!uniform && !live) return;
+  unsigned long long* cnt = counters + (size_t)(uniform ? g0 : group) * K;
+  // np = position of the first 0, or the length when there is none (:18-20)
+  const uint32_t L = x.len, np = x.np <= x.len ? x.np : x.len;
+  const uint32_t L_up = hasup ? u.len : 1u;                                  // :23
+  const uint32_t np_up = hasup ? (u.np <= u.len ? u.np : u.len) : 0u;        // :21
+  const uint32_t lv = live ? 1u : 0u;
+  for (int n = 1; n <= N; ++n) {
+    unsigned long long* cn = cnt + PER_N * (n - 1);
+    const uint32_t un = (uint32_t)n;
+    const bool in_pre = lv && un <= np;
+    const uint32_t xn = in_pre ? sym_bin(x, un) : 1u;
+    add_counter(cn + PRE_TOT, in_pre, uniform);                               // :31-33
+    add_counter(cn + PRE_HIT, in_pre && xn == 0, uniform);
+    const bool csel = in_pre && un <= np_up;                                  // :38,:50
+    const uint32_t yn = (lv && hasup && un <= L_up) ? sym_bin(u, un) : 2u;    // 2 = NaN / out of range
+    add_counter(cn + C_TOT, csel, uniform);
+    add_counter(cn + C0_HIT, csel && xn == 0 && yn == 0, uniform);
+    add_counter(cn + C0N_HIT, csel && yn == 0, uniform);
+    add_counter(cn + C1_HIT, csel && xn == 0 && yn == 1, uniform);
+    add_counter(cn + C1N_HIT, csel && yn == 1, uniform);
+    const bool bsel = lv && un + 1 <= np && np_up < un + 1;                   // :62-72
+    add_counter(cn + BL_TOT, bsel, uniform);
+    add_counter(cn + BL_HIT, bsel && sym_bin(x, un + 1) == 0 && xn == 1, uniform);
+    add_counter(cn + BLN_HIT, bsel && xn == 1, uniform);
+    const bool ssel = lv && un + np <= L;                                     // :77-80
+    const uint32_t xs = ssel ? sym_bin(x, un + np) : 1u;
+    add_counter(cn + SUF_TOT, ssel, uniform);
+    add_counter(cn + SUF_HIT, ssel && xs == 0, uniform);
+    const bool cssel = ssel && un + np_up <= L_up;                            // :84-106
+    const uint32_t ys = (cssel && hasup) ? sym_bin(u, un + np_up) : 2u;
+    add_counter(cn + CS_TOT, cssel, uniform);
+    add_counter(cn + S0_HIT, cssel && xs == 0 && ys == 0, uniform);
+    add_counter(cn + S0N_HIT, cssel && yn == 0, uniform);
+    add_counter(cn + S1_HIT, cssel && xs == 0 && ys == 1, uniform);
+    add_counter(cn + S1N_HIT, cssel && yn == 1, uniform);
+  }
+  // rest contexts (:111-126): bins from absolute position Nlbp+1 on
+  unsigned long long* cr = cnt + PER_N * N;
+  const uint32_t n0 = (uint32_t)N + 1u;
+  uint32_t rp_tot = 0, rp_hit = 0, rs_tot = 0, rs_hit = 0;
+  if (lv && n0 <= np) {
+    rp_tot = np - (uint32_t)N;
+    rp_hit = sym_bin(x, np) == 0 ? 1u : 0u;   // bins n0..np-1 are prefix ones
+  } else if (lv && n0 <= L) {
+    rs_tot = L - (uint32_t)N;
+    for (uint32_t b = n0; b <= L; ++b) rs_hit += sym_bin(x, b) == 0;
+  }
+  add_counter(cr + RP_TOT, rp_tot, uniform);
+  add_counter(cr + RP_HIT, rp_hit, uniform);
+  add_counter(cr + RS_TOT, rs_tot, uniform);
+  add_counter(cr + RS_HIT, rs_hit, uniform);
+}
+
+double frac(unsigned long long hit, unsigned long long tot) { return tot ? (double)hit / (double)tot : 0.0; }
+
+}  // namespace
+
+extern "C" {
+
+int cabac_iss_num_counters(int Nlbp) {
+  if (Nlbp < 1 || Nlbp > MAX_NLBP) return ISSCABAC_ERR_INVALID;
+  return PER_N * Nlbp + N_REST;
+}
+
+int cabac_iss_ctx_stats(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_sym_off,
+                        const void* d_symbols, int sym_width, uint64_t n_symbols, uint32_t streams_per_group,
+                        uint64_t* d_counters, void* stream) {
+  if (!cfg || !d_sym_off || !d_counters || (n_symbols && !d_symbols)) { set_error("cabac_iss_ctx_stats: null pointer"); return ISSCABAC_ERR_INVALID; }
+  if (cfg->Nlbp < 1 || cfg->Nlbp > MAX_NLBP) { set_error("Nlbp must be 1..%d", MAX_NLBP); return ISSCABAC_ERR_INVALID; }
+  if (cfg->method < 0 || cfg->method > ISSCABAC_BIN_FL32) { set_error("binarization method %d not supported", cfg->method); return ISSCABAC_ERR_UNSUPPORTED; }
+  if (sym_width != 1 && sym_width != 2 && sym_width != 4) { set_error("sym_width must be 1, 2 or 4"); return ISSCABAC_ERR_INVALID; }
+  if (streams_per_group == 0) streams_per_group = 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t groups = (n_streams + streams_per_group - 1) / streams_per_group;
+  const size_t K = (size_t)cabac_iss_num_counters(cfg->Nlbp);
+  CK(cudaMemsetAsync(d_counters, 0, groups * K * sizeof(uint64_t), st));
+  if (n_symbols == 0 || n_streams == 0) return ISSCABAC_OK;
+  const uint32_t blocks = (uint32_t)((n_symbols + 255) / 256);
+  k_iss_ctx_stats<<<blocks, 256, 0, st>>>(*cfg, d_symbols, sym_width, n_symbols, d_sym_off, n_streams, streams_per_group,
+                                          reinterpret_cast<unsigned long long*>(d_counters));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_iss_ctx_stats");
+}
+
+// counters -> p(0) per context (7*Nlbp+2 doubles per group, cabacInitContextModel.m:128), then
+// cabacEncode.m:26-31: equalProb override, uint8(p*255) (MATLAB rounding: half away from zero,
+// saturating), p = q/255, and the state bytes initByProb would derive from those p
+// (CABAC_ContextModelsInit.cpp:124-148).  Any output pointer may be NULL.
+int cabac_iss_ctx_from_counters(const isscabac_symcfg* cfg, const uint64_t* h_counters, uint32_t n_groups,
+                                int equal_prob, double* h_p0, uint8_t* h_ctx_quant, uint8_t* h_ctx_state) {
+  if (!cfg || (n_groups && !h_counters)) { set_error("cabac_iss_ctx_from_counters: null pointer"); return ISSCABAC_ERR_INVALID; }
+  const int N = cfg->Nlbp;
+  const int K = cabac_iss_num_counters(N);
+  if (K < 0) { set_error("Nlbp must be 1..%d", MAX_NLBP); return ISSCABAC_ERR_INVALID; }
+  const int nctx = 7 * N + 2;
+  for (uint32_t g = 0; g < n_groups; ++g) {
+    const unsigned long long* c = reinterpret_cast<const unsigned long long*>(h_counters) + (size_t)g * K;
+    double p[7 * MAX_NLBP + 2];
+    for (int i = 0; i < nctx; ++i) p[i] = 0.0;
+    for (int n = 0; n < N; ++n) {
+      const unsigned long long* cn = c + PER_N * n;
+      p[n] = frac(cn[PRE_HIT], cn[PRE_TOT]);
+      // joint / marginal, the marginal replaced by 1 when it is empty or zero (:41-45 etc.)
+      auto cond = [&](unsigned long long hit, unsigned long long norm_hit, unsigned long long tot) {
+        const double nr = norm_hit > 0 ? frac(norm_hit, tot) : 1.0;
+        return frac(hit, tot) / nr;
+      };
+      if (cfg->types & ISSCABAC_CM_COND0) p[N + n] = cond(cn[C0_HIT], cn[C0N_HIT], cn[C_TOT]);
+      if (cfg->types & ISSCABAC_CM_COND1) p[2 * N + n] = cond(cn[C1_HIT], cn[C1N_HIT], cn[C_TOT]);
+      if (cfg->types & ISSCABAC_CM_CONDBINLFT) p[3 * N + n] = cond(cn[BL_HIT], cn[BLN_HIT], cn[BL_TOT]);
+      p[4 * N + n] = frac(cn[SUF_HIT], cn[SUF_TOT]);
+      if (cfg->types & ISSCABAC_CM_CONDS0) p[5 * N + n] = cond(cn[S0_HIT], cn[S0N_HIT], cn[CS_TOT]);
+      if (cfg->types & ISSCABAC_CM_CONDS1) p[6 * N + n] = cond(cn[S1_HIT], cn[S1N_HIT], cn[CS_TOT]);
+    }
+    const unsigned long long* cr = c + PER_N * N;
+    p[7 * N] = frac(cr[RP_HIT], cr[RP_TOT]);
+    p[7 * N + 1] = frac(cr[RS_HIT], cr[RS_TOT]);
+    double pq[7 * MAX_NLBP + 2];
+    for (int i = 0; i < nctx; ++i) {
+      const double v = equal_prob ? 0.5 : p[i];
+      double q = floor(v * 255.0 + 0.5);            // uint8(): round half away from zero (v >= 0), saturate
+      q = std::max(0.0, std::min(q, 255.0));
+      if (h_p0) h_p0[(size_t)g * nctx + i] = v;
+      if (h_ctx_quant) h_ctx_quant[(size_t)g * nctx + i] = (uint8_t)q;
+      pq[i] = q / 255.0;
+    }
+    if (h_ctx_state) {
+      int rc = cabac_ctx_from_prob(pq, (uint32_t)nctx, h_ctx_state + (size_t)g * nctx);
+      if (rc) return rc;
+    }
+  }
+  return ISSCABAC_OK;
+}
+
+}  // extern "C"

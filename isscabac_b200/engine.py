@@ -353,3 +353,35 @@ def decode_symbols_host(cfg: SymCfg, payload, byte_off, sym_off, ctx_init, dtype
     check(lib().cabac_decode_symbols_host(C.byref(cfg), C.c_uint32(n), vp(boff), vp(pay), vp(off), vp(c),
                                           C.c_uint32(n_ctx), per, vp(out), out.dtype.itemsize, vp(ok)))
     return out[:int(off[-1])], ok[:n]
+
+
+# ------------------------------------------------------------------------------------
+# ISS context-init statistics (ISS/+coder/cabacInitContextModel.m)
+# ------------------------------------------------------------------------------------
+def iss_ctx_stats(cfg: SymCfg, symbols, sym_off, streams_per_group: int = 1) -> torch.Tensor:
+    """Per-group counters (int64 [n_groups, K]) of the context-init statistics, reduced on the device."""
+    dev = _require_cuda()
+    sym_t, width = _sym_tensor(symbols, dev)
+    off_t = _dev(sym_off, torch.int64, dev)
+    n = off_t.numel() - 1
+    L = lib()
+    K = int(L.cabac_iss_num_counters(int(cfg.Nlbp)))
+    if K < 0:
+        raise CabacError(K, "Nlbp out of range")
+    groups = (n + streams_per_group - 1) // max(streams_per_group, 1)
+    cnt = torch.empty((max(groups, 1), K), dtype=torch.int64, device=dev)
+    check(L.cabac_iss_ctx_stats(C.byref(cfg), C.c_uint32(n), vp(off_t), vp(sym_t), width, C.c_uint64(sym_t.numel()),
+                                C.c_uint32(int(streams_per_group)), vp(cnt), _stream_ptr()))
+    return cnt[:groups]
+
+
+def iss_ctx_from_counters(cfg: SymCfg, counters, equal_prob: bool = False):
+    """-> (p0 float64 [g, 7N+2], ctxInit0 uint8 [g, 7N+2] (the side information), state bytes uint8 [g, 7N+2])."""
+    c = np.ascontiguousarray(counters.cpu().numpy() if isinstance(counters, torch.Tensor) else counters, dtype=np.uint64)
+    g = c.shape[0]
+    nctx = 7 * int(cfg.Nlbp) + 2
+    p0 = np.zeros((g, nctx), dtype=np.float64)
+    q = np.zeros((g, nctx), dtype=np.uint8)
+    st = np.zeros((g, nctx), dtype=np.uint8)
+    check(lib().cabac_iss_ctx_from_counters(C.byref(cfg), vp(c), C.c_uint32(g), int(bool(equal_prob)), vp(p0), vp(q), vp(st)))
+    return p0, q, st
