@@ -21,6 +21,7 @@
 #include "../../include/isscabac.h"
 #include "cabac_lane.cuh"
 #include "cabac_wide.cuh"
+#include "wide_common.cuh"
 #include "internal.h"
 
 using namespace cabac;
@@ -338,57 +339,13 @@ __global__ void __launch_bounds__(NT) k_decode_ops(CodecParams P) {
 //                          slot n_ctx is the bypass slot (state 0x80)
 // Per lane and 16 ops: one 16-byte op load (next block prefetched), 16 branch-free bin steps,
 // 4 word emissions (encode) or refills (decode), one 16-byte store of the bins (decode).
-constexpr int WIDE_MAX_WARPS = 16;
-constexpr size_t WIDE_TAB_BYTES = (size_t)kNumRows * 32 * sizeof(uint2);
-
-struct WideRowTable {
-  uint2 r[kNumRows];
-  constexpr WideRowTable() : r{} {
-    for (uint32_t i = 0; i < kNumRows; ++i) r[i] = wide_row(i);
-  }
-};
-__constant__ WideRowTable c_wide_rows = WideRowTable();
-
-struct WCtx {
-  uint32_t* p;  // this lane's column of this warp's context block
-  __device__ __forceinline__ uint32_t load(uint32_t c) const { return p[c * 32]; }
-  __device__ __forceinline__ void store(uint32_t c, uint32_t v) const { p[c * 32] = v; }
-};
-struct WTab {
-  const uint2* p;  // this lane's column of the table
-  __device__ __forceinline__ uint2 row(uint32_t st) const { return p[st * 32]; }
-};
-
-// fills the table, initialises this warp's context block; returns false for lanes without a stream.
-// The per-lane offsets are made opaque so that they stay in registers (the optimiser otherwise
-// recomputes them from threadIdx at every table access).
-__device__ __forceinline__ bool wide_setup(const CodecParams& P, uint8_t* smem, uint32_t& s, WCtx& ctx, WTab& tab,
-                                           uint32_t& n_ctx) {
-  uint2* t = reinterpret_cast<uint2*>(smem);
-  for (uint32_t i = threadIdx.x; i < kNumRows * 32; i += blockDim.x) t[i] = c_wide_rows.r[i >> 5];
-  const uint32_t warp = threadIdx.x >> 5, lane = cb_keep32(threadIdx.x & 31);
-  const uint32_t nw = blockDim.x >> 5;
-  n_ctx = cb_keep32(P.n_ctx);
-  s = (blockIdx.x * nw + warp) * 32 + lane;
-  const bool valid = s < P.n_streams;
-  const uint32_t coff = cb_keep32(warp * (n_ctx + 1) * 32 + lane);
-  uint32_t* c0 = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + coff;
-  const uint8_t* init = P.ctx_init + (P.per_stream_init && valid ? (uint64_t)s * n_ctx : 0);
-  for (uint32_t c = 0; c < n_ctx; ++c) c0[c * 32] = init[c] & 127u;
-  c0[n_ctx * 32] = kEpState;
-  ctx.p = c0;
-  tab.p = t + lane;
-  __syncthreads();
-  return valid;
-}
-
 __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_ops_wide(CodecParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t s;
   WCtx ctx;
   WTab tab;
   uint32_t n_ctx;
-  if (!wide_setup(P, smem, s, ctx, tab, n_ctx)) return;
+  if (!wide_setup(P.n_streams, P.n_ctx, P.ctx_init, P.per_stream_init, smem, s, ctx, tab, n_ctx)) return;
   const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
   const uint8_t* p = reinterpret_cast<const uint8_t*>(P.ops) + o0;
   const uint64_t n = o1 - o0;
@@ -434,7 +391,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_ops_wide(CodecPa
   WCtx ctx;
   WTab tab;
   uint32_t n_ctx;
-  if (!wide_setup(P, smem, s, ctx, tab, n_ctx)) return;
+  if (!wide_setup(P.n_streams, P.n_ctx, P.ctx_init, P.per_stream_init, smem, s, ctx, tab, n_ctx)) return;
   const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
   const uint8_t* p = reinterpret_cast<const uint8_t*>(P.ops) + o0;
   uint8_t* q = P.bins + o0;
@@ -633,6 +590,48 @@ int sm_count() {
   return n > 0 ? n : 1;
 }
 
+// A zeroed u32 work counter for persistent kernels: slots of a small per-device ring that is
+// allocated once (no stream-ordered allocation on the launch path); the slot is cleared on the
+// caller's stream right before use.  512 launches may be in flight per device.
+int work_counter(cudaStream_t st, uint32_t** out) {
+  constexpr int kDevs = 64, kSlots = 512;
+  static uint32_t* ring[kDevs] = {};
+  static unsigned next[kDevs] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 0 || dev >= kDevs) { set_error("device index out of range"); return ISSCABAC_ERR_UNSUPPORTED; }
+  if (!ring[dev]) {
+    e = cudaMalloc(reinterpret_cast<void**>(&ring[dev]), kSlots * sizeof(uint32_t));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(work counters)");
+  }
+  uint32_t* slot = ring[dev] + (next[dev]++ % kSlots);
+  e = cudaMemsetAsync(slot, 0, sizeof(uint32_t), st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(work counter)");
+  *out = slot;
+  return ISSCABAC_OK;
+}
+
+// The launch paths that need stream-ordered scratch use the device's default memory pool; by
+// default that pool hands its memory back to the driver at every synchronisation, which makes
+// each later cudaMallocAsync a slow driver call.  Keep freed blocks cached instead (once per device).
+int keep_pool_cached() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev >= 0 && dev < 64 && !done[dev]) {
+    cudaMemPool_t pool;
+    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetDefaultMemPool");
+    uint64_t thr = ~0ull;
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemPoolSetAttribute");
+    done[dev] = true;
+  }
+  return ISSCABAC_OK;
+}
+
 size_t smem_limit() {
   static size_t lim = 0;
   if (!lim) {
@@ -673,24 +672,15 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   const size_t lim = smem_limit();
   if (!lim) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
   // hot path: u8 ops, context block of one warp fits shared memory next to the table
-  const size_t warp_ctx = ((size_t)P.n_ctx + 1) * 32 * 4;
-  if (op_width == 1 && P.n_ctx <= 125 && WIDE_TAB_BYTES + warp_ctx <= lim) {
-    const uint32_t sms = (uint32_t)sm_count();
-    const uint32_t tiles = (P.n_streams + 31) / 32;
-    // warps per CTA: spread the tiles evenly over the SMs (whole CTAs per SM), at most 16
-    uint32_t ctas_per_sm = (tiles + sms * WIDE_MAX_WARPS - 1) / (sms * WIDE_MAX_WARPS);
-    uint32_t nw = (tiles + sms * ctas_per_sm - 1) / (sms * ctas_per_sm);
-    const uint32_t nw_smem = (uint32_t)((lim - WIDE_TAB_BYTES) / warp_ctx);
-    if (nw > nw_smem) nw = nw_smem;
-    if (nw > WIDE_MAX_WARPS) nw = WIDE_MAX_WARPS;
-    if (nw < 1) nw = 1;
-    const size_t smem = WIDE_TAB_BYTES + warp_ctx * nw;
+  uint32_t nw, grid;
+  size_t wsmem;
+  if (op_width == 1 && wide_geometry(P.n_streams, P.n_ctx, nw, grid, wsmem)) {
     auto kernel = ENC ? k_encode_ops_wide : k_decode_ops_wide;
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (wsmem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
     }
-    kernel<<<(tiles + nw - 1) / nw, nw * 32, smem, st>>>(P);
+    kernel<<<grid, nw * 32, wsmem, st>>>(P);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, ENC ? "k_encode_ops_wide" : "k_decode_ops_wide");
   }
@@ -707,6 +697,7 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
     return rc;
   }
   void* scratch = nullptr;
+  if ((rc = keep_pool_cached())) return rc;
   cudaError_t e = cudaMallocAsync(&scratch, (size_t)P.n_ctx * P.n_streams, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(ctx scratch)");
   P.ctx_scratch = static_cast<uint8_t*>(scratch);

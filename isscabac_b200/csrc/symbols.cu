@@ -18,6 +18,7 @@
 #include "../../include/isscabac.h"
 #include "cabac_lane.cuh"
 #include "internal.h"
+#include "wide_common.cuh"
 
 using namespace cabac;
 using namespace isscabac_internal;
@@ -51,38 +52,114 @@ __device__ __forceinline__ SymCfg to_cfg(const isscabac_symcfg& c) {
 }
 
 // ---- symbol-parallel binarizer ------------------------------------------------
-__global__ void k_sym_count(isscabac_symcfg c, const void* sym, int width, uint64_t n, uint32_t* counts) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  counts[i] = sym_code(load_sym(sym, width, i), c.Nq, c.method).len;
+// Tiles of 2,048 consecutive symbols, 8 per thread.  Pass 1 sums the (closed-form) bin counts of
+// every tile; a device-wide scan over the tile sums gives each tile's first op position; pass 2
+// recomputes the counts, scans them inside the block and writes the ops.  Only pass 2 needs to
+// know which stream a symbol belongs to (context selection looks at the position inside the
+// stream, and the thread that owns a stream's first symbol records op_off[s]): one binary search
+// per warp, then every lane walks forward from there.
+constexpr int BIN_THREADS = 256, BIN_ITEMS = 8, BIN_TILE = BIN_THREADS * BIN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& block_total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  uint32_t off = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < BIN_THREADS / 32; ++w) {
+    const uint32_t t = s_warp[w];
+    if (w < wid) off += t;
+    tot += t;
+  }
+  block_total = tot;
+  return off + inc - v;
 }
 
-__global__ void k_stream_op_off(const uint64_t* sym_off, const uint64_t* sym_op_off, uint64_t* op_off, uint32_t n_streams) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s <= n_streams) op_off[s] = sym_op_off[sym_off[s]];
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_count(isscabac_symcfg c, const void* sym, int width, uint64_t n,
+                                                            uint32_t* tile_sums) {
+  __shared__ uint32_t s_warp[BIN_THREADS / 32];
+  const uint64_t i0 = (uint64_t)blockIdx.x * BIN_TILE + (uint64_t)threadIdx.x * BIN_ITEMS;
+  uint32_t tot = 0;
+#pragma unroll
+  for (int k = 0; k < BIN_ITEMS; ++k)
+    if (i0 + k < n) tot += sym_code(load_sym(sym, width, i0 + k), c.Nq, c.method).len;
+  uint32_t block_total;
+  block_exclusive_scan(tot, s_warp, block_total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = block_total;
 }
 
-__global__ void k_sym_emit(isscabac_symcfg c, const void* sym, int width, uint64_t n, const uint64_t* sym_off,
-                           uint32_t n_streams, const uint64_t* sym_op_off, uint8_t* ops, uint64_t cap) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const SymCfg cfg = to_cfg(c);
-  // stream of symbol i: last s with sym_off[s] <= i
-  uint32_t lo = 0, hi = n_streams;
+// last s < n_streams with sym_off[s] <= i, searched in [lo, n_streams)
+__device__ __forceinline__ uint32_t find_stream(const uint64_t* sym_off, uint32_t lo, uint32_t n_streams, uint64_t i) {
+  uint32_t hi = n_streams;
   while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
+    const uint32_t mid = (lo + hi) >> 1;
     if (sym_off[mid] <= i) lo = mid; else hi = mid;
   }
-  const uint64_t in_stream = i - sym_off[lo];
-  const bool up = sym_has_up(cfg, in_stream);
-  const SymCode code = sym_code(load_sym(sym, width, i), cfg.Nq, cfg.method);
-  SymCode u = {0, 0, 0};
-  if (up) u = sym_code(load_sym(sym, width, i - 1), cfg.Nq, cfg.method);
-  uint64_t o = sym_op_off[i];
-  for (uint32_t b = 1; b <= code.len; ++b, ++o) {
-    int cx = select_ctx(cfg, b, code.np, u, up);
-    uint32_t cd = cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx;
-    if (o < cap) ops[o] = (uint8_t)((cd << 1) | sym_bin(code, b));
+  return lo;
+}
+
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, const void* sym, int width, uint64_t n,
+                                                           const uint64_t* sym_off, uint32_t n_streams,
+                                                           const uint64_t* tile_prefix, uint64_t* op_off, uint8_t* ops,
+                                                           uint64_t cap) {
+  __shared__ uint32_t s_warp[BIN_THREADS / 32];
+  const SymCfg cfg = to_cfg(c);
+  const uint64_t i0 = (uint64_t)blockIdx.x * BIN_TILE + (uint64_t)threadIdx.x * BIN_ITEMS;
+  SymCode code[BIN_ITEMS];
+  uint32_t tot = 0;
+#pragma unroll
+  for (int k = 0; k < BIN_ITEMS; ++k) {
+    code[k] = SymCode{0, 0, 0};
+    if (i0 + k < n) code[k] = sym_code(load_sym(sym, width, i0 + k), cfg.Nq, cfg.method);
+    tot += code[k].len;
+  }
+  uint32_t block_total;
+  uint64_t o = tile_prefix[blockIdx.x] + block_exclusive_scan(tot, s_warp, block_total);
+  // stream of this thread's first symbol: one search per warp, then forward from the warp's stream
+  uint32_t sw = 0;
+  if ((threadIdx.x & 31) == 0 && i0 < n) sw = find_stream(sym_off, 0, n_streams, i0);
+  sw = __shfl_sync(0xffffffffu, sw, 0);
+  if (i0 >= n) return;
+  uint32_t s = sw;
+  if (sw + 1 < n_streams && sym_off[sw + 1] <= i0) s = find_stream(sym_off, sw, n_streams, i0);
+  uint64_t start = sym_off[s], next = sym_off[s + 1];
+  SymCode prev = {0, 0, 0};
+  if (i0 > start) prev = sym_code(load_sym(sym, width, i0 - 1), cfg.Nq, cfg.method);
+#pragma unroll
+  for (int k = 0; k < BIN_ITEMS; ++k) {
+    const uint64_t i = i0 + k;
+    if (i >= n) break;
+    if (i == next) {   // next non-empty stream
+      ++s;
+      while (s + 1 < n_streams && sym_off[s + 1] == i) ++s;
+      start = i;
+      next = sym_off[s + 1];
+    }
+    if (i == start) {  // first symbol of stream s: record where its ops begin (also for empty streams in front of it)
+      for (uint32_t e = s;; --e) {
+        op_off[e] = o;
+        if (e == 0 || sym_off[e - 1] != i) break;
+      }
+    }
+    const bool up = sym_has_up(cfg, i - start);
+    if (ops) {
+      for (uint32_t b = 1; b <= code[k].len; ++b) {
+        const int cx = select_ctx(cfg, b, code[k].np, prev, up);
+        const uint32_t cd = cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx;
+        if (o + b - 1 < cap) ops[o + b - 1] = (uint8_t)((cd << 1) | sym_bin(code[k], b));
+      }
+    }
+    o += code[k].len;
+    prev = code[k];
+    if (i == n - 1) {  // streams that start at the very end are empty; op_off[n_streams] = total
+      for (uint32_t e = s + 1; e <= n_streams; ++e) op_off[e] = o;
+    }
   }
 }
 
@@ -192,6 +269,223 @@ __global__ void __launch_bounds__(NT) k_decode_symbols(SymParams P) {
   if (P.finish_ok) P.finish_ok[s] = (uint8_t)dec_finish(D);
 }
 
+// ---- fused symbol encode / decode, wide-window formulation ------------------------
+// Persistent warps (wide_common.cuh: per-lane replicated table, per-warp context block).  Every
+// LANE runs a small state machine over the symbols of its current stream -- binarizer, context
+// selection and (decode) finish detector + debinarizer in closed form -- that yields or consumes
+// ONE bin per step, so the 32 lanes stay in lockstep bin by bin whatever their symbols' lengths
+// are; the coder step is the same branch-free encw_op / decw_op as in the op-array kernels, with
+// one word emission / refill after every 4th step.  No op array touches HBM.
+// Load balance for ragged streams (lognormal lengths): a lane that finishes
+// its stream takes the next unclaimed stream id from a global counter and carries on, so a warp
+// never idles behind its longest stream; only the last few streams of the job run alone.
+// Longest-first processing order for ragged streams: streams are bucketed by the magnitude of
+// their symbol count (bucket = bit length), buckets laid out in descending order.  Within a
+// bucket the order is arrival order -- results do not depend on it, every stream is independent.
+constexpr int ORDER_BUCKETS = 65;
+__global__ void k_order_hist(const uint64_t* off, uint32_t n, uint32_t* hist) {
+  __shared__ uint32_t h[ORDER_BUCKETS];
+  for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) atomicAdd(&h[64 - __clzll((long long)(off[s + 1] - off[s]))], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x)
+    if (h[i]) atomicAdd(&hist[i], h[i]);
+}
+__global__ void k_order_scatter(const uint64_t* off, uint32_t n, const uint32_t* hist, uint32_t* cursor, uint32_t* order) {
+  __shared__ uint32_t base[ORDER_BUCKETS];
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int b = ORDER_BUCKETS - 1; b >= 0; --b) { base[b] = acc; acc += hist[b]; }
+  }
+  __syncthreads();
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int b = 64 - __clzll((long long)(off[s + 1] - off[s]));
+  order[base[b] + atomicAdd(&cursor[b], 1u)] = s;
+}
+
+struct LaneCtx {
+  WCtx ctx;
+  uint32_t n_ctx;
+  const uint8_t* init;
+  int per_stream;
+  __device__ __forceinline__ void reset(uint32_t s) const {
+    const uint8_t* p = init + (per_stream ? (uint64_t)s * n_ctx : 0);
+    for (uint32_t c = 0; c < n_ctx; ++c) ctx.store(c, p[c] & 127u);
+  }
+};
+
+// PROF / METH: profile and binarization fixed at compile time for the combinations the
+// applications use (the closed-form helpers then fold to a few instructions); -1 = read from cfg.
+template <int PROF, int METH>
+__device__ __forceinline__ SymCfg fixed_cfg(const isscabac_symcfg& c) {
+  SymCfg cfg = to_cfg(c);
+  if (PROF >= 0) cfg.profile = PROF;
+  if (METH >= 0) cfg.method = METH;
+  return cfg;
+}
+// "has an up / previous neighbour" without a division: r = row of the symbol inside its column
+__device__ __forceinline__ bool has_up_row(const SymCfg& cfg, uint32_t i_rel, uint32_t r) {
+  if (cfg.profile == PROFILE_ISS) return cfg.rows ? r != 0 : i_rel > 0;
+  if (cfg.profile == PROFILE_DEMO) return i_rel > 0;
+  return false;
+}
+
+template <int PROF, int METH>
+__global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(SymParams P, uint32_t* next_stream, const uint32_t* order) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint32_t s, n_ctx;
+  WCtx ctx;
+  WTab tab;
+  wide_setup(P.n_streams, P.n_ctx, P.ctx_init, 0, smem, s, ctx, tab, n_ctx);   // shared init: reset() below does the rest
+  const LaneCtx lc{ctx, n_ctx, P.ctx_init, P.per_stream_init};
+  const SymCfg cfg = fixed_cfg<PROF, METH>(P.cfg);
+  const uint32_t cap = (uint32_t)(P.slab_stride > 0xfffffffcull ? 0xfffffffcull : P.slab_stride);
+  EncWide E;
+  encw_start(E, nullptr, 0);
+  const uint8_t* src = nullptr;     // first symbol of the stream
+  uint32_t i = 0, cnt = 0, row = 0; // next symbol to fetch (stream-relative), symbols in the stream, row in the column
+  SymCode cur = {0, 0, 0}, prev = {0, 0, 0};
+  uint32_t b = 1;                   // next bin of `cur`; b > cur.len: fetch the next symbol first
+  bool up = false, active = false, have = s < P.n_streams;
+  if (have && order) s = order[s];
+  for (;;) {
+    if (!active && have) {          // claim the stream: (re)initialise contexts and coder
+      lc.reset(s);
+      const uint64_t s0 = P.sym_off[s];
+      cnt = (uint32_t)(P.sym_off[s + 1] - s0);
+      src = static_cast<const uint8_t*>(P.symbols) + s0 * (uint64_t)P.sym_width;
+      encw_start(E, P.slab + (uint64_t)s * P.slab_stride, cap);
+      i = 0; row = 0; cur = SymCode{0, 0, 0}; prev = cur; b = 1; up = false;
+      active = true;
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (active && (b <= cur.len || i < cnt)) {
+        if (j == 3 && E.n > 47) encw_emit(E);
+        if (b > cur.len) {
+          prev = cur;
+          cur = sym_code(load_sym(src, P.sym_width, i), cfg.Nq, cfg.method);
+          up = has_up_row(cfg, i, row);
+          ++i;
+          if (++row == cfg.rows) row = 0;
+          b = 1;
+        }
+        const int cx = select_ctx(cfg, b, cur.np, prev, up);
+        encw_op(E, cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx, sym_bin(cur, b), ctx, tab, n_ctx);
+        ++b;
+      }
+    }
+    encw_emit(E);
+    if (active && !(b <= cur.len || i < cnt)) {   // stream complete: finish(), then take the next unclaimed one
+      const uint32_t len = encw_finish(E);
+      P.lengths[s] = len;
+      if (len > cap && P.overflow) atomicOr(P.overflow, 1u);
+      encw_start(E, nullptr, 0);
+      active = false;
+      s = gridDim.x * blockDim.x + atomicAdd(next_stream, 1u);
+      have = s < P.n_streams;
+      if (have && order) s = order[s];
+    }
+  }
+}
+
+template <int PROF, int METH>
+__global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_symbols_wide(SymParams P, uint32_t* next_stream, const uint32_t* order) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint32_t s, n_ctx;
+  WCtx ctx;
+  WTab tab;
+  wide_setup(P.n_streams, P.n_ctx, P.ctx_init, 0, smem, s, ctx, tab, n_ctx);
+  const LaneCtx lc{ctx, n_ctx, P.ctx_init, P.per_stream_init};
+  const SymCfg cfg = fixed_cfg<PROF, METH>(P.cfg);
+  DecWide D;
+  decw_start(D, P.bytes, 0);
+  uint8_t* dst = nullptr;           // first symbol of the stream in the output
+  uint32_t i = 0, cnt = 0, row = 0; // symbol being decoded (stream-relative), symbols in the stream, row in the column
+  SymDec sd;
+  symdec_reset(sd);
+  SymCode prev = {0, 0, 0};
+  bool up = false, active = false, have = s < P.n_streams;
+  if (have && order) s = order[s];
+  for (;;) {
+    if (!active && have) {
+      lc.reset(s);
+      const uint64_t s0 = P.sym_off[s];
+      cnt = (uint32_t)(P.sym_off[s + 1] - s0);
+      dst = static_cast<uint8_t*>(P.out_symbols) + s0 * (uint64_t)P.sym_width;
+      const uint64_t b0 = P.byte_off[s], b1 = P.byte_off[s + 1];
+      decw_start(D, P.bytes + b0, (uint32_t)(b1 - b0));
+      i = 0; row = 0; symdec_reset(sd); prev = SymCode{0, 0, 0}; up = false;
+      active = true;
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (active && i < cnt) {
+        const int cx = select_ctx(cfg, sd.n + 1, sd.np, prev, up);
+        const uint32_t bin = decw_op(D, cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx, ctx, tab, n_ctx);
+        uint32_t v = 0;
+        if (symdec_push(sd, bin, cfg, v)) {
+          store_sym(dst, P.sym_width, i, v);
+          // the finished symbol's bin string as the next symbol's neighbour: its length, the
+          // position of its first zero (length + 1 when it has none) and its suffix bits
+          prev = SymCode{sd.n, sd.np != 0xffffffffu ? sd.np : (cfg.method == BIN_TU && bin == 0 ? sd.n : sd.n + 1u), sd.suf};
+          ++i;
+          if (++row == cfg.rows) row = 0;
+          symdec_reset(sd);
+          up = has_up_row(cfg, i, row);
+        }
+      }
+    }
+    decw_refill(D);
+    if (active && i >= cnt) {
+      if (P.finish_ok) P.finish_ok[s] = (uint8_t)decw_finish(D);
+      decw_start(D, P.bytes, 0);
+      active = false;
+      s = gridDim.x * blockDim.x + atomicAdd(next_stream, 1u);
+      have = s < P.n_streams;
+      if (have && order) s = order[s];
+    }
+  }
+}
+
+// persistent launch: as many warps as the streams need, at most what is resident on the device
+template <class K>
+int launch_sym_wide(K kernel, const SymParams& P, cudaStream_t st, const char* name, bool& done) {
+  uint32_t nw, grid;
+  size_t smem;
+  done = false;
+  if (!wide_geometry(P.n_streams, P.n_ctx, nw, grid, smem)) return ISSCABAC_OK;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(nw * 32), smem));
+  const uint32_t resident = (uint32_t)(per_sm > 0 ? per_sm : 1) * (uint32_t)sm_count();
+  if (grid > resident) grid = resident;
+  uint32_t* counter = nullptr;     // streams claimed beyond the first one of every lane (lane g starts with stream g)
+  int rc = work_counter(st, &counter);
+  if (rc) return rc;
+  // more streams than lanes: lanes will claim further streams, so hand them out longest first
+  uint32_t* order = nullptr;
+  if (P.n_streams > grid * nw * 32) {
+    if ((rc = keep_pool_cached())) return rc;
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&order), ((size_t)P.n_streams + 2 * ORDER_BUCKETS) * sizeof(uint32_t), st));
+    uint32_t* hist = order + P.n_streams;
+    CK(cudaMemsetAsync(hist, 0, 2 * ORDER_BUCKETS * sizeof(uint32_t), st));
+    const uint32_t blocks = (P.n_streams + 255) / 256;
+    k_order_hist<<<blocks, 256, 0, st>>>(P.sym_off, P.n_streams, hist);
+    k_order_scatter<<<blocks, 256, 0, st>>>(P.sym_off, P.n_streams, hist, hist + ORDER_BUCKETS, order);
+  }
+  kernel<<<grid, nw * 32, smem, st>>>(P, counter, order);
+  cudaError_t e = cudaGetLastError();
+  if (order) cudaFreeAsync(order, st);
+  done = true;
+  return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, name);
+}
+
 int check_cfg(const isscabac_symcfg* cfg, uint32_t n_ctx, int sym_width, bool need_ctx) {
   if (!cfg) { set_error("symcfg is NULL"); return ISSCABAC_ERR_INVALID; }
   if (cfg->profile < 0 || cfg->profile > ISSCABAC_PROFILE_FLAT_EPSUF) { set_error("unknown profile %d", cfg->profile); return ISSCABAC_ERR_INVALID; }
@@ -227,10 +521,10 @@ extern "C" {
 
 size_t cabac_binarize_scratch_bytes(uint64_t n_symbols, uint32_t n_streams) {
   (void)n_streams;
-  size_t counts = ((size_t)n_symbols * 4 + 255) & ~(size_t)255;
-  size_t offs = (((size_t)n_symbols + 1) * 8 + 255) & ~(size_t)255;
-  uint64_t tiles = (n_symbols + 2047) / 2048;
-  return counts + offs + (tiles + 1) * 8 + 512;
+  const uint64_t tiles = (n_symbols + BIN_TILE - 1) / BIN_TILE;
+  const size_t sums = ((size_t)tiles * 4 + 255) & ~(size_t)255;
+  const size_t pref = (((size_t)tiles + 1) * 8 + 255) & ~(size_t)255;
+  return sums + pref + cabac_compact_scratch_bytes((uint32_t)tiles) + 256;
 }
 
 int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_sym_off,
@@ -241,18 +535,23 @@ int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const
   int rc = check_cfg(cfg, 0, sym_width, false);
   if (rc) return rc;
   if (!d_sym_off || !d_op_off || !d_scratch || (n_symbols && !d_symbols)) { set_error("cabac_binarize_symbols: null pointer"); return ISSCABAC_ERR_INVALID; }
+  if (n_symbols == 0 || n_streams == 0) {
+    CK(cudaMemsetAsync(d_op_off, 0, ((size_t)n_streams + 1) * sizeof(uint64_t), st));
+    return ISSCABAC_OK;
+  }
+  const uint64_t tiles64 = (n_symbols + BIN_TILE - 1) / BIN_TILE;
+  if (tiles64 > 0x7fffffffull) { set_error("cabac_binarize_symbols: too many symbols for one call"); return ISSCABAC_ERR_UNSUPPORTED; }
+  const uint32_t tiles = (uint32_t)tiles64;
   uint8_t* scr = static_cast<uint8_t*>(d_scratch);
-  size_t counts_b = ((size_t)n_symbols * 4 + 255) & ~(size_t)255;
-  size_t offs_b = (((size_t)n_symbols + 1) * 8 + 255) & ~(size_t)255;
-  uint32_t* counts = reinterpret_cast<uint32_t*>(scr);
-  uint64_t* sym_op_off = reinterpret_cast<uint64_t*>(scr + counts_b);
-  void* scan_scr = scr + counts_b + offs_b;
-  const uint32_t blocks = (uint32_t)((n_symbols + 255) / 256);
-  if (n_symbols) k_sym_count<<<blocks, 256, 0, st>>>(*cfg, d_symbols, sym_width, n_symbols, counts);
-  if ((rc = exclusive_scan_u32_u64(counts, sym_op_off, n_symbols, scan_scr, st))) return rc;
-  k_stream_op_off<<<(n_streams + 256) / 256, 256, 0, st>>>(d_sym_off, sym_op_off, d_op_off, n_streams);
-  if (d_ops && n_symbols)
-    k_sym_emit<<<blocks, 256, 0, st>>>(*cfg, d_symbols, sym_width, n_symbols, d_sym_off, n_streams, sym_op_off, d_ops, ops_cap);
+  const size_t sums_b = ((size_t)tiles * 4 + 255) & ~(size_t)255;
+  const size_t pref_b = (((size_t)tiles + 1) * 8 + 255) & ~(size_t)255;
+  uint32_t* tile_sums = reinterpret_cast<uint32_t*>(scr);
+  uint64_t* tile_prefix = reinterpret_cast<uint64_t*>(scr + sums_b);
+  void* scan_scr = scr + sums_b + pref_b;
+  k_bin_count<<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, sym_width, n_symbols, tile_sums);
+  if ((rc = exclusive_scan_u32_u64(tile_sums, tile_prefix, tiles, scan_scr, st))) return rc;
+  k_bin_emit<<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, sym_width, n_symbols, d_sym_off, n_streams, tile_prefix,
+                                            d_op_off, d_ops, ops_cap);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "cabac_binarize_symbols");
 }
@@ -276,8 +575,18 @@ int cabac_encode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const u
   P.sym_off = d_sym_off; P.symbols = d_symbols; P.ctx_init = d_ctx_init;
   P.slab = d_slab; P.slab_stride = slab_stride; P.lengths = d_lengths; P.bits_after = d_bits_after_symbol; P.overflow = d_overflow;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return d_bits_after_symbol ? launch_sym(k_encode_symbols<true>, P, st, "k_encode_symbols")
-                             : launch_sym(k_encode_symbols<false>, P, st, "k_encode_symbols");
+  if (d_bits_after_symbol) return launch_sym(k_encode_symbols<true>, P, st, "k_encode_symbols");   // getNumBits() trace
+  bool done;
+#define SYM_WIDE_CASE(K, PR, ME) \
+  if (cfg->profile == PR && cfg->method == ME) rc = launch_sym_wide(K<PR, ME>, P, st, #K, done); else
+  SYM_WIDE_CASE(k_encode_symbols_wide, ISSCABAC_PROFILE_ISS, ISSCABAC_BIN_EG0)
+  SYM_WIDE_CASE(k_encode_symbols_wide, ISSCABAC_PROFILE_FLAT, ISSCABAC_BIN_EG0)
+  SYM_WIDE_CASE(k_encode_symbols_wide, ISSCABAC_PROFILE_FLAT_EPSUF, ISSCABAC_BIN_EG2)
+  SYM_WIDE_CASE(k_encode_symbols_wide, ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_TU)
+  SYM_WIDE_CASE(k_encode_symbols_wide, ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_EG0)
+  rc = launch_sym_wide(k_encode_symbols_wide<-1, -1>, P, st, "k_encode_symbols_wide", done);
+  if (rc || done) return rc;
+  return launch_sym(k_encode_symbols<false>, P, st, "k_encode_symbols");
 }
 
 int cabac_decode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_byte_off,
@@ -293,6 +602,15 @@ int cabac_decode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const u
   P.cfg = *cfg; P.n_streams = n_streams; P.n_ctx = n_ctx; P.per_stream_init = per_stream_init; P.sym_width = sym_width;
   P.sym_off = d_sym_off; P.ctx_init = d_ctx_init; P.byte_off = d_byte_off; P.bytes = d_bytes;
   P.out_symbols = d_symbols; P.finish_ok = d_finish_ok;
+  bool done;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SYM_WIDE_CASE(k_decode_symbols_wide, ISSCABAC_PROFILE_ISS, ISSCABAC_BIN_EG0)
+  SYM_WIDE_CASE(k_decode_symbols_wide, ISSCABAC_PROFILE_FLAT, ISSCABAC_BIN_EG0)
+  SYM_WIDE_CASE(k_decode_symbols_wide, ISSCABAC_PROFILE_FLAT_EPSUF, ISSCABAC_BIN_EG2)
+  SYM_WIDE_CASE(k_decode_symbols_wide, ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_TU)
+  SYM_WIDE_CASE(k_decode_symbols_wide, ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_EG0)
+  rc = launch_sym_wide(k_decode_symbols_wide<-1, -1>, P, st, "k_decode_symbols_wide", done);
+  if (rc || done) return rc;
   return launch_sym(k_decode_symbols, P, static_cast<cudaStream_t>(stream), "k_decode_symbols");
 }
 

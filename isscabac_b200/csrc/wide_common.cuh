@@ -1,0 +1,78 @@
+// wide_common.cuh -- what the wide-window kernels (kernels.cu: op arrays, symbols.cu: fused
+// binarizer + coder) share: the per-lane replicated state table, the per-warp context block and
+// the launch geometry (one warp per tile of 32 streams, NW warps per CTA).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cabac_wide.cuh"
+#include "internal.h"
+
+namespace cabac {
+
+constexpr int WIDE_MAX_WARPS = 16;
+constexpr size_t WIDE_TAB_BYTES = (size_t)kNumRows * 32 * sizeof(uint2);
+
+struct WideRowTable {
+  uint2 r[kNumRows];
+  constexpr WideRowTable() : r{} {
+    for (uint32_t i = 0; i < kNumRows; ++i) r[i] = wide_row(i);
+  }
+};
+static __constant__ WideRowTable c_wide_rows = WideRowTable();
+
+struct WCtx {
+  uint32_t* p;  // this lane's column of this warp's context block
+  __device__ __forceinline__ uint32_t load(uint32_t c) const { return p[c * 32]; }
+  __device__ __forceinline__ void store(uint32_t c, uint32_t v) const { p[c * 32] = v; }
+};
+struct WTab {
+  const uint2* p;  // this lane's column of the table
+  __device__ __forceinline__ uint2 row(uint32_t st) const { return p[st * 32]; }
+};
+
+// Fills the table, initialises this warp's context block (slot n_ctx = bypass slot); returns
+// false for lanes without a stream.  The per-lane offsets are made opaque so that they stay in
+// registers (the optimiser otherwise recomputes them from threadIdx at every table access).
+__device__ __forceinline__ bool wide_setup(uint32_t n_streams, uint32_t n_ctx_in, const uint8_t* ctx_init,
+                                           int per_stream_init, uint8_t* smem, uint32_t& s, WCtx& ctx, WTab& tab,
+                                           uint32_t& n_ctx) {
+  uint2* t = reinterpret_cast<uint2*>(smem);
+  for (uint32_t i = threadIdx.x; i < kNumRows * 32; i += blockDim.x) t[i] = c_wide_rows.r[i >> 5];
+  const uint32_t warp = threadIdx.x >> 5, lane = cb_keep32(threadIdx.x & 31);
+  const uint32_t nw = blockDim.x >> 5;
+  n_ctx = cb_keep32(n_ctx_in);
+  s = (blockIdx.x * nw + warp) * 32 + lane;
+  const bool valid = s < n_streams;
+  const uint32_t coff = cb_keep32(warp * (n_ctx + 1) * 32 + lane);
+  uint32_t* c0 = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + coff;
+  const uint8_t* init = ctx_init + (per_stream_init && valid ? (uint64_t)s * n_ctx : 0);
+  for (uint32_t c = 0; c < n_ctx; ++c) c0[c * 32] = init[c] & 127u;
+  c0[n_ctx * 32] = kEpState;
+  ctx.p = c0;
+  tab.p = t + lane;
+  __syncthreads();
+  return valid;
+}
+
+// Host: warps per CTA / grid / dynamic shared memory for n_streams streams with n_ctx contexts.
+// Tiles are spread evenly over the SMs in whole CTAs (65,536 streams = 2,048 tiles = 14 warps on
+// each of 147 SMs).  Returns false when one warp's context block does not fit shared memory.
+inline bool wide_geometry(uint32_t n_streams, uint32_t n_ctx, uint32_t& nw, uint32_t& grid, size_t& smem) {
+  const size_t lim = isscabac_internal::smem_limit();
+  const size_t warp_ctx = ((size_t)n_ctx + 1) * 32 * 4;
+  if (!lim || n_ctx > 125 || WIDE_TAB_BYTES + warp_ctx > lim) return false;
+  const uint32_t sms = (uint32_t)isscabac_internal::sm_count();
+  const uint32_t tiles = (n_streams + 31) / 32;
+  const uint32_t ctas_per_sm = (tiles + sms * WIDE_MAX_WARPS - 1) / (sms * WIDE_MAX_WARPS);
+  nw = (tiles + sms * ctas_per_sm - 1) / (sms * (ctas_per_sm ? ctas_per_sm : 1));
+  const uint32_t nw_smem = (uint32_t)((lim - WIDE_TAB_BYTES) / warp_ctx);
+  if (nw > nw_smem) nw = nw_smem;
+  if (nw > (uint32_t)WIDE_MAX_WARPS) nw = WIDE_MAX_WARPS;
+  if (nw < 1) nw = 1;
+  grid = (tiles + nw - 1) / nw;
+  smem = WIDE_TAB_BYTES + warp_ctx * nw;
+  return true;
+}
+
+}  // namespace cabac
