@@ -106,7 +106,7 @@ int cabac_host_free(void* p) {
 // ---------------------------------------------------------------------------
 namespace {
 
-constexpr int kChunks = 8;   // stream groups in flight
+constexpr int kChunks = 16;  // stream groups in flight
 constexpr int kLanes = 4;    // CUDA streams
 
 struct Pipeline {

@@ -106,3 +106,52 @@ def test_symbol_host_api(I):
     assert bytes(payload) == bytes(s_ref[0, :l_ref[0]]) and (bits == b_ref).all()
     dec, ok = I.decode_symbols_host(cfg, payload, boff, off, ci, dtype=np.uint8)
     assert ok.all() and (dec == sym).all()
+
+
+@pytest.mark.parametrize("name,scale", [("c2", 0.25), ("c4", 1 / 16), ("c5", 1 / 16)])
+def test_baseline_symbol_configs_properties(I, name, scale):
+    """BASELINE.json configs 2, 4 and 5 at a reduced stream count (tools/bench_symbols.py runs them at full
+    size): size-independent properties -- fused and two-pass (binarize -> op encoder) encoders agree on
+    every stream length, decode(encode(x)) == x, every finish() check holds, compaction is dense."""
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    T = I.CM_COND0 | I.CM_COND1 | I.CM_CONDS0 | I.CM_CONDS1
+    if name == "c2":
+        n, rows = int(65520 * scale), 400
+        u = torch.rand(n * rows, generator=g, device=dev)
+        sym = torch.where(u < 0.7, torch.zeros_like(u), 1 + torch.floor(torch.log(torch.rand(u.shape, generator=g, device=dev)) / np.log(0.6))).clamp_(0, 7).to(torch.uint8)
+        off = torch.arange(n + 1, dtype=torch.int64, device=dev) * rows
+        cfg, nctx = I.make_cfg(I.PROFILE_ISS, I.BIN_EG0, 8, 3, T, rows=rows), 23
+    elif name == "c4":
+        n, per = int((1 << 20) * scale), 1024
+        sym = torch.floor(torch.log(torch.rand(n * per, generator=g, device=dev)) / np.log(0.5)).clamp_(0, 15).to(torch.uint8)
+        off = torch.arange(n + 1, dtype=torch.int64, device=dev) * per
+        cfg, nctx = I.make_cfg(I.PROFILE_FLAT, I.BIN_EG0, 16, 3, 0), 8
+    else:
+        rng = np.random.default_rng(4)
+        n = int((1 << 20) * scale)
+        lens = np.clip(np.round(rng.lognormal(np.log(256), 1.0, size=n)), 1, 65536).astype(np.int64)
+        lens[:3] = [0, 1, 65536]                                     # empty, minimal and maximal streams
+        offn = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=offn[1:])
+        sym = torch.floor(-6.0 * torch.log(torch.rand(int(offn[-1]), generator=g, device=dev))).clamp_(0, 255).to(torch.uint8)
+        off = torch.as_tensor(offn, device=dev)
+        cfg, nctx = I.make_cfg(I.PROFILE_FLAT_EPSUF, I.BIN_EG2, 256, 3, 0), 4
+    ctx = torch.full((nctx,), 1, dtype=torch.uint8, device=dev)
+    ops, op_off = I.binarize_symbols(cfg, sym, off)
+    stride = (int((op_off[1:] - op_off[:-1]).max().item()) // 4 + 64 + 15) & ~15
+    e1 = I.encode_ops(ops, op_off, ctx, slab_stride=stride)
+    e2 = I.encode_symbols(cfg, sym, off, ctx, slab_stride=stride)
+    e1.check_overflow(); e2.check_overflow()
+    assert bool((e1.lengths == e2.lengths).all().item())
+    p1, p2 = I.compact(e1), I.compact(e2)
+    assert bool((p1.byte_off == p2.byte_off).all().item()) and bool((p1.payload == p2.payload).all().item())
+    assert int(p1.byte_off[-1].item()) == int(e1.lengths.to(torch.int64).sum().item())     # dense, no gaps
+    dec, ok = I.decode_symbols(cfg, p2, off, ctx, sym_dtype=torch.uint8)
+    assert bool(ok.all().item()) and bool((dec == sym).all().item())
+    bins, ok2 = I.decode_ops(p1, ops, op_off, ctx)
+    assert bool(ok2.all().item()) and bool((bins == (ops & 1)).all().item())
+    if name == "c5":   # the empty stream is the two bytes of start(); finish() (KAT K0)
+        b = p1.payload[int(p1.byte_off[0].item()):int(p1.byte_off[1].item())].cpu().numpy()
+        assert bytes(b) == bytes.fromhex("fe80")
