@@ -197,6 +197,36 @@ int cabac_decode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, co
 int cabac_host_alloc(void** p, size_t bytes);
 int cabac_host_free(void* p);
 
+/* ---- container: wire format for many streams (host only) ------------------- */
+/* The reference has one file per stream (CABAC/SimpleCABACMex.cpp:195,288) and ships the
+ * context initialisation as uint8 side information in a .mat file (ISS/ISS.m:197-201,
+ * ISS/+coder/cabacEncode.m:30).  The container holds payload + u64 offset table + per-stream
+ * unit (symbol / op) counts + context-init bytes in one buffer; the bytes of stream s are
+ * exactly the file the reference would have written, so a stream cut out with
+ * cabac_container_stream() is decodable by the reference's decodeStart ... decodeFinish.
+ * Layout: see isscabac_b200/csrc/container.cpp.  All pointers are HOST pointers. */
+typedef struct {
+  uint32_t n_streams, n_ctx;
+  int32_t per_stream_init;   /* ctx_init holds n_streams*n_ctx bytes instead of n_ctx */
+  int32_t ctx_is_prob;       /* ctx_init bytes are uint8(p0*255) side info (cabacEncode.m:30), not state bytes */
+  int32_t has_cfg;           /* cfg / sym_width are meaningful (symbol-level streams) */
+  int32_t sym_width;
+  isscabac_symcfg cfg;
+  uint64_t payload_bytes;
+  const uint64_t* byte_off;  /* n_streams + 1 */
+  const uint64_t* unit_off;  /* n_streams + 1 exclusive offsets of symbols (or ops) per stream; may be NULL */
+  const uint8_t* ctx_init;
+  const uint8_t* payload;
+} isscabac_container_view;
+uint32_t cabac_crc32(const uint8_t* p, uint64_t n);                 /* IEEE CRC-32 as used by the container */
+uint64_t cabac_container_size(const isscabac_container_view* v);    /* 0 on invalid view */
+int cabac_container_write(const isscabac_container_view* v, uint8_t* out, uint64_t cap, uint64_t* written);
+/* Validates magic, version, checksums (payload CRC only when verify_payload_crc != 0), section
+ * table and monotone offsets; the view then points INTO buf (8-byte aligned). */
+int cabac_container_parse(const uint8_t* buf, uint64_t n, int verify_payload_crc, isscabac_container_view* v);
+int cabac_container_stream(const isscabac_container_view* v, uint32_t s, const uint8_t** bytes, uint64_t* n_bytes,
+                           const uint8_t** ctx_init, uint64_t* n_units);
+
 /* ---- single-stream engine handle (backs the SimpleCABAC C++ facade) -------- */
 /* One handle = the reference's `class CABAC` aggregate (SimpleCABACMex.cpp:69-80): a
  * bitstream name or memory buffer, an encoder context set and a decoder context set.

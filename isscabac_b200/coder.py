@@ -80,6 +80,29 @@ def decode_matrices(enc, shapes, per_column: bool = False):
     return out
 
 
+def to_container(enc, sym_width: int = 4) -> np.ndarray:
+    """encode_matrices result -> one buffer (container.py): payload, offset table, symbols per stream and
+    the uint8 side information ctxInit0 of every stream (what the reference ships in a .mat file,
+    ISS/ISS.m:197-201); any stream of it is a bitstream the reference decodes unchanged."""
+    from . import container as K
+    q_rows = np.ascontiguousarray(enc["ctxInit0"][enc["group_of_stream"]], dtype=np.uint8)
+    return K.pack(enc["payload"], enc["byte_off"], q_rows, unit_off=enc["sym_off"], cfg=enc["cfg"],
+                  sym_width=sym_width, ctx_is_prob=True)
+
+
+def from_container(blob):
+    """Inverse of to_container: -> the dict decode_matrices takes (context states re-derived from the
+    uint8 side information exactly like cabacDecode.m:13 does)."""
+    from . import container as K
+    c = K.unpack(blob)
+    q = c.ctx_init if c.ctx_init.ndim == 2 else c.ctx_init[None, :].repeat(max(c.n_streams, 1), 0)
+    st = E.ctx_from_prob(q.astype(np.float64).reshape(-1) / 255.0).reshape(q.shape)
+    return dict(payload=torch.as_tensor(c.payload, device="cuda") if c.payload.size else torch.zeros(1, dtype=torch.uint8, device="cuda"),
+                byte_off=torch.as_tensor(c.byte_off.astype(np.int64), device="cuda"),
+                ctxInit0=q, ctx_state=st, sym_off=c.unit_off.astype(np.int64), cfg=c.cfg,
+                group_of_stream=np.arange(c.n_streams))
+
+
 def cabacEncode(G, Nq=2, param=None):
     """ISS/+coder/cabacEncode.m: -> (nbits, ctxInit0).  The bitstream goes to param['fn']."""
     param = dict(param or {})

@@ -95,3 +95,25 @@ def test_batched_matrices_and_column_streams():
                 assert bytes(pay[boff[i]:boff[i + 1]]) == s["payload"].cpu().numpy().tobytes()
         else:
             assert len(boff) - 1 == sum(m.shape[1] for m in mats)
+
+
+def test_matrices_through_the_container():
+    """encode_matrices -> container blob (payload + offsets + symbol counts + uint8 side info) -> decode;
+    a single column stream cut out of the blob is decoded by the oracle with the states derived from
+    the side information bytes, the way cabacDecode.m:13 derives them."""
+    from isscabac_b200 import coder, container as K
+    rng = np.random.default_rng(6)
+    param = dict(binMethod="DEC2EG0", cmTypes=["cond0", "cond1", "conds0", "conds1"], Nlbp=3)
+    mats = [iss_matrix(rng, 109, 20) for _ in range(5)]
+    enc = coder.encode_matrices(mats, 8, param, per_column=True)
+    blob = coder.to_container(enc)
+    dec = coder.decode_matrices(coder.from_container(blob.tobytes()), [m.shape for m in mats], per_column=True)
+    assert all(np.array_equal(a, b) for a, b in zip(dec, mats))
+    c = K.unpack(blob)
+    assert c.ctx_is_prob and c.n_streams == 100 and c.ctx_init.shape == (100, 23)
+    s = 47                                                   # column 7 of matrix 2
+    ocfg = O.make_cfg(O.PROFILE_ISS, O.BIN_EG0, 8, 3, ALLT, 109)
+    st = O.ctx_from_p0(c.stream_ctx(s).astype(np.float64) / 255)
+    one = c.stream(s)
+    out, ok = O.decode_symbols(ocfg, one, np.array([0, one.size], dtype=np.uint64), np.array([0, 109], dtype=np.uint64), st)
+    assert ok.all() and np.array_equal(out, mats[2][:, 7])
