@@ -197,6 +197,28 @@ int cabac_decode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, co
 int cabac_host_alloc(void** p, size_t bytes);
 int cabac_host_free(void* p);
 
+/* ---- statistics outputs (device) -------------------------------------------- */
+/* What the reference collects with one MEX call per bin: ctxHist / ctxCost of
+ * ISS/+coder/cabacEncode.m:40-41,61-65, and -- under RWTH_TRACE_CABAC_STATES (CommonDef.h:39-43,
+ * Windows builds) -- per-context trace-state histograms, 128x128 transition counts and step logs
+ * (CABAC/ContextModel.cpp:97-134, SimpleCABACMex.cpp:231-241,356-466).  Computed here in one pass
+ * over the op arrays (for decoder-side statistics pass the decoded bins in bit 0 of the ops).
+ * Trace-state index of a state byte: mps == 0 ? 63 - state : state + 64 (ContextModel.cpp:99-101).
+ * Streams are pooled in groups of streams_per_group consecutive streams.  Outputs (device,
+ * zeroed by the call; all but d_state_hist optional):
+ *   d_state_hist  u64[groups][n_ctx][128]       visits per trace state BEFORE each update; its sum over
+ *                                               the 128 states is the bins coded per context (ctxHist)
+ *   d_trans       u32[groups][n_ctx][128][128]  [state before][state after] transition counts
+ *   d_cost_bits   u64[groups][n_ctx + 1]        bits getNumBits() advanced by while a bin of the context
+ *                                               was coded (ctxCost); slot n_ctx = bypass + terminate bins
+ *   d_step_states u8[n_ops][2]                  context state byte before / after every op (0xFF, 0xFF
+ *                                               for bypass and terminate ops)
+ *   d_final_ctx   u8[n_streams][n_ctx]          context state bytes after the last op of every stream */
+int cabac_ctx_trace_ops(uint32_t n_streams, const uint64_t* d_op_off, const void* d_ops, int op_width,
+                        const uint8_t* d_ctx_init, uint32_t n_ctx, int per_stream_init,
+                        uint32_t streams_per_group, uint64_t* d_state_hist, uint32_t* d_trans,
+                        uint64_t* d_cost_bits, uint8_t* d_step_states, uint8_t* d_final_ctx, void* stream);
+
 /* ---- container: wire format for many streams (host only) ------------------- */
 /* The reference has one file per stream (CABAC/SimpleCABACMex.cpp:195,288) and ships the
  * context initialisation as uint8 side information in a .mat file (ISS/ISS.m:197-201,
@@ -258,6 +280,16 @@ int simplecabac_decode_bin_trm(simplecabac* h, unsigned* bin);
 int simplecabac_decode_ops(simplecabac* h, const uint16_t* ops, uint32_t n, uint8_t* bins);
 int simplecabac_decode_finish(simplecabac* h);   /* ISSCABAC_ERR_CORRUPT if the checks fail */
 int simplecabac_get_ctx_state(simplecabac* h, int decoder_set, unsigned ctx_idx, unsigned* state, unsigned* mps);
+/* Trace statistics of one context (the reference's RWTH_TRACE_CABAC_STATES members,
+ * ContextModel.cpp:97-134).  Tracing is off by default; enable it before the first bin.  Like the
+ * reference, the logs start at initByProb / initByState and run across streams.
+ * steps5: 5 bytes per step [bin, trace state before, mps before, trace state after, mps after]
+ * (capacity cap_steps steps; *n_steps = steps available); for the decoder set the bin byte is 0, as
+ * in the reference (SimpleCABACMex.cpp:318-320 samples it before decodeBin).  trans: 128*128 u32,
+ * index state_before*128 + state_after, or NULL. */
+int simplecabac_set_trace(simplecabac* h, int on);
+int simplecabac_get_stats(simplecabac* h, int decoder_set, unsigned ctx_idx, uint8_t* steps5, uint64_t cap_steps,
+                          uint64_t* n_steps, uint32_t* trans);
 
 /* ---- MEX command protocol (CABAC/SimpleCABACMex.cpp:100-472) ---------------- */
 /* One call = one mexFunction invocation.  args[0] is the command string; numeric
@@ -271,6 +303,13 @@ typedef struct {
 } isscabac_mxarg;
 int simplecabac_dispatch(int nlhs, double* out, int out_cap, int* out_n,
                          int nrhs, const isscabac_mxarg* args, char* err, int errcap);
+
+/* getEncoderStats / getDecoderStats (SimpleCABACMex.cpp:356-466, compiled into Windows builds of the
+ * reference only): args = {command, handle, ctxIdx}; same arity checks and error texts.  The two
+ * outputs are typed arrays there (uint8 5 x M, uint32 128 x 128), hence a separate entry point.
+ * The handle must have tracing on (command "setTrace", handle, 1 -- or simplecabac_set_trace). */
+int simplecabac_dispatch_stats(int nlhs, int nrhs, const isscabac_mxarg* args, uint8_t* steps5, uint64_t cap_steps,
+                               uint64_t* n_steps, uint32_t* trans, char* err, int errcap);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -111,6 +111,11 @@ void run(int nlhs, double* out, int out_cap, int* out_n, int nrhs, const isscaba
   } else if (cmd == "decodeFinish") {
     if (nrhs < 2) mex_err(kNeedHandle);
     check_rc(simplecabac_decode_finish(get_handle(args)));
+  } else if (cmd == "setTrace") {
+    // not in the reference: its Windows builds always trace (CommonDef.h:39-40), its Linux builds never do
+    if (nrhs < 2) mex_err(kNeedHandle);
+    simplecabac* h = get_handle(args);
+    check_rc(simplecabac_set_trace(h, (nrhs > 2 && args[2].d) ? (int)args[2].d[0] : 1));
   } else if (cmd == "destroy") {
     // not in the reference (its instances are leaked by design, SimpleCABACMex.cpp:149-150)
     if (nrhs < 2) mex_err(kNeedHandle);
@@ -126,6 +131,33 @@ void run(int nlhs, double* out, int out_cap, int* out_n, int nrhs, const isscaba
 }
 
 }  // namespace
+
+// getEncoderStats / getDecoderStats, SimpleCABACMex.cpp:356-466 (same checks, same order, same texts)
+extern "C" int simplecabac_dispatch_stats(int nlhs, int nrhs, const isscabac_mxarg* args, uint8_t* steps5,
+                                          uint64_t cap_steps, uint64_t* n_steps, uint32_t* trans, char* err, int errcap) {
+  if (n_steps) *n_steps = 0;
+  if (err && errcap > 0) err[0] = 0;
+  try {
+    if (nrhs < 1 || !is_char(args[0]) || !args[0].s) mex_err("Error: Invalid Command\n");
+    const std::string cmd(args[0].s);
+    if (cmd != "getEncoderStats" && cmd != "getDecoderStats") mex_err("Error: Invalid Command\n");
+    if (nrhs < 2) mex_err(kNeedHandle);
+    if (nlhs != 2) mex_err("Error: invalid command, provide two variables to store the trace \n");
+    simplecabac* h = get_handle(args);
+    const int ctx = (int)((nrhs > 2 && args[2].d) ? args[2].d[0] : 0.0);
+    check_rc(simplecabac_get_stats(h, cmd == "getDecoderStats", (unsigned)ctx, steps5, cap_steps, n_steps, trans));
+  } catch (const MexError& e) {
+    if (err && errcap > 0) {
+      strncpy(err, e.msg.c_str(), (size_t)errcap - 1);
+      err[errcap - 1] = 0;
+    }
+    return 1;
+  } catch (...) {
+    if (err && errcap > 0) snprintf(err, (size_t)errcap, "Error: internal failure\n");
+    return 1;
+  }
+  return 0;
+}
 
 extern "C" int simplecabac_dispatch(int nlhs, double* out, int out_cap, int* out_n,
                                     int nrhs, const isscabac_mxarg* args, char* err, int errcap) {

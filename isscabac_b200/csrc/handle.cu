@@ -137,6 +137,10 @@ struct simplecabac {
   std::vector<uint8_t> in_bytes; bool in_set = false;
   uint8_t* d_in = nullptr; size_t d_in_cap = 0; uint32_t in_len = 0;
   uint8_t* h_bins = nullptr; uint8_t* d_bins_mapped = nullptr; size_t bins_cap = 0;
+  // trace (RWTH_TRACE_CABAC_STATES): the (bin, ctx) history since initBy*, per context set
+  bool trace = false;
+  std::vector<uint16_t> enc_log, dec_log;
+  std::vector<uint8_t> init_bytes = std::vector<uint8_t>(kMaxCtx, (uint8_t)1);
 };
 
 namespace {
@@ -194,6 +198,9 @@ int init_ctx(simplecabac* h, const uint8_t* ctx, uint32_t n) {
   std::vector<uint8_t> full(kMaxCtx, (uint8_t)1);
   if (n > ISSCABAC_MAX_CTX) { set_error("at most %u contexts", ISSCABAC_MAX_CTX); return ISSCABAC_ERR_INVALID; }
   memcpy(full.data(), ctx, n);
+  h->init_bytes = full;       // a fresh `class CABAC` in the reference: its trace members start empty
+  h->enc_log.clear();
+  h->dec_log.clear();
   CK(cudaMemcpyAsync(h->d_state->enc_ctx, full.data(), kMaxCtx, cudaMemcpyHostToDevice, h->st));
   CK(cudaMemcpyAsync(h->d_state->dec_ctx, full.data(), kMaxCtx, cudaMemcpyHostToDevice, h->st));
   CK(cudaStreamSynchronize(h->st));
@@ -266,6 +273,7 @@ static int queue_op(simplecabac* h, uint32_t op) {
   if (!h) return ISSCABAC_ERR_INVALID;
   if (!h->encoding) { set_error("encode call outside encodeStart()...encodeFinish()"); return ISSCABAC_ERR_STATE; }
   h->pending.push_back((uint16_t)op);
+  if (h->trace) h->enc_log.push_back((uint16_t)op);
   if (h->pending.size() >= (1u << 20)) return enc_flush(h, false);
   return ISSCABAC_OK;
 }
@@ -391,6 +399,8 @@ int simplecabac_decode_ops(simplecabac* h, const uint16_t* ops, uint32_t n, uint
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->st));
   memcpy(bins, h->h_bins, n);
+  if (h->trace)
+    for (uint32_t i = 0; i < n; ++i) h->dec_log.push_back((uint16_t)((ops[i] & ~1u) | (bins[i] & 1u)));
   return ISSCABAC_OK;
 }
 
@@ -435,6 +445,63 @@ int simplecabac_decode_finish(simplecabac* h) {
   CK(cudaStreamSynchronize(h->st));
   h->decoding = false;
   if (!ok) { set_error("terminate bin / stop bit check failed (Decoder::finish asserts)"); return ISSCABAC_ERR_CORRUPT; }
+  return ISSCABAC_OK;
+}
+
+int simplecabac_set_trace(simplecabac* h, int on) {
+  if (!h) return ISSCABAC_ERR_INVALID;
+  h->trace = on != 0;
+  return ISSCABAC_OK;
+}
+
+// getEncoderStats / getDecoderStats (SimpleCABACMex.cpp:356-466) for one context.  The state
+// sequence of a context depends only on the bins coded with it, so the history is filtered to
+// that context on the host and walked by the device trace kernel (stats.cu) as a one-context,
+// one-stream job.
+int simplecabac_get_stats(simplecabac* h, int decoder_set, unsigned ctx_idx, uint8_t* steps5, uint64_t cap_steps,
+                          uint64_t* n_steps, uint32_t* trans) {
+  if (!h || ctx_idx >= kMaxCtx) { set_error("simplecabac_get_stats: bad handle or context index"); return ISSCABAC_ERR_INVALID; }
+  if (!h->trace) { set_error("tracing is off for this handle (simplecabac_set_trace)"); return ISSCABAC_ERR_STATE; }
+  const std::vector<uint16_t>& log = decoder_set ? h->dec_log : h->enc_log;
+  std::vector<uint8_t> ops;   // u8 op format, context 0
+  for (uint16_t o : log)
+    if ((unsigned)(o >> 1) == ctx_idx) ops.push_back((uint8_t)(o & 1u));
+  const uint64_t n = ops.size();
+  if (n_steps) *n_steps = n;
+  if (trans) memset(trans, 0, 128 * 128 * 4);
+  if (n == 0) return ISSCABAC_OK;
+  uint8_t* d = nullptr;   // [ops n | pad | off 16 | ctx 8 | hist 1024 | trans 65536 | steps 2n]
+  const size_t o_off = (n + 7) & ~(size_t)7, o_ctx = o_off + 16, o_hist = o_ctx + 8, o_trans = o_hist + 1024,
+               o_steps = o_trans + 65536, total = o_steps + 2 * n;
+  CK(cudaMalloc((void**)&d, total));
+  const uint64_t off[2] = {0, n};
+  const uint8_t ctx0 = h->init_bytes[ctx_idx];
+  cudaError_t e = cudaMemcpyAsync(d, ops.data(), n, cudaMemcpyHostToDevice, h->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_off, off, 16, cudaMemcpyHostToDevice, h->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_ctx, &ctx0, 1, cudaMemcpyHostToDevice, h->st);
+  int rc = e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "cudaMemcpyAsync(trace)");
+  if (!rc)
+    rc = cabac_ctx_trace_ops(1, reinterpret_cast<uint64_t*>(d + o_off), d, 1, d + o_ctx, 1, 0, 1,
+                             reinterpret_cast<uint64_t*>(d + o_hist), reinterpret_cast<uint32_t*>(d + o_trans), nullptr,
+                             d + o_steps, nullptr, h->st);
+  std::vector<uint8_t> st2(2 * n);
+  if (!rc) {
+    e = cudaMemcpyAsync(st2.data(), d + o_steps, 2 * n, cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess && trans) e = cudaMemcpyAsync(trans, d + o_trans, 65536, cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "trace read-back");
+  }
+  cudaFree(d);
+  if (rc) return rc;
+  auto ts = [](uint32_t b) { return (b & 1u) ? (b >> 1) + 64u : 63u - (b >> 1); };   // ContextModel.cpp:128-129
+  for (uint64_t i = 0; i < n && i < cap_steps && steps5; ++i) {
+    const uint32_t p = st2[2 * i], a = st2[2 * i + 1];
+    steps5[5 * i + 0] = decoder_set ? 0 : ops[i];   // the reference decoder logs the bin before decoding it
+    steps5[5 * i + 1] = (uint8_t)ts(p);
+    steps5[5 * i + 2] = (uint8_t)(p & 1u);
+    steps5[5 * i + 3] = (uint8_t)ts(a);
+    steps5[5 * i + 4] = (uint8_t)(a & 1u);
+  }
   return ISSCABAC_OK;
 }
 

@@ -385,3 +385,47 @@ def iss_ctx_from_counters(cfg: SymCfg, counters, equal_prob: bool = False):
     st = np.zeros((g, nctx), dtype=np.uint8)
     check(lib().cabac_iss_ctx_from_counters(C.byref(cfg), vp(c), C.c_uint32(g), int(bool(equal_prob)), vp(p0), vp(q), vp(st)))
     return p0, q, st
+
+
+# ------------------------------------------------------------------------------------
+# statistics outputs (ctxHist / ctxCost of cabacEncode.m:40-65, trace members of ContextModel.cpp:97-134)
+# ------------------------------------------------------------------------------------
+@dataclass
+class CtxTrace:
+    state_hist: torch.Tensor             # int64 [groups, n_ctx, 128] visits per trace state before each update
+    trans: torch.Tensor | None           # int32 [groups, n_ctx, 128, 128] (u32 values) [before][after]
+    cost_bits: torch.Tensor | None       # int64 [groups, n_ctx + 1]; last slot = bypass + terminate bins
+    step_states: torch.Tensor | None     # u8 [n_ops, 2] state byte before / after (0xFF for non-context ops)
+    final_ctx: torch.Tensor | None       # u8 [n_streams, n_ctx]
+
+    @property
+    def usage(self) -> torch.Tensor:
+        """bins coded per context (ctxHist of cabacEncode.m:40,61)"""
+        return self.state_hist.sum(-1)
+
+
+def trace_state(state_byte):
+    """Trace-state index of a context state byte (ContextModel.cpp:99-101)."""
+    b = np.asarray(state_byte).astype(np.int64)
+    return np.where(b & 1, (b >> 1) + 64, 63 - (b >> 1))
+
+
+def ctx_trace_ops(ops, op_off, ctx_init, streams_per_group: int = 1, want_trans: bool = False, want_cost: bool = False,
+                  want_steps: bool = False, want_final: bool = False) -> CtxTrace:
+    """One pass over the op arrays on the device; see cabac_ctx_trace_ops in include/isscabac.h."""
+    dev = _require_cuda()
+    ops_t, width = _ops_tensor(ops, dev)
+    off_t = _dev(op_off, torch.int64, dev)
+    n = off_t.numel() - 1
+    ctx_t, n_ctx, per = _ctx_tensor(ctx_init, n, dev)
+    spg = max(int(streams_per_group), 1)
+    groups = max((n + spg - 1) // spg, 1)
+    n_ops = ops_t.numel() // width
+    hist = torch.empty((groups, n_ctx, 128), dtype=torch.int64, device=dev)
+    trans = torch.empty((groups, n_ctx, 128, 128), dtype=torch.int32, device=dev) if want_trans else None
+    cost = torch.empty((groups, n_ctx + 1), dtype=torch.int64, device=dev) if want_cost else None
+    steps = torch.empty((max(n_ops, 1), 2), dtype=torch.uint8, device=dev) if want_steps else None
+    final = torch.empty((max(n, 1), n_ctx), dtype=torch.uint8, device=dev) if want_final else None
+    check(lib().cabac_ctx_trace_ops(C.c_uint32(n), vp(off_t), vp(ops_t), width, vp(ctx_t), C.c_uint32(n_ctx), per,
+                                    C.c_uint32(spg), vp(hist), vp(trans), vp(cost), vp(steps), vp(final), _stream_ptr()))
+    return CtxTrace(hist, trans, cost, steps[:n_ops] if want_steps else None, final[:n] if want_final else None)

@@ -54,6 +54,39 @@ def SimpleCABACMex(cmd, *args, nargout=None):
     return None
 
 
+def SimpleCABACMexStats(cmd, handle, ctxID, nargout=2):
+    """[trace, stats] = SimpleCABACMex('getEncoderStats' | 'getDecoderStats', handle, ctxID)
+    (SimpleCABACMex.cpp:356-466, Windows builds of the reference).  -> (trace uint8 [5, M] as MATLAB
+    sees it, stats uint32 [128, 128] in MATLAB's column-major view: stats[a, p] = transitions p -> a)."""
+    allargs = (cmd, handle, ctxID)
+    arr = (MxArg * 3)()
+    keep = []
+    for i, a in enumerate(allargs):
+        if isinstance(a, str):
+            b = a.encode()
+            keep.append(b)
+            arr[i] = MxArg(1, b, None, 1, len(b))
+        else:
+            d = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+            keep.append(d)
+            arr[i] = MxArg(0, None, d.ctypes.data_as(f64p), 1, d.size)
+    err = C.create_string_buffer(512)
+    n = C.c_uint64(0)
+    trans = np.zeros(128 * 128, dtype=np.uint32)
+    L = lib()
+    rc = L.simplecabac_dispatch_stats(int(nargout), 3, arr, None, C.c_uint64(0), C.byref(n), None, err, 512)
+    if rc != 0:
+        raise MexError(err.value.decode(errors="replace"))
+    steps = np.zeros(max(int(n.value), 1) * 5, dtype=np.uint8)
+    rc = L.simplecabac_dispatch_stats(int(nargout), 3, arr, steps.ctypes.data_as(C.c_void_p), C.c_uint64(int(n.value)),
+                                      C.byref(n), trans.ctypes.data_as(C.c_void_p), err, 512)
+    if rc != 0:
+        raise MexError(err.value.decode(errors="replace"))
+    m = int(n.value)
+    # memory order of the reference: trace[entry*5 + k] in a 5 x M matrix, stats[p*128 + a] in a 128 x 128 one
+    return steps[:5 * m].reshape(m, 5).T.copy(), trans.reshape(128, 128).T.copy()
+
+
 class cabacWrapper:
     """CABAC/cabacWrapper.m -- thin 1:1 forwarding to the MEX commands."""
 
@@ -92,6 +125,18 @@ class cabacWrapper:
 
     def getNumBits(self):
         return int(SimpleCABACMex("getNumBits", self.cabac_handle))
+
+    def setTrace(self, on=1):
+        """Not in the reference: its Windows builds always trace, its Linux builds never do."""
+        SimpleCABACMex("setTrace", self.cabac_handle, on)
+
+    def getEncoderStats(self, ctxID):
+        """cabacWrapper.m:69-71 -> (trace, stats)"""
+        return SimpleCABACMexStats("getEncoderStats", self.cabac_handle, ctxID)
+
+    def getDecoderStats(self, ctxID):
+        """cabacWrapper.m:72-74 -> (trace, stats)"""
+        return SimpleCABACMexStats("getDecoderStats", self.cabac_handle, ctxID)
 
     def close(self):
         """Not in the reference (its instances leak by design): releases the GPU-side state."""

@@ -105,6 +105,31 @@ void decode_symbols(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) 
   }
 }
 
+// [trace, stats] = SimpleCABACMex('getEncoderStats' | 'getDecoderStats', handle, ctxIdx): the typed
+// outputs of SimpleCABACMex.cpp:374,393 (uint8 5 x M, uint32 128 x 128), filled in the same memory order
+void stats(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  std::vector<isscabac_mxarg> args((size_t)nrhs);
+  std::vector<std::string> strs((size_t)nrhs);
+  memset(args.data(), 0, args.size() * sizeof(isscabac_mxarg));
+  for (int i = 0; i < nrhs; ++i) {
+    if (mxIsClass(prhs[i], "char")) {
+      char* c = mxArrayToString(prhs[i]);
+      strs[i] = c ? c : "";
+      args[i].is_char = 1; args[i].s = strs[i].c_str(); args[i].m = 1; args[i].n = (int32_t)strs[i].size();
+    } else {
+      args[i].d = mxGetPr(prhs[i]); args[i].m = (int32_t)mxGetM(prhs[i]); args[i].n = (int32_t)mxGetN(prhs[i]);
+    }
+  }
+  static char err[512];
+  uint64_t n = 0;
+  if (simplecabac_dispatch_stats(nlhs, nrhs, args.data(), nullptr, 0, &n, nullptr, err, (int)sizeof err)) mexErrMsgTxt(err);
+  plhs[0] = mxCreateNumericMatrix(5, (size_t)n, mxUINT8_CLASS, mxREAL);
+  plhs[1] = mxCreateNumericMatrix(128, 128, mxUINT32_CLASS, mxREAL);
+  if (simplecabac_dispatch_stats(nlhs, nrhs, args.data(), (uint8_t*)mxGetData(plhs[0]), n, &n,
+                                 (uint32_t*)mxGetData(plhs[1]), err, (int)sizeof err))
+    mexErrMsgTxt(err);
+}
+
 }  // namespace
 
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
@@ -113,6 +138,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     const std::string cmd(c ? c : "");
     if (cmd == "encodeSymbols") { encode_symbols(nlhs, plhs, nrhs, prhs); return; }
     if (cmd == "decodeSymbols") { decode_symbols(nlhs, plhs, nrhs, prhs); return; }
+    if (cmd == "getEncoderStats" || cmd == "getDecoderStats") { stats(nlhs, plhs, nrhs, prhs); return; }
   }
   // the reference's own command set: repack and dispatch
   std::vector<isscabac_mxarg> args((size_t)(nrhs > 0 ? nrhs : 1));

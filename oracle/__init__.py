@@ -42,7 +42,7 @@ def build(force: bool = False) -> None:
     """Compile the C restatement and, when the reference tree is present, oracle/_ref."""
     need = force or not os.path.exists(os.path.join(HERE, "liboracle_cabac.so"))
     if os.path.isdir(REF_DIR):
-        for f in ("libref_cabac.so", "libref_mex.so"):
+        for f in ("libref_cabac.so", "libref_mex.so", "libref_mex_trace.so"):
             need = need or not os.path.exists(os.path.join(HERE, "_ref", f))
     if need or force:
         subprocess.run(["make", "-C", HERE, "all"] + (["-B"] if force else []),
@@ -110,6 +110,21 @@ def ref_mex():
             build()
         _MEX = C.CDLL(p) if os.path.exists(p) else False
     return _MEX or None
+
+
+_MEXT = None
+
+
+def ref_mex_trace():
+    """The unmodified reference mexFunction built with -D_WIN32, i.e. with the reference's
+    RWTH_TRACE_CABAC_STATES code (getEncoderStats / getDecoderStats) compiled in."""
+    global _MEXT
+    if _MEXT is None:
+        p = os.path.join(HERE, "_ref", "libref_mex_trace.so")
+        if not os.path.exists(p) and os.path.isdir(REF_DIR):
+            build()
+        _MEXT = C.CDLL(p) if os.path.exists(p) else False
+    return _MEXT or None
 
 
 def tmpdir() -> str:
@@ -391,11 +406,11 @@ class _MexArg(C.Structure):
                 ("m", C.c_int), ("n", C.c_int)]
 
 
-def mex_call(nlhs, *args):
+def mex_call(nlhs, *args, trace_build=False):
     """Drive the reference mexFunction: args are str or array-likes of doubles.
     -> (rc, outputs list[float], error text)  rc 1 = mexErrMsgTxt raised."""
-    m = ref_mex()
-    assert m is not None, "oracle/_ref/libref_mex.so not built"
+    m = ref_mex_trace() if trace_build else ref_mex()
+    assert m is not None, "oracle/_ref/libref_mex*.so not built"
     keep = []
     arr = (_MexArg * max(len(args), 1))()
     for i, a in enumerate(args):
@@ -414,6 +429,42 @@ def mex_call(nlhs, *args):
     err = C.create_string_buffer(512)
     rc = m.refmex_call(int(nlhs), out, 16, C.byref(out_n), len(args), arr, err, 512)
     return rc, [out[i] for i in range(out_n.value)], err.value.decode(errors="replace")
+
+
+def mex_stats(handle: float, ctx_idx: int, decoder: bool = False, cap_steps: int = 1 << 20):
+    """getEncoderStats / getDecoderStats of the trace build -> (steps uint8 [M, 5], trans uint32 [128, 128]
+    indexed [state_p, state_a] in the reference's memory order)."""
+    m = ref_mex_trace()
+    assert m is not None
+    m.refmex_stats.restype = C.c_long
+    steps = np.zeros((cap_steps, 5), dtype=np.uint8)
+    trans = np.zeros((128, 128), dtype=np.uint32)
+    err = C.create_string_buffer(512)
+    n = m.refmex_stats(int(bool(decoder)), C.c_double(handle), int(ctx_idx), _p(steps, _u8p), C.c_long(cap_steps),
+                       _p(trans, _u32p), err, 512)
+    if n < 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return steps[:n].copy(), trans
+
+
+# pure-Python restatement of the trace members (ContextModel.cpp:97-134, SimpleCABACMex.cpp:231-241,
+# 318-327): state sequence of ONE context given the bins coded with it.  decoder=True mirrors the
+# reference decoder's log, which records the bin variable BEFORE decodeBin fills it in (always 0).
+def trace_context(init_byte: int, bins, decoder: bool = False):
+    L = lib()
+    st = int(init_byte) & 127
+    steps = np.zeros((len(bins), 5), dtype=np.uint8)
+    trans = np.zeros((128, 128), dtype=np.uint32)
+    hist = np.zeros(128, dtype=np.uint64)
+    ts = lambda b: (b >> 1) + 64 if (b & 1) else 63 - (b >> 1)
+    for i, b in enumerate(bins):
+        nxt = int(L.orc_ctx_next_mps(st)) if (int(b) & 1) == (st & 1) else int(L.orc_ctx_next_lps(st))
+        # addCabacStep gets the raw state numbers and logs the TRACE states (ContextModel.cpp:128-132)
+        steps[i] = (0 if decoder else int(b), ts(st), st & 1, ts(nxt), nxt & 1)
+        hist[ts(st)] += 1
+        trans[ts(st), ts(nxt)] += 1
+        st = nxt
+    return steps, trans, hist
 
 
 def ref_prob_to_state(p0) -> np.ndarray:

@@ -249,6 +249,44 @@ def gen_symbols():
     np.savez_compressed(os.path.join(OUT, "symbols_refengine.npz"), **cases)
 
 
+def gen_trace():
+    """getEncoderStats / getDecoderStats of the reference's trace build (oracle/_ref/libref_mex_trace.so =
+    the unmodified SimpleCABACMex.cpp with -D_WIN32, CommonDef.h:39-40): step logs and transition counts
+    of every context, plus getNumBits() after every bin (the ctxCost of cabacEncode.m:63-65)."""
+    rng = np.random.default_rng(77)
+    p0 = [0.3, 0.7, 0.5, 0.92]
+    fn = os.path.join(O.tmpdir(), "golden_trace.bin")
+    rc, out, err = O.mex_call(1, "initByProb", fn, p0, trace_build=True)
+    assert rc == 0, err
+    h = out[0]
+    O.mex_call(0, "encodeStart", [h], trace_build=True)
+    seq, bits = [], []
+    pr = [0.3, 0.7, 0.5, 0.05]
+    for _ in range(1200):
+        c = int(rng.integers(0, 4))
+        b = int(rng.random() < pr[c])
+        seq.append([b, c])
+        rc, _, err = O.mex_call(0, "encodeBin", [h], [b], [c], trace_build=True)
+        assert rc == 0, err
+        bits.append(int(O.mex_call(1, "getNumBits", [h], trace_build=True)[1][0]))
+    O.mex_call(0, "encodeFinish", [h], trace_build=True)
+    data = open(fn, "rb").read()
+    O.mex_call(0, "decodeStart", [h], trace_build=True)
+    for b, c in seq:
+        rc, out, err = O.mex_call(1, "decodeBin", [h], [c], trace_build=True)
+        assert rc == 0 and int(out[0]) == b
+    O.mex_call(0, "decodeFinish", [h], trace_build=True)
+    res = {"p0": p0, "seq": seq, "bits_after_bin": bits, "bytes": data.hex(), "enc": [], "dec": []}
+    for c in range(4):
+        for key, dec in (("enc", False), ("dec", True)):
+            steps, trans = O.mex_stats(h, c, decoder=dec)
+            nz = np.argwhere(trans)
+            res[key].append({"steps": steps.reshape(-1).tolist(),
+                             "trans": [[int(a), int(b), int(trans[a, b])] for a, b in nz]})
+    with open(os.path.join(OUT, "mex_trace.json"), "w") as f:
+        json.dump(res, f)
+
+
 if __name__ == "__main__":
     assert O.ref() is not None, "needs oracle/_ref (build container with /root/reference)"
     os.makedirs(OUT, exist_ok=True)
@@ -260,4 +298,5 @@ if __name__ == "__main__":
     gen_prob()
     gen_mex()
     gen_symbols()
+    gen_trace()
     print("golden vectors written to", OUT)

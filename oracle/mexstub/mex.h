@@ -18,8 +18,12 @@ struct mxArray {
   std::string s;
   std::vector<double> d;
   size_t m = 0, n = 0;
+  // typed numeric matrices (mxCreateNumericMatrix): raw little-endian element storage
+  int class_id = 0;                 // 0 = double / char, else mxUINT8_CLASS / mxUINT32_CLASS
+  std::vector<unsigned char> raw;
 };
 enum mxComplexity { mxREAL = 0, mxCOMPLEX = 1 };
+enum mxClassID { mxDOUBLE_CLASS = 6, mxUINT8_CLASS = 9, mxUINT32_CLASS = 13 };   // MATLAB's own numbering
 
 struct MexStubError : public std::runtime_error {
   explicit MexStubError(const char* msg) : std::runtime_error(msg) {}
@@ -47,6 +51,16 @@ inline mxArray* mxCreateDoubleMatrix(size_t m, size_t n, mxComplexity) {
   mxArray* a = new mxArray;
   a->m = m; a->n = n; a->d.assign(m * n, 0.0);
   return a;
+}
+inline mxArray* mxCreateNumericMatrix(size_t m, size_t n, mxClassID cls, mxComplexity) {
+  mxArray* a = new mxArray;
+  a->m = m; a->n = n; a->class_id = (int)cls;
+  if (cls == mxDOUBLE_CLASS) { a->class_id = 0; a->d.assign(m * n, 0.0); }
+  else a->raw.assign(m * n * (cls == mxUINT32_CLASS ? 4 : 1), 0);
+  return a;
+}
+inline void* mxGetData(const mxArray* a) {
+  return a->class_id ? (void*)const_cast<unsigned char*>(a->raw.data()) : (void*)const_cast<double*>(a->d.data());
 }
 inline size_t mxGetNumberOfElements(const mxArray* a) { return a->is_char ? a->s.size() : a->d.size(); }
 inline size_t mxGetM(const mxArray* a) { return a->m; }

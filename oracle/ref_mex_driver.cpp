@@ -47,6 +47,34 @@ int refmex_call(int nlhs, double* out, int out_cap, int* out_n,
   return 0;
 }
 
+#if RWTH_TRACE_CABAC_STATES
+// getEncoderStats / getDecoderStats (SimpleCABACMex.cpp:356-466; compiled in only when the
+// reference is built the way its Windows project builds it, -D_WIN32 -> CommonDef.h:39-40).
+// steps: 5 bytes per step [bin state_p mps_p state_a mps_a]; trans: 128*128 u32 in the
+// reference's memory order (index state_p*128 + state_a).  Returns the number of steps, -1 on
+// a mexErrMsgTxt (text in err).
+long refmex_stats(int decoder, double handle, int ctx_idx, unsigned char* steps, long cap_steps, unsigned* trans,
+                  char* err, int errcap) {
+  mxArray cmd, h, c;
+  cmd.is_char = true; cmd.s = decoder ? "getDecoderStats" : "getEncoderStats";
+  h.d.assign(1, handle); h.m = h.n = 1;
+  c.d.assign(1, (double)ctx_idx); c.m = c.n = 1;
+  const mxArray* prhs[3] = {&cmd, &h, &c};
+  mxArray* plhs[2] = {nullptr, nullptr};
+  try {
+    mexFunction(2, plhs, 3, prhs);
+  } catch (const MexStubError& e) {
+    if (err && errcap > 0) { strncpy(err, e.what(), errcap - 1); err[errcap - 1] = 0; }
+    return -1;
+  }
+  long n = plhs[0] ? (long)plhs[0]->n : 0;
+  if (plhs[0] && steps) memcpy(steps, plhs[0]->raw.data(), (size_t)(n < cap_steps ? n : cap_steps) * 5);
+  if (plhs[1] && trans) memcpy(trans, plhs[1]->raw.data(), 128 * 128 * 4);
+  delete plhs[0]; delete plhs[1];
+  return n;
+}
+#endif
+
 // p(0) -> (state<<1)|mps through the reference's own initContextModelsByP0Prob
 // (CABAC_ContextModelsInit.cpp:82-148); n < 1000.
 int refmex_prob_to_state(const double* p0, int n, unsigned char* out) {

@@ -3,6 +3,7 @@
 //   argv[1] = scratch bitstream file.  Exit code 0 = all checks passed.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "mex.h"
@@ -41,6 +42,21 @@ int main(int argc, char** argv) {
     for (double v : a) bad += call(1, {str("decodeBin"), h, vec({0})})[0]->d[0] != v;
     for (double v : b) bad += call(1, {str("decodeBin"), h, vec({1})})[0]->d[0] != v;
     call(0, {str("decodeFinish"), h});
+    // --- trace statistics (Windows builds of the reference): typed outputs, 5 x M uint8 + 128 x 128 uint32
+    {
+      mxArray* t = call(1, {str("initByState"), str(fn), vec({0, 1, 0})})[0];   // one context, (mps 1, state 0)
+      call(0, {str("setTrace"), t, vec({1})});
+      call(0, {str("encodeStart"), t});
+      for (double v : {1.0, 1.0, 0.0}) call(0, {str("encodeBin"), t, vec({v}), vec({0})});
+      call(0, {str("encodeFinish"), t});
+      std::vector<mxArray*> st = call(2, {str("getEncoderStats"), t, vec({0})});
+      // states: (1,0) -> MPS -> (1,1) -> MPS -> (1,2) -> LPS -> next_lps(state 2) ; trace state = state + 64
+      const unsigned char want[10] = {1, 64, 1, 65, 1, 1, 65, 1, 66, 1};
+      bad += !(st[0]->m == 5 && st[0]->n == 3 && st[0]->raw.size() == 15 && memcmp(st[0]->raw.data(), want, 10) == 0);
+      bad += !(st[0]->raw[10] == 0 && st[0]->raw[11] == 66);
+      const unsigned* tr = (const unsigned*)st[1]->raw.data();
+      bad += !(st[1]->raw.size() == 128 * 128 * 4 && tr[64 * 128 + 65] == 1 && tr[65 * 128 + 66] == 1);
+    }
     // an error must surface as mexErrMsgTxt with the reference's text
     try { call(0, {str("bogus")}); bad += 1; } catch (const MexStubError& e) { bad += std::string(e.what()).find("Invalid Command") == std::string::npos; }
     // --- batch commands: a 50 x 4 matrix, ISS profile, one stream per column
