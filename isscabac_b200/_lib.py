@@ -38,9 +38,14 @@ class MxArg(C.Structure):
 def lib() -> C.CDLL:
     global _LIB
     if _LIB is None:
-        path = _build.LIB
-        if _build.needs_build():
-            path = _build.build()
+        path = os.environ.get("ISSCABAC_LIB")      # a tuning variant built by build.build_variant()
+        if path:
+            if not os.path.exists(path):
+                raise FileNotFoundError(f"ISSCABAC_LIB={path} does not exist")
+        else:
+            path = _build.LIB
+            if _build.needs_build():
+                path = _build.build()
         L = C.CDLL(path)
         L.isscabac_strerror.restype = C.c_char_p
         L.isscabac_last_error.restype = C.c_char_p

@@ -46,5 +46,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Tuning aid (tools/tune.py): the same sources with extra -D flags -> isscabac_b200/_variants/lib<name>.so.
+    Select it at run time with ISSCABAC_LIB=<path> (see _lib.py)."""
+    out_dir = os.path.join(HERE, "_variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"lib{name}.so")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-x", "cu"] + srcs + ["-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError(f"nvcc failed building variant {name}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -96,6 +96,19 @@ CB_HD uint32_t cb_xor_and1(uint32_t a, uint32_t b) {
   return (a ^ b) & 1u;
 #endif
 }
+// (a ^ b) & mask as ONE three-input logic op whose result the optimiser cannot see through (it
+// would otherwise turn the selects that test it into shift/mask arithmetic); ptxas folds the
+// "!= 0" test of the caller into the predicate output of the same LOP3
+template <uint32_t MASK>
+CB_HD uint32_t cb_xor_and(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(d) : "r"(a), "r"(b), "n"(MASK));
+  return d;
+#else
+  return (a ^ b) & MASK;
+#endif
+}
 CB_HD uint32_t cb_keep32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
   asm volatile("" : "+r"(v));

@@ -36,12 +36,59 @@ namespace cabac {
 constexpr uint32_t kEpState = 128;     // dummy state byte of the bypass slot
 constexpr uint32_t kNumRows = 129;     // fused rows 0..127 + the bypass row
 
-// rows as the wide kernels use them: x = four LPS sub-ranges, y = nextMPS | nextLPS << 8
-CB_HD constexpr uint2 wide_row(uint32_t st) {
-  return st < 128 ? fused_row(st) : uint2{0u, kEpState | (kEpState << 8)};
+// Rows as the wide kernels use them.  A context slot does not hold the state byte but a TOKEN for
+// it: on the device the shared-memory address of this lane's copy of the state's row, in the host
+// emulation the state byte itself.  The row load therefore needs no address arithmetic, and the
+// next token comes straight out of the row (one select) instead of being extracted from a packed
+// byte pair and turned into an address again.  mps4 = the MPS bit replicated into bit 0 of every
+// byte, so that "is this bin the LPS" is one logic op against the op word whatever byte of the
+// word the op sits in.
+struct alignas(16) WRow {
+  uint32_t lps4;       // four LPS sub-ranges (0 for the bypass row)
+  uint32_t next_mps;   // token of the state after an MPS
+  uint32_t next_lps;   // token of the state after an LPS
+  uint32_t mps4;       // (st & 1) * 0x01010101
+};
+// the row in terms of state bytes (next_* = state bytes): the host emulation uses it as is, the
+// device table replaces the two next states by tokens
+CB_HD constexpr WRow wide_row(uint32_t st) {
+  return st < 128 ? WRow{fused_row(st).x, next_mps(st), next_lps(st), (st & 1u) * 0x01010101u}
+                  : WRow{0u, kEpState, kEpState, 0u};
 }
 
 CB_HD uint32_t cb_bswap(uint32_t x) { return cb_perm(x, 0, 0x0123); }
+
+// Warp vote: true when `p` holds for any lane executing this call together with the caller (the
+// host emulation is one lane).  Used to move words out of / into the window LAZILY: with 32
+// unrelated streams per warp some lane crosses the 32-bit mark at almost every check, so an eager
+// "if (n >= 32) emit" makes the whole warp walk through the emission code on every check with a
+// tenth of its lanes active.  Waiting until some lane is about to run out of window lets all lanes
+// that have a full word move it at the same time, a third as often.
+#ifndef CABAC_LAZY
+#define CABAC_LAZY 1
+#endif
+// VOTE = all 32 lanes of the warp execute this call together (the caller guarantees it: the kernels
+// walk the blocks every lane of a full warp has in lockstep); otherwise this lane decides alone
+template <bool VOTE>
+CB_HD bool cb_any(bool p) {
+#if defined(__CUDA_ARCH__) && CABAC_LAZY
+  return VOTE ? __any_sync(0xffffffffu, p) != 0 : p;
+#else
+  return p;
+#endif
+}
+
+// Window budget of a 4-bin group (<= 6 bits per bin, the window holds 53): a lane enters the group
+// with at most kLazy-1 = 41 bits, may reach 53 after two bins, is brought back under 32 by the
+// mid-group guard if it passed 41, and leaves the group with at most 53.
+constexpr int kLazy = CABAC_LAZY ? 42 : 32;
+// The decoder's refill is kept eager: the lazy schedule needs the mid-group guard on top of the
+// vote, and the decoder is bound by its decision -> token -> row chain, not by instruction count
+// (measured on B200: 517 eager vs 520 lazy Gbins/s, inside the run-to-run spread).
+#ifndef CABAC_LAZY_DEC
+#define CABAC_LAZY_DEC 0
+#endif
+constexpr int kLazyDec = CABAC_LAZY_DEC ? 42 : 32;
 
 // ---------------------------------------------------------------------------
 // encoder
@@ -102,12 +149,13 @@ CB_HD void encw_emit(EncWide& E) {
   }
 }
 
-// One bin, context-coded or bypass (see the file header).  st = state byte of the slot the
-// op addresses (kEpState for a bypass op), row = wide_row(st); returns the new state byte.
-CB_HD uint32_t encw_bin(EncWide& E, uint32_t o, bool is_ep, uint32_t st, uint2 row) {
-  const uint32_t lps = cb_prmt(0, row.x, E.range >> 6);   // selector 4..7 = row.x byte q (range is 256..510)
+// One bin, context-coded or bypass (see the file header).  row = the row of the slot the op
+// addresses (the bypass row for a bypass op); the bin is bit 8*B of `w`.  Returns the new token.
+template <int B>
+CB_HD uint32_t encw_bin(EncWide& E, uint32_t w, bool is_ep, const WRow& row) {
+  const uint32_t lps = cb_prmt(0, row.lps4, E.range >> 6);   // selector 4..7 = lps4 byte q (range is 256..510)
   const uint32_t rmps = E.range - lps;
-  const uint32_t is_lps = cb_xor_and1(st, o);
+  const uint32_t is_lps = cb_xor_and<(1u << (8 * B))>(row.mps4, w);   // non-zero = LPS
   const uint32_t x2 = is_ep ? E.range : 2u * rmps;
   const uint32_t rsel = is_lps ? lps : rmps;
   const int nn = cb_clz(rsel | 4u) - 23;     // min(clz(rsel)-23, 6): Encoder.cpp:482-492 incl. the state-63 row
@@ -117,7 +165,7 @@ CB_HD uint32_t encw_bin(EncWide& E, uint32_t o, bool is_ep, uint32_t st, uint2 r
   E.W = W << ns;
   E.range = is_ep ? E.range : (rsel << nn);
   E.n += ns;
-  return cb_prmt(row.y, 0, is_lps | 0x4440u);
+  return is_lps ? row.next_lps : row.next_mps;
 }
 
 // encodeBinTrm, Encoder.cpp:326-367 (the only op that is a real branch; a handful per stream)
@@ -223,13 +271,14 @@ CB_HD void decw_start(DecWide& D, const uint8_t* in, uint32_t len) {
   decw_refill(D);   // bytes 3..6
 }
 
-// One bin, context-coded or bypass; returns the bin, st is updated in place.
-CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, uint32_t& st, uint2 row) {
-  const uint32_t lps = cb_prmt(0, row.x, D.range >> 6);
+// One bin, context-coded or bypass; returns the bin in bit 8*B (all other bits 0), tok = the new token.
+template <int B>
+CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, uint32_t& tok, const WRow& row) {
+  const uint32_t lps = cb_prmt(0, row.lps4, D.range >> 6);
   const uint32_t rmps = D.range - lps;
   const uint32_t x2 = is_ep ? D.range : 2u * rmps;
   const uint32_t scaled = x2 << 21;                        // reference: scaledRange << 15 (bypass: compare before the shift)
-  const uint32_t is_lps = D.hi >= scaled ? 1u : 0u;
+  const bool is_lps = D.hi >= scaled;
   const uint32_t rsel = is_lps ? lps : rmps;
   const int nn = cb_clz(rsel | 4u) - 23;
   const int ns = is_ep ? 1 : nn;
@@ -238,9 +287,8 @@ CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, uint32_t& st, uint2 row) {
   D.lo <<= ns;
   D.range = is_ep ? D.range : (rsel << nn);
   D.f += ns;
-  const uint32_t bin = (st ^ is_lps) & 1u;
-  st = cb_prmt(row.y, 0, is_lps | 0x4440u);
-  return bin;
+  tok = is_lps ? row.next_lps : row.next_mps;
+  return (row.mps4 ^ (is_lps ? 0xffffffffu : 0u)) & (1u << (8 * B));   // bin = mps ^ isLPS
 }
 
 // decodeBinTrm, Decoder.cpp:423-472
@@ -289,31 +337,30 @@ CB_HD bool block_has_trm(const uint32_t cw[4]) {
   return ((h0 | h1 | h2 | h3) & 0x80808080u) != 0u;
 }
 
-// Context storage as the kernels see it: slot c of this lane, c == n_ctx is the bypass slot.
-// Tab::row(st) returns wide_row(st).  `code` = op >> 1, `ob` = any word whose bit 0 is the bin.
-template <class Ctx, class Tab>
-CB_HD void encw_op(EncWide& E, uint32_t code, uint32_t ob, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
+// Context storage as the kernels see it: slot c of this lane holds a token, c == n_ctx is the
+// bypass slot.  Tab::token(st) = token of a state byte, Tab::row(tok) = its row.  `code` = op >> 1,
+// the bin is bit 8*B of `w`.
+template <int B, class Ctx, class Tab>
+CB_HD void encw_op(EncWide& E, uint32_t code, uint32_t w, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
   const bool is_ep = code > kOpTrmCode;
   const uint32_t c = code < n_ctx ? code : n_ctx;
-  const uint32_t st = ctx.load(c);
-  ctx.store(c, encw_bin(E, ob, is_ep, st, tab.row(st)));
+  ctx.store(c, encw_bin<B>(E, w, is_ep, tab.row(ctx.load(c))));
 }
 
-// 16 ops without a terminate op: 4 x (4 bins, emit).  Worst case 6 bits per bin: n <= 31
-// after an emit, <= 49 after three more bins; the window holds n <= 53, so one early emit is
-// needed only when n > 47 before the fourth bin (never seen outside adversarial inputs).
-template <class Ctx, class Tab>
+// 16 ops without a terminate op: 4 x (2 bins, guard, 2 bins, voted emit); see kLazy for the
+// window budget.  The guard fires for a lane that gained more than 10 bits in two bins.
+template <bool VOTE, class Ctx, class Tab>
 CB_HD void encw_block16(EncWide& E, const uint32_t w[4], const uint32_t cw[4],
                         const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const uint32_t codes = cw[g];   // the four op codes, one per byte
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      if (b == 3 && E.n > 47) encw_emit(E);
-      encw_op(E, cb_prmt(codes, 0, 0x4440u + b), w[g] >> (8 * b), ctx, tab, n_ctx);
-    }
-    encw_emit(E);
+    encw_op<0>(E, cb_prmt(codes, 0, 0x4440u), w[g], ctx, tab, n_ctx);
+    encw_op<1>(E, cb_prmt(codes, 0, 0x4441u), w[g], ctx, tab, n_ctx);
+    if (E.n >= kLazy) encw_emit(E);
+    encw_op<2>(E, cb_prmt(codes, 0, 0x4442u), w[g], ctx, tab, n_ctx);
+    encw_op<3>(E, cb_prmt(codes, 0, 0x4443u), w[g], ctx, tab, n_ctx);
+    if (cb_any<VOTE>(E.n >= kLazy)) encw_emit(E);
   }
 }
 
@@ -322,33 +369,35 @@ CB_HD void encw_block16(EncWide& E, const uint32_t w[4], const uint32_t cw[4],
 template <class Ctx, class Tab>
 CB_HD void encw_general(EncWide& E, uint32_t o, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
   if ((o >> 1) == kOpTrmCode) encw_trm(E, o & 1u);
-  else encw_op(E, o >> 1, o, ctx, tab, n_ctx);
+  else encw_op<0>(E, o >> 1, o, ctx, tab, n_ctx);
   encw_emit(E);
 }
 
-template <class Ctx, class Tab>
+template <int B, class Ctx, class Tab>
 CB_HD uint32_t decw_op(DecWide& D, uint32_t code, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
   const bool is_ep = code > kOpTrmCode;
   const uint32_t c = code < n_ctx ? code : n_ctx;
-  uint32_t st = ctx.load(c);
-  const uint32_t bin = decw_bin(D, is_ep, st, tab.row(st));
-  ctx.store(c, st);
+  uint32_t tok = ctx.load(c);
+  const uint32_t bin = decw_bin<B>(D, is_ep, tok, tab.row(tok));
+  ctx.store(c, tok);
   return bin;
 }
 
 // 16 ops without a terminate op -> 16 bins packed one per byte (little-endian in r[0..3]).
-// f <= 31 after a refill and <= 49 before the fourth bin; decisions need f <= 53.
-template <class Ctx, class Tab>
+// Decisions need f <= 53; same lazy schedule and window budget as the encoder (kLazy).
+template <bool VOTE, class Ctx, class Tab>
 CB_HD void decw_block16(DecWide& D, const uint32_t cw[4], uint32_t r[4],
                         const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const uint32_t codes = cw[g];
-    uint32_t acc = 0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc |= decw_op(D, cb_prmt(codes, 0, 0x4440u + b), ctx, tab, n_ctx) << (8 * b);
+    uint32_t acc = decw_op<0>(D, cb_prmt(codes, 0, 0x4440u), ctx, tab, n_ctx);
+    acc |= decw_op<1>(D, cb_prmt(codes, 0, 0x4441u), ctx, tab, n_ctx);
+    if (CABAC_LAZY_DEC && D.f >= kLazyDec) decw_refill(D);
+    acc |= decw_op<2>(D, cb_prmt(codes, 0, 0x4442u), ctx, tab, n_ctx);
+    acc |= decw_op<3>(D, cb_prmt(codes, 0, 0x4443u), ctx, tab, n_ctx);
     r[g] = acc;
-    decw_refill(D);
+    if (cb_any<(VOTE && CABAC_LAZY_DEC)>(D.f >= kLazyDec)) decw_refill(D);
   }
 }
 
@@ -356,7 +405,7 @@ template <class Ctx, class Tab>
 CB_HD uint32_t decw_general(DecWide& D, uint32_t o, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
   uint32_t bin;
   if ((o >> 1) == kOpTrmCode) bin = decw_trm(D);
-  else bin = decw_op(D, o >> 1, ctx, tab, n_ctx);
+  else bin = decw_op<0>(D, o >> 1, ctx, tab, n_ctx);
   decw_refill(D);
   return bin;
 }

@@ -18,6 +18,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "../../include/isscabac.h"
 #include "cabac_lane.cuh"
 #include "cabac_wide.cuh"
@@ -344,8 +346,8 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_ops_wide(CodecPa
   uint32_t s;
   WCtx ctx;
   WTab tab;
-  uint32_t n_ctx;
-  if (!wide_setup(P.n_streams, P.n_ctx, P.ctx_init, P.per_stream_init, smem, s, ctx, tab, n_ctx)) return;
+  uint32_t n_ctx, vmask;
+  if (!wide_setup(P.n_streams, P.n_ctx, P.ctx_init, P.per_stream_init, smem, s, ctx, tab, n_ctx, &vmask)) return;
   const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
   const uint8_t* p = reinterpret_cast<const uint8_t*>(P.ops) + o0;
   const uint64_t n = o1 - o0;
@@ -361,22 +363,31 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_ops_wide(CodecPa
   p += head;
   const uint64_t nblk = (n - head) >> 4;
   const uint32_t tail = (uint32_t)((n - head) & 15u);
-  // body: 16 ops per load, next block prefetched while this one is coded
+  // body: 16 ops per load, next block prefetched while this one is coded.  In a full warp the
+  // blocks every lane has are walked in lockstep (LOCK): the lazy emission votes across the warp
+  // and a block with a terminate op sends the whole warp down the general path.  Lanes with
+  // longer streams -- and warps with idle lanes -- go on without votes.
+  const uint32_t common = __reduce_min_sync(vmask, (uint32_t)(nblk > 0xffffffffull ? 0xffffffffull : nblk));
   if (nblk) {
     uint4 cur = __ldg(reinterpret_cast<const uint4*>(p));
-    for (uint64_t b = nblk; b != 0; --b) {
+    uint64_t b = 0;
+    auto block = [&](auto lock) {
+      constexpr bool LOCK = decltype(lock)::value;
       uint4 nxt = cur;
-      if (b > 1) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
+      if (b + 1 < nblk) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
       const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
       const uint32_t cw[4] = {op_codes4(cur.x), op_codes4(cur.y), op_codes4(cur.z), op_codes4(cur.w)};
-      if (block_has_trm(cw)) {
+      if (cb_any<LOCK>(block_has_trm(cw))) {
         for (int k = 0; k < 16; ++k) encw_general(E, p[k], ctx, tab, n_ctx);
       } else {
-        encw_block16(E, w, cw, ctx, tab, n_ctx);
+        encw_block16<LOCK>(E, w, cw, ctx, tab, n_ctx);
       }
       cur = nxt;
       p += 16;
-    }
+    };
+    if (vmask == 0xffffffffu)
+      for (; b < common; ++b) block(std::true_type{});
+    for (; b < nblk; ++b) block(std::false_type{});
   }
   for (uint32_t i = 0; i < tail; ++i) encw_general(E, p[i], ctx, tab, n_ctx);
 
@@ -385,13 +396,16 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_ops_wide(CodecPa
   if (len > cap && P.overflow) atomicOr(P.overflow, 1u);
 }
 
-__global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_ops_wide(CodecParams P) {
+#ifndef WIDE_DEC_MINBLOCKS
+#define WIDE_DEC_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, WIDE_DEC_MINBLOCKS) k_decode_ops_wide(CodecParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t s;
   WCtx ctx;
   WTab tab;
-  uint32_t n_ctx;
-  if (!wide_setup(P.n_streams, P.n_ctx, P.ctx_init, P.per_stream_init, smem, s, ctx, tab, n_ctx)) return;
+  uint32_t n_ctx, vmask;
+  if (!wide_setup(P.n_streams, P.n_ctx, P.ctx_init, P.per_stream_init, smem, s, ctx, tab, n_ctx, &vmask)) return;
   const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
   const uint8_t* p = reinterpret_cast<const uint8_t*>(P.ops) + o0;
   uint8_t* q = P.bins + o0;
@@ -409,17 +423,21 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_ops_wide(CodecPa
   const uint64_t nblk = (n - head) >> 4;
   const uint32_t tail = (uint32_t)((n - head) & 15u);
   const bool out_vec = (reinterpret_cast<uintptr_t>(q) & 15u) == 0;  // true whenever ops and bins share their alignment
+  // lockstep blocks first, like the encoder
+  const uint32_t common = __reduce_min_sync(vmask, (uint32_t)(nblk > 0xffffffffull ? 0xffffffffull : nblk));
   if (nblk) {
     uint4 cur = __ldg(reinterpret_cast<const uint4*>(p));
-    for (uint64_t b = nblk; b != 0; --b) {
+    uint64_t b = 0;
+    auto block = [&](auto lock) {
+      constexpr bool LOCK = decltype(lock)::value;
       uint4 nxt = cur;
-      if (b > 1) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
+      if (b + 1 < nblk) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
       const uint32_t cw[4] = {op_codes4(cur.x), op_codes4(cur.y), op_codes4(cur.z), op_codes4(cur.w)};
-      if (block_has_trm(cw)) {
+      if (cb_any<LOCK>(block_has_trm(cw))) {
         for (int k = 0; k < 16; ++k) q[k] = (uint8_t)decw_general(D, p[k], ctx, tab, n_ctx);
       } else {
         uint32_t r[4];
-        decw_block16(D, cw, r, ctx, tab, n_ctx);
+        decw_block16<LOCK>(D, cw, r, ctx, tab, n_ctx);
         if (out_vec) {
           *reinterpret_cast<uint4*>(q) = make_uint4(r[0], r[1], r[2], r[3]);
         } else {
@@ -430,7 +448,10 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_ops_wide(CodecPa
       cur = nxt;
       p += 16;
       q += 16;
-    }
+    };
+    if (vmask == 0xffffffffu)
+      for (; b < common; ++b) block(std::true_type{});
+    for (; b < nblk; ++b) block(std::false_type{});
   }
   for (uint32_t i = 0; i < tail; ++i) q[i] = (uint8_t)decw_general(D, p[i], ctx, tab, n_ctx);
 

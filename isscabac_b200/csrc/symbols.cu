@@ -308,12 +308,13 @@ __global__ void k_order_scatter(const uint64_t* off, uint32_t n, const uint32_t*
 
 struct LaneCtx {
   WCtx ctx;
+  WTab tab;
   uint32_t n_ctx;
   const uint8_t* init;
   int per_stream;
   __device__ __forceinline__ void reset(uint32_t s) const {
     const uint8_t* p = init + (per_stream ? (uint64_t)s * n_ctx : 0);
-    for (uint32_t c = 0; c < n_ctx; ++c) ctx.store(c, p[c] & 127u);
+    for (uint32_t c = 0; c < n_ctx; ++c) ctx.store(c, tab.token(p[c] & 127u));
   }
 };
 
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
   WCtx ctx;
   WTab tab;
   wide_setup(P.n_streams, P.n_ctx, P.ctx_init, 0, smem, s, ctx, tab, n_ctx);   // shared init: reset() below does the rest
-  const LaneCtx lc{ctx, n_ctx, P.ctx_init, P.per_stream_init};
+  const LaneCtx lc{ctx, tab, n_ctx, P.ctx_init, P.per_stream_init};
   const SymCfg cfg = fixed_cfg<PROF, METH>(P.cfg);
   const uint32_t cap = (uint32_t)(P.slab_stride > 0xfffffffcull ? 0xfffffffcull : P.slab_stride);
   EncWide E;
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
           b = 1;
         }
         const int cx = select_ctx(cfg, b, cur.np, prev, up);
-        encw_op(E, cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx, sym_bin(cur, b), ctx, tab, n_ctx);
+        encw_op<0>(E, cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx, sym_bin(cur, b), ctx, tab, n_ctx);
         ++b;
       }
     }
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_symbols_wide(Sym
   WCtx ctx;
   WTab tab;
   wide_setup(P.n_streams, P.n_ctx, P.ctx_init, 0, smem, s, ctx, tab, n_ctx);
-  const LaneCtx lc{ctx, n_ctx, P.ctx_init, P.per_stream_init};
+  const LaneCtx lc{ctx, tab, n_ctx, P.ctx_init, P.per_stream_init};
   const SymCfg cfg = fixed_cfg<PROF, METH>(P.cfg);
   DecWide D;
   decw_start(D, P.bytes, 0);
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_symbols_wide(Sym
     for (int j = 0; j < 4; ++j) {
       if (active && i < cnt) {
         const int cx = select_ctx(cfg, sd.n + 1, sd.np, prev, up);
-        const uint32_t bin = decw_op(D, cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx, ctx, tab, n_ctx);
+        const uint32_t bin = decw_op<0>(D, cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx, ctx, tab, n_ctx);
         uint32_t v = 0;
         if (symdec_push(sd, bin, cfg, v)) {
           store_sym(dst, P.sym_width, i, v);

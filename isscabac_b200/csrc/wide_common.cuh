@@ -11,10 +11,11 @@
 namespace cabac {
 
 constexpr int WIDE_MAX_WARPS = 16;
-constexpr size_t WIDE_TAB_BYTES = (size_t)kNumRows * 32 * sizeof(uint2);
+constexpr uint32_t WIDE_ROW_STRIDE = 32 * sizeof(WRow);   // bytes between consecutive states of one lane
+constexpr size_t WIDE_TAB_BYTES = (size_t)kNumRows * WIDE_ROW_STRIDE;
 
 struct WideRowTable {
-  uint2 r[kNumRows];
+  WRow r[kNumRows];
   constexpr WideRowTable() : r{} {
     for (uint32_t i = 0; i < kNumRows; ++i) r[i] = wide_row(i);
   }
@@ -26,9 +27,19 @@ struct WCtx {
   __device__ __forceinline__ uint32_t load(uint32_t c) const { return p[c * 32]; }
   __device__ __forceinline__ void store(uint32_t c, uint32_t v) const { p[c * 32] = v; }
 };
+// Table [state][lane] of 16-byte rows in shared memory: lane l always reads its own column, so 32
+// lanes with 32 unrelated states never conflict (each quarter-warp of an LDS.128 covers all 32
+// banks once).  A token is the shared-window address of a row of this lane's column; the next_*
+// fields of the rows hold tokens of the same column.
 struct WTab {
-  const uint2* p;  // this lane's column of the table
-  __device__ __forceinline__ uint2 row(uint32_t st) const { return p[st * 32]; }
+  uint32_t base;  // shared-window address of row 0 of this lane's column
+  __device__ __forceinline__ uint32_t token(uint32_t st) const { return base + st * WIDE_ROW_STRIDE; }
+  __device__ __forceinline__ WRow row(uint32_t tok) const {
+    WRow r;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.lps4), "=r"(r.next_mps), "=r"(r.next_lps), "=r"(r.mps4) : "r"(tok));
+    return r;
+  }
 };
 
 // Fills the table, initialises this warp's context block (slot n_ctx = bypass slot); returns
@@ -36,9 +47,16 @@ struct WTab {
 // registers (the optimiser otherwise recomputes them from threadIdx at every table access).
 __device__ __forceinline__ bool wide_setup(uint32_t n_streams, uint32_t n_ctx_in, const uint8_t* ctx_init,
                                            int per_stream_init, uint8_t* smem, uint32_t& s, WCtx& ctx, WTab& tab,
-                                           uint32_t& n_ctx) {
-  uint2* t = reinterpret_cast<uint2*>(smem);
-  for (uint32_t i = threadIdx.x; i < kNumRows * 32; i += blockDim.x) t[i] = c_wide_rows.r[i >> 5];
+                                           uint32_t& n_ctx, uint32_t* vmask = nullptr) {
+  WRow* t = reinterpret_cast<WRow*>(smem);
+  const uint32_t tab0 = (uint32_t)__cvta_generic_to_shared(smem);
+  for (uint32_t i = threadIdx.x; i < kNumRows * 32; i += blockDim.x) {
+    WRow r = c_wide_rows.r[i >> 5];
+    const uint32_t col = tab0 + (i & 31u) * (uint32_t)sizeof(WRow);
+    r.next_mps = col + r.next_mps * WIDE_ROW_STRIDE;
+    r.next_lps = col + r.next_lps * WIDE_ROW_STRIDE;
+    t[i] = r;
+  }
   const uint32_t warp = threadIdx.x >> 5, lane = cb_keep32(threadIdx.x & 31);
   const uint32_t nw = blockDim.x >> 5;
   n_ctx = cb_keep32(n_ctx_in);
@@ -47,11 +65,12 @@ __device__ __forceinline__ bool wide_setup(uint32_t n_streams, uint32_t n_ctx_in
   const uint32_t coff = cb_keep32(warp * (n_ctx + 1) * 32 + lane);
   uint32_t* c0 = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + coff;
   const uint8_t* init = ctx_init + (per_stream_init && valid ? (uint64_t)s * n_ctx : 0);
-  for (uint32_t c = 0; c < n_ctx; ++c) c0[c * 32] = init[c] & 127u;
-  c0[n_ctx * 32] = kEpState;
+  tab.base = cb_keep32(tab0 + lane * (uint32_t)sizeof(WRow));
+  for (uint32_t c = 0; c < n_ctx; ++c) c0[c * 32] = tab.token(init[c] & 127u);
+  c0[n_ctx * 32] = tab.token(kEpState);
   ctx.p = c0;
-  tab.p = t + lane;
   __syncthreads();
+  if (vmask) *vmask = __ballot_sync(0xffffffffu, valid);   // the lanes of this warp that hold a stream
   return valid;
 }
 

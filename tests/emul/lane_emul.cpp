@@ -118,8 +118,9 @@ struct HostCtx {
   uint32_t load(uint32_t c) const { return p[c]; }
   void store(uint32_t c, uint32_t v) const { p[c] = v; }
 };
-struct HostTab {
-  uint2 row(uint32_t st) const { return wide_row(st); }
+struct HostTab {   // host tokens are the state bytes themselves
+  uint32_t token(uint32_t st) const { return st; }
+  WRow row(uint32_t tok) const { return wide_row(tok); }
 };
 inline uint32_t ld32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 }  // namespace
@@ -149,7 +150,7 @@ int emul_encode_ops_wide(uint32_t n_streams, const uint64_t* op_off, const uint8
       if (block_has_trm(cw)) {
         for (int k = 0; k < 16; ++k) encw_general(E, p[i + k], ctx, tab, n_ctx);
       } else {
-        encw_block16(E, w, cw, ctx, tab, n_ctx);
+        encw_block16<false>(E, w, cw, ctx, tab, n_ctx);
       }
     }
     for (; i < n; ++i) encw_general(E, p[i], ctx, tab, n_ctx);
@@ -184,7 +185,7 @@ int emul_decode_ops_wide(uint32_t n_streams, const uint64_t* byte_off, const uin
         for (int k = 0; k < 16; ++k) q[i + k] = (uint8_t)decw_general(D, p[i + k], ctx, tab, n_ctx);
       } else {
         uint32_t r[4];
-        decw_block16(D, cw, r, ctx, tab, n_ctx);
+        decw_block16<false>(D, cw, r, ctx, tab, n_ctx);
         memcpy(q + i, r, 16);
       }
     }
