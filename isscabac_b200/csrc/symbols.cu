@@ -52,13 +52,18 @@ __device__ __forceinline__ SymCfg to_cfg(const isscabac_symcfg& c) {
 }
 
 // ---- symbol-parallel binarizer ------------------------------------------------
-// Tiles of 2,048 consecutive symbols, 8 per thread.  Pass 1 sums the (closed-form) bin counts of
-// every tile; a device-wide scan over the tile sums gives each tile's first op position; pass 2
-// recomputes the counts, scans them inside the block and writes the ops.  Only pass 2 needs to
-// know which stream a symbol belongs to (context selection looks at the position inside the
-// stream, and the thread that owns a stream's first symbol records op_off[s]): one binary search
-// per warp, then every lane walks forward from there.
+// Tiles of 2,048 consecutive symbols, 8 per thread (one 8/16/32-byte vector load per thread).
+// Pass 1 sums the (closed-form) bin counts of every tile; a device-wide scan over the tile sums
+// gives each tile's first op position; pass 2 recomputes the counts, scans them inside the block,
+// writes the ops of the tile into shared memory -- at the same offset modulo 16 as their place in
+// HBM -- and copies them out with 16-byte stores (a thread's own ops are a run of ~2 bytes per
+// symbol: written straight to HBM they would be byte stores scattered over 18 sectors per warp
+// instruction).  Only pass 2 needs to know which stream a symbol belongs to (context selection
+// looks at the position inside the stream, and the thread that owns a stream's first symbol
+// records op_off[s]): one binary search per tile, a short one per thread inside the tile's range.
+// HBM traffic: 2 x symbols in, ops out, 12 B per tile.
 constexpr int BIN_THREADS = 256, BIN_ITEMS = 8, BIN_TILE = BIN_THREADS * BIN_ITEMS;
+constexpr uint32_t BIN_STAGE = 16384;   // ops staged per round (a tile of EG0 symbols has ~5 K)
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& block_total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -81,22 +86,47 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
   return off + inc - v;
 }
 
-__global__ void __launch_bounds__(BIN_THREADS) k_bin_count(isscabac_symcfg c, const void* sym, int width, uint64_t n,
-                                                            uint32_t* tile_sums) {
+// the 8 symbols of this thread (0 past the end): one vector load when the run is whole and aligned
+template <int W>
+__device__ __forceinline__ void load_syms8(const void* sym, uint64_t i0, uint64_t n, uint32_t v[BIN_ITEMS]) {
+  const uint8_t* base = static_cast<const uint8_t*>(sym) + i0 * W;
+  if (i0 + BIN_ITEMS <= n && (reinterpret_cast<uintptr_t>(base) & (W == 1 ? 7u : 15u)) == 0) {
+    if (W == 1) {
+      const uint2 q = __ldg(reinterpret_cast<const uint2*>(base));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { v[k] = (q.x >> (8 * k)) & 0xffu; v[4 + k] = (q.y >> (8 * k)) & 0xffu; }
+    } else if (W == 2) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(base));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { v[2 * k] = w[k] & 0xffffu; v[2 * k + 1] = w[k] >> 16; }
+    } else {
+      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(base)), q1 = __ldg(reinterpret_cast<const uint4*>(base) + 1);
+      v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < BIN_ITEMS; ++k) v[k] = i0 + k < n ? load_sym(sym, W, i0 + k) : 0u;
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_count(isscabac_symcfg c, const void* sym, uint64_t n, uint32_t* tile_sums) {
   __shared__ uint32_t s_warp[BIN_THREADS / 32];
   const uint64_t i0 = (uint64_t)blockIdx.x * BIN_TILE + (uint64_t)threadIdx.x * BIN_ITEMS;
+  uint32_t v[BIN_ITEMS];
+  load_syms8<W>(sym, i0, n, v);
   uint32_t tot = 0;
 #pragma unroll
   for (int k = 0; k < BIN_ITEMS; ++k)
-    if (i0 + k < n) tot += sym_code(load_sym(sym, width, i0 + k), c.Nq, c.method).len;
+    if (i0 + k < n) tot += sym_code(v[k], c.Nq, c.method).len;
   uint32_t block_total;
   block_exclusive_scan(tot, s_warp, block_total);
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = block_total;
 }
 
-// last s < n_streams with sym_off[s] <= i, searched in [lo, n_streams)
-__device__ __forceinline__ uint32_t find_stream(const uint64_t* sym_off, uint32_t lo, uint32_t n_streams, uint64_t i) {
-  uint32_t hi = n_streams;
+// last s in [lo, hi) with sym_off[s] <= i  (sym_off[lo] <= i is known)
+__device__ __forceinline__ uint32_t find_stream(const uint64_t* sym_off, uint32_t lo, uint32_t hi, uint64_t i) {
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
     if (sym_off[mid] <= i) lo = mid; else hi = mid;
@@ -104,62 +134,111 @@ __device__ __forceinline__ uint32_t find_stream(const uint64_t* sym_off, uint32_
   return lo;
 }
 
-__global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, const void* sym, int width, uint64_t n,
+// stream of the first symbol of every tile (and of the last symbol overall in slot n_tiles): one
+// binary search per thread, all tiles in parallel -- inside k_bin_emit the same search would be one
+// thread walking 20 dependent loads while the other 255 of its CTA wait
+__global__ void k_bin_tile_streams(const uint64_t* sym_off, uint32_t n_streams, uint64_t n, uint32_t n_tiles,
+                                   uint32_t* tile_stream) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_tiles) return;
+  const uint64_t i = t < n_tiles ? (uint64_t)t * BIN_TILE : n - 1;
+  tile_stream[t] = find_stream(sym_off, 0, n_streams, i);
+}
+
+template <int W>
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, const void* sym, uint64_t n,
                                                            const uint64_t* sym_off, uint32_t n_streams,
+                                                           const uint32_t* tile_stream,
                                                            const uint64_t* tile_prefix, uint64_t* op_off, uint8_t* ops,
                                                            uint64_t cap) {
   __shared__ uint32_t s_warp[BIN_THREADS / 32];
+  __shared__ __align__(16) uint8_t s_ops[BIN_STAGE + 16];
   const SymCfg cfg = to_cfg(c);
-  const uint64_t i0 = (uint64_t)blockIdx.x * BIN_TILE + (uint64_t)threadIdx.x * BIN_ITEMS;
+  const uint64_t t0 = (uint64_t)blockIdx.x * BIN_TILE;
+  const uint64_t i0 = t0 + (uint64_t)threadIdx.x * BIN_ITEMS;
+  // streams this tile touches: [s_lo, s_hi] (the next tile's first stream bounds this tile's last)
+  const uint32_t s_lo = tile_stream[blockIdx.x], s_hi = tile_stream[blockIdx.x + 1];
+  uint32_t v[BIN_ITEMS];
+  load_syms8<W>(sym, i0, n, v);
   SymCode code[BIN_ITEMS];
   uint32_t tot = 0;
 #pragma unroll
   for (int k = 0; k < BIN_ITEMS; ++k) {
     code[k] = SymCode{0, 0, 0};
-    if (i0 + k < n) code[k] = sym_code(load_sym(sym, width, i0 + k), cfg.Nq, cfg.method);
+    if (i0 + k < n) code[k] = sym_code(v[k], cfg.Nq, cfg.method);
     tot += code[k].len;
   }
   uint32_t block_total;
-  uint64_t o = tile_prefix[blockIdx.x] + block_exclusive_scan(tot, s_warp, block_total);
-  // stream of this thread's first symbol: one search per warp, then forward from the warp's stream
-  uint32_t sw = 0;
-  if ((threadIdx.x & 31) == 0 && i0 < n) sw = find_stream(sym_off, 0, n_streams, i0);
-  sw = __shfl_sync(0xffffffffu, sw, 0);
-  if (i0 >= n) return;
-  uint32_t s = sw;
-  if (sw + 1 < n_streams && sym_off[sw + 1] <= i0) s = find_stream(sym_off, sw, n_streams, i0);
-  uint64_t start = sym_off[s], next = sym_off[s + 1];
-  SymCode prev = {0, 0, 0};
-  if (i0 > start) prev = sym_code(load_sym(sym, width, i0 - 1), cfg.Nq, cfg.method);
+  const uint32_t lo = block_exclusive_scan(tot, s_warp, block_total);
+  const uint64_t tile_base = tile_prefix[blockIdx.x];
+  SymCode prev0 = {0, 0, 0};
+  uint32_t up_mask = 0;
+  if (i0 < n) {
+    uint32_t s = find_stream(sym_off, s_lo, s_hi + 1, i0);
+    uint64_t start = sym_off[s], next = sym_off[s + 1];
+    if (i0 > start) prev0 = sym_code(load_sym(sym, W, i0 - 1), cfg.Nq, cfg.method);
+    uint64_t o = tile_base + lo;
 #pragma unroll
-  for (int k = 0; k < BIN_ITEMS; ++k) {
-    const uint64_t i = i0 + k;
-    if (i >= n) break;
-    if (i == next) {   // next non-empty stream
-      ++s;
-      while (s + 1 < n_streams && sym_off[s + 1] == i) ++s;
-      start = i;
-      next = sym_off[s + 1];
-    }
-    if (i == start) {  // first symbol of stream s: record where its ops begin (also for empty streams in front of it)
-      for (uint32_t e = s;; --e) {
-        op_off[e] = o;
-        if (e == 0 || sym_off[e - 1] != i) break;
+    for (int k = 0; k < BIN_ITEMS; ++k) {
+      const uint64_t i = i0 + k;
+      if (i >= n) break;
+      if (i == next) {   // next non-empty stream
+        ++s;
+        while (s + 1 < n_streams && sym_off[s + 1] == i) ++s;
+        start = i;
+        next = sym_off[s + 1];
+      }
+      if (i == start) {  // first symbol of stream s: record where its ops begin (also for empty streams in front of it)
+        for (uint32_t e = s;; --e) {
+          op_off[e] = o;
+          if (e == 0 || sym_off[e - 1] != i) break;
+        }
+      }
+      if (sym_has_up(cfg, i - start)) up_mask |= 1u << k;
+      o += code[k].len;
+      if (i == n - 1) {  // streams that start at the very end are empty; op_off[n_streams] = total
+        for (uint32_t e = s + 1; e <= n_streams; ++e) op_off[e] = o;
       }
     }
-    const bool up = sym_has_up(cfg, i - start);
-    if (ops) {
-      for (uint32_t b = 1; b <= code[k].len; ++b) {
-        const int cx = select_ctx(cfg, b, code[k].np, prev, up);
-        const uint32_t cd = cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx;
-        if (o + b - 1 < cap) ops[o + b - 1] = (uint8_t)((cd << 1) | sym_bin(code[k], b));
+  }
+  if (!ops) return;      // offsets only (first of the two calls)
+  // ops: staged in shared memory at the same offset modulo 16 as in HBM, copied out in 16-byte pieces
+  const uint32_t skew = (uint32_t)((reinterpret_cast<uintptr_t>(ops) + tile_base) & 15u);
+  for (uint32_t r0 = 0; r0 < block_total; r0 += BIN_STAGE) {
+    if (lo < r0 + BIN_STAGE && lo + tot > r0) {
+      uint32_t pos = lo;
+      SymCode prev = prev0;
+#pragma unroll
+      for (int k = 0; k < BIN_ITEMS; ++k) {
+        const bool up = (up_mask >> k) & 1u;
+        for (uint32_t b = 1; b <= code[k].len; ++b) {
+          const uint32_t at = pos + b - 1 - r0;   // wraps for positions before this round: fails the test
+          if (at < BIN_STAGE) {
+            const int cx = select_ctx(cfg, b, code[k].np, prev, up);
+            const uint32_t cd = cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx;
+            s_ops[at + skew] = (uint8_t)((cd << 1) | sym_bin(code[k], b));
+          }
+        }
+        pos += code[k].len;
+        prev = code[k];
       }
     }
-    o += code[k].len;
-    prev = code[k];
-    if (i == n - 1) {  // streams that start at the very end are empty; op_off[n_streams] = total
-      for (uint32_t e = s + 1; e <= n_streams; ++e) op_off[e] = o;
-    }
+    __syncthreads();
+    uint32_t cnt = block_total - r0 < BIN_STAGE ? block_total - r0 : BIN_STAGE;
+    const uint64_t g0 = tile_base + r0;                 // first op of this round
+    if (g0 >= cap) cnt = 0;
+    else if (g0 + cnt > cap) cnt = (uint32_t)(cap - g0);
+    uint8_t* dst = ops + g0;
+    // bytes up to the first 16-byte boundary, whole 16-byte pieces, the rest
+    const uint32_t head = cnt < ((16u - skew) & 15u) ? cnt : ((16u - skew) & 15u);
+    if (threadIdx.x < head) dst[threadIdx.x] = s_ops[skew + threadIdx.x];
+    const uint32_t nvec = (cnt - head) >> 4;
+    const uint4* sv = reinterpret_cast<const uint4*>(s_ops + skew + head);   // (skew + head) % 16 == 0
+    uint4* dv = reinterpret_cast<uint4*>(dst + head);
+    for (uint32_t j = threadIdx.x; j < nvec; j += BIN_THREADS) dv[j] = sv[j];
+    const uint32_t done = head + (nvec << 4);
+    if (threadIdx.x < cnt - done) dst[done + threadIdx.x] = s_ops[skew + done + threadIdx.x];
+    __syncthreads();
   }
 }
 
@@ -525,7 +604,8 @@ size_t cabac_binarize_scratch_bytes(uint64_t n_symbols, uint32_t n_streams) {
   const uint64_t tiles = (n_symbols + BIN_TILE - 1) / BIN_TILE;
   const size_t sums = ((size_t)tiles * 4 + 255) & ~(size_t)255;
   const size_t pref = (((size_t)tiles + 1) * 8 + 255) & ~(size_t)255;
-  return sums + pref + cabac_compact_scratch_bytes((uint32_t)tiles) + 256;
+  const size_t tstr = (((size_t)tiles + 1) * 4 + 255) & ~(size_t)255;
+  return sums + pref + tstr + cabac_compact_scratch_bytes((uint32_t)tiles) + 256;
 }
 
 int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_sym_off,
@@ -548,11 +628,20 @@ int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const
   const size_t pref_b = (((size_t)tiles + 1) * 8 + 255) & ~(size_t)255;
   uint32_t* tile_sums = reinterpret_cast<uint32_t*>(scr);
   uint64_t* tile_prefix = reinterpret_cast<uint64_t*>(scr + sums_b);
-  void* scan_scr = scr + sums_b + pref_b;
-  k_bin_count<<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, sym_width, n_symbols, tile_sums);
+  const size_t tstr_b = (((size_t)tiles + 1) * 4 + 255) & ~(size_t)255;
+  uint32_t* tile_stream = reinterpret_cast<uint32_t*>(scr + sums_b + pref_b);
+  void* scan_scr = scr + sums_b + pref_b + tstr_b;
+  k_bin_tile_streams<<<(tiles + 1 + 255) / 256, 256, 0, st>>>(d_sym_off, n_streams, n_symbols, tiles, tile_stream);
+  if (sym_width == 1) k_bin_count<1><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, tile_sums);
+  else if (sym_width == 2) k_bin_count<2><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, tile_sums);
+  else k_bin_count<4><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, tile_sums);
   if ((rc = exclusive_scan_u32_u64(tile_sums, tile_prefix, tiles, scan_scr, st))) return rc;
-  k_bin_emit<<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, sym_width, n_symbols, d_sym_off, n_streams, tile_prefix,
-                                            d_op_off, d_ops, ops_cap);
+  if (sym_width == 1)
+    k_bin_emit<1><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, d_sym_off, n_streams, tile_stream, tile_prefix, d_op_off, d_ops, ops_cap);
+  else if (sym_width == 2)
+    k_bin_emit<2><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, d_sym_off, n_streams, tile_stream, tile_prefix, d_op_off, d_ops, ops_cap);
+  else
+    k_bin_emit<4><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, d_sym_off, n_streams, tile_stream, tile_prefix, d_op_off, d_ops, ops_cap);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "cabac_binarize_symbols");
 }
