@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
   uint32_t i = 0, cnt = 0, row = 0; // next symbol to fetch (stream-relative), symbols in the stream, row in the column
   SymCode cur = {0, 0, 0}, prev = {0, 0, 0};
   uint32_t b = 1;                   // next bin of `cur`; b > cur.len: fetch the next symbol first
+  uint32_t nextv = 0;               // value of symbol i, loaded one symbol ahead
   bool up = false, active = false, have = s < P.n_streams;
   if (have && order) s = order[s];
   for (;;) {
@@ -439,6 +440,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
       src = static_cast<const uint8_t*>(P.symbols) + s0 * (uint64_t)P.sym_width;
       encw_start(E, P.slab + (uint64_t)s * P.slab_stride, cap);
       i = 0; row = 0; cur = SymCode{0, 0, 0}; prev = cur; b = 1; up = false;
+      nextv = cnt ? load_sym(src, P.sym_width, 0) : 0u;
       active = true;
     }
     if (!__any_sync(0xffffffffu, active)) break;
@@ -448,7 +450,10 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
         if (j == 3 && E.n > 47) encw_emit(E);
         if (b > cur.len) {
           prev = cur;
-          cur = sym_code(load_sym(src, P.sym_width, i), cfg.Nq, cfg.method);
+          cur = sym_code(nextv, cfg.Nq, cfg.method);
+          // the symbol after this one is requested now and used a symbol (several bins) later: a lane
+          // that runs alone at the end of a ragged job must not wait for HBM once per symbol
+          if (i + 1 < cnt) nextv = load_sym(src, P.sym_width, i + 1);
           up = has_up_row(cfg, i, row);
           ++i;
           if (++row == cfg.rows) row = 0;
