@@ -20,7 +20,13 @@ from . import engine as E
 
 
 def _cfg(Nq, param, rows):
-    return E.make_cfg(E.PROFILE_ISS, param.get("binMethod", "DEC2EG0"), int(Nq), int(param.get("Nlbp", 3)),
+    method = param.get("binMethod", "DEC2EG0")
+    if int(Nq) <= 2:
+        # cabacEncode.m:16 / cabacDecode.m:62: with two levels nothing is binarised, every symbol IS its one
+        # bin -- which is what the truncated-unary code of two levels produces (0 -> '0', 1 -> '1', no
+        # terminating zero at Nq-1, cabacBinarizer.m:31-32), whatever binMethod says
+        method, Nq = "DEC2TU", 2
+    return E.make_cfg(E.PROFILE_ISS, method, int(Nq), int(param.get("Nlbp", 3)),
                       list(param.get("cmTypes", ["cond0", "cond1", "conds0", "conds1"])), rows=int(rows))
 
 

@@ -117,3 +117,23 @@ def test_matrices_through_the_container():
     one = c.stream(s)
     out, ok = O.decode_symbols(ocfg, one, np.array([0, one.size], dtype=np.uint64), np.array([0, 109], dtype=np.uint64), st)
     assert ok.all() and np.array_equal(out, mats[2][:, 7])
+
+
+def test_two_level_matrices_are_coded_without_binarisation(tmp_path):
+    """Nq = 2 (the default of cabacEncode.m:12): every symbol is its own single bin (cabacEncode.m:16,
+    cabacDecode.m:62-66), whatever binMethod says; the bytes are what the reference engine writes for
+    those bins with the ISS context rule."""
+    from isscabac_b200 import coder
+    rng = np.random.default_rng(8)
+    G = (rng.random((60, 7)) < 0.3).astype(np.uint32)
+    param = dict(binMethod="DEC2EG0", cmTypes=["cond0", "cond1", "conds0", "conds1"], Nlbp=3, fn=str(tmp_path / "b.bit"))
+    nbits, ctx0 = coder.cabacEncode(G, 2, param)
+    assert np.array_equal(coder.cabacDecode(2, param, ctx0, G.shape), G)
+    ocfg = O.make_cfg(O.PROFILE_ISS, O.BIN_TU, 2, 3, ALLT, 60)
+    flat = G.T.reshape(-1).astype(np.uint32)
+    ops = O.symbols_to_ops(ocfg, flat)
+    assert len(ops) == flat.size and np.array_equal(ops & 1, flat)          # one bin per symbol, the value itself
+    st = O.ctx_from_p0(ctx0.astype(np.float64) / 255)
+    slab, lens = O.encode_ops(ops, np.array([0, len(ops)], dtype=np.uint64), st, out_stride=4096,
+                              impl="ref" if O.ref() is not None else "oracle")
+    assert open(param["fn"], "rb").read() == bytes(slab[0, :lens[0]]) and nbits == 8 * int(lens[0])
