@@ -82,13 +82,14 @@ CB_HD bool cb_any(bool p) {
 // with at most kLazy-1 = 41 bits, may reach 53 after two bins, is brought back under 32 by the
 // mid-group guard if it passed 41, and leaves the group with at most 53.
 constexpr int kLazy = CABAC_LAZY ? 42 : 32;
-// The decoder's refill is kept eager: the lazy schedule needs the mid-group guard on top of the
-// vote, and the decoder is bound by its decision -> token -> row chain, not by instruction count
-// (measured on B200: 517 eager vs 520 lazy Gbins/s, inside the run-to-run spread).
+// The decoder's refill: 0 = eager, 1 = the encoder's schedule (voted at 42 + mid-group guard),
+// 2 = voted at 36 without a guard.  Measured on B200 at C3: 523 / 517 / 546 Gbins/s.
 #ifndef CABAC_LAZY_DEC
-#define CABAC_LAZY_DEC 0
+#define CABAC_LAZY_DEC 2
 #endif
-constexpr int kLazyDec = CABAC_LAZY_DEC ? 42 : 32;
+// 2 = voted refill without the mid-group guard: a lane enters a group with at most 35 unfilled bits,
+// so the fourth decision of the group still sees f <= 35 + 18 = 53
+constexpr int kLazyDec = CABAC_LAZY_DEC == 2 ? 36 : (CABAC_LAZY_DEC ? 42 : 32);
 
 // ---------------------------------------------------------------------------
 // encoder
@@ -393,7 +394,7 @@ CB_HD void decw_block16(DecWide& D, const uint32_t cw[4], uint32_t r[4],
     const uint32_t codes = cw[g];
     uint32_t acc = decw_op<0>(D, cb_prmt(codes, 0, 0x4440u), ctx, tab, n_ctx);
     acc |= decw_op<1>(D, cb_prmt(codes, 0, 0x4441u), ctx, tab, n_ctx);
-    if (CABAC_LAZY_DEC && D.f >= kLazyDec) decw_refill(D);
+    if (CABAC_LAZY_DEC == 1 && D.f >= kLazyDec) decw_refill(D);
     acc |= decw_op<2>(D, cb_prmt(codes, 0, 0x4442u), ctx, tab, n_ctx);
     acc |= decw_op<3>(D, cb_prmt(codes, 0, 0x4443u), ctx, tab, n_ctx);
     r[g] = acc;

@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (active && (b <= cur.len || i < cnt)) {
-        if (j == 3 && E.n > 47) encw_emit(E);
+        if (j == 2 && E.n >= kLazy) encw_emit(E);   // window budget of a 4-bin group, see kLazy
         if (b > cur.len) {
           prev = cur;
           cur = sym_code(nextv, cfg.Nq, cfg.method);
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
         ++b;
       }
     }
-    encw_emit(E);
+    if (__any_sync(0xffffffffu, E.n >= kLazy)) encw_emit(E);   // lazy, voted: all 32 lanes are here
     if (active && !(b <= cur.len || i < cnt)) {   // stream complete: finish(), then take the next unclaimed one
       const uint32_t len = encw_finish(E);
       P.lengths[s] = len;
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_symbols_wide(Sym
         }
       }
     }
-    decw_refill(D);
+    if (__any_sync(0xffffffffu, D.f >= kLazyDec)) decw_refill(D);
     if (active && i >= cnt) {
       if (P.finish_ok) P.finish_ok[s] = (uint8_t)decw_finish(D);
       decw_start(D, P.bytes, 0);
