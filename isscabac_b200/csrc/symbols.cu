@@ -54,16 +54,13 @@ __device__ __forceinline__ SymCfg to_cfg(const isscabac_symcfg& c) {
 // ---- symbol-parallel binarizer ------------------------------------------------
 // Tiles of 2,048 consecutive symbols, 8 per thread (one 8/16/32-byte vector load per thread).
 // Pass 1 sums the (closed-form) bin counts of every tile; a device-wide scan over the tile sums
-// gives each tile's first op position; pass 2 recomputes the counts, scans them inside the block,
-// writes the ops of the tile into shared memory -- at the same offset modulo 16 as their place in
-// HBM -- and copies them out with 16-byte stores (a thread's own ops are a run of ~2 bytes per
-// symbol: written straight to HBM they would be byte stores scattered over 18 sectors per warp
-// instruction).  Only pass 2 needs to know which stream a symbol belongs to (context selection
+// gives each tile's first op position; pass 2 recomputes the counts, scans them inside the block
+// and produces the ops op-parallel, one aligned 16-byte piece of the op array per thread (see
+// k_bin_emit).  Only pass 2 needs to know which stream a symbol belongs to (context selection
 // looks at the position inside the stream, and the thread that owns a stream's first symbol
 // records op_off[s]): one binary search per tile, a short one per thread inside the tile's range.
 // HBM traffic: 2 x symbols in, ops out, 12 B per tile.
 constexpr int BIN_THREADS = 256, BIN_ITEMS = 8, BIN_TILE = BIN_THREADS * BIN_ITEMS;
-constexpr uint32_t BIN_STAGE = 16384;   // ops staged per round (a tile of EG0 symbols has ~5 K)
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& block_total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -110,16 +107,27 @@ __device__ __forceinline__ void load_syms8(const void* sym, uint64_t i0, uint64_
   }
 }
 
-template <int W>
+// PROF / METH: profile and binarization fixed at compile time for the combinations the
+// applications use (the closed-form helpers then fold to a few instructions); -1 = read from cfg.
+template <int PROF, int METH>
+__device__ __forceinline__ SymCfg fixed_cfg(const isscabac_symcfg& c) {
+  SymCfg cfg = to_cfg(c);
+  if (PROF >= 0) cfg.profile = PROF;
+  if (METH >= 0) cfg.method = METH;
+  return cfg;
+}
+
+template <int W, int METH>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_count(isscabac_symcfg c, const void* sym, uint64_t n, uint32_t* tile_sums) {
   __shared__ uint32_t s_warp[BIN_THREADS / 32];
+  const SymCfg cfg = fixed_cfg<-1, METH>(c);
   const uint64_t i0 = (uint64_t)blockIdx.x * BIN_TILE + (uint64_t)threadIdx.x * BIN_ITEMS;
   uint32_t v[BIN_ITEMS];
   load_syms8<W>(sym, i0, n, v);
   uint32_t tot = 0;
 #pragma unroll
   for (int k = 0; k < BIN_ITEMS; ++k)
-    if (i0 + k < n) tot += sym_code(v[k], c.Nq, c.method).len;
+    if (i0 + k < n) tot += sym_code(v[k], cfg.Nq, cfg.method).len;
   uint32_t block_total;
   block_exclusive_scan(tot, s_warp, block_total);
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = block_total;
@@ -145,19 +153,101 @@ __global__ void k_bin_tile_streams(const uint64_t* sym_off, uint32_t n_streams, 
   tile_stream[t] = find_stream(sym_off, 0, n_streams, i);
 }
 
-template <int W>
+// Op strings by table.  For the alphabets the applications use, the ops of a symbol -- bins AND
+// context ids -- are a function of a small key: the symbol itself (FLAT profiles), the symbol and
+// the first bin of its predecessor (DEMO, cabacDemo.m:113-121), the symbol and its up neighbour
+// (ISS, cabacContextSelection.m:24-67 looks at nothing else).  k_bin_lut computes the string of
+// every key once per call with the same closed-form code as everywhere else (sym_code / select_ctx /
+// sym_bin); the emit kernel then fetches ops with one byte load each.  Entry = 15 op bytes + the
+// length; symbols outside the table (value beyond its domain, more than 15 bins) take the
+// closed-form route op by op.
+constexpr uint32_t LUT_MAX = 1024, LUT_ESC = 0xffffu;
+struct LutGeom { uint32_t dom, entries; };
+__host__ __device__ inline LutGeom lut_geom(int profile, int method, uint32_t Nq) {
+  if (method == BIN_FL32) return LutGeom{0u, 0u};
+  const uint32_t nq = Nq ? Nq : 256u;
+  if (profile == PROFILE_ISS) { const uint32_t d = nq < 31u ? nq : 31u; return LutGeom{d, d * (d + 1u)}; }
+  const uint32_t d = nq < 256u ? nq : 256u;
+  return LutGeom{d, profile == PROFILE_DEMO ? 3u * d : d};
+}
+// key of a symbol: v = its value, u = the value of its neighbour, has_up = the neighbour exists
+__device__ __forceinline__ uint32_t lut_index(const SymCfg& cfg, uint32_t dom, uint32_t v, uint32_t u, bool has_up) {
+  if (v >= dom) return LUT_ESC;
+  if (cfg.profile == PROFILE_ISS) return (has_up && u >= dom) ? LUT_ESC : v * (dom + 1u) + (has_up ? u + 1u : 0u);
+  if (cfg.profile == PROFILE_DEMO) return v + dom * (has_up ? (sym_code(u, cfg.Nq, cfg.method).np > 1u ? 1u : 2u) : 0u);
+  return v;
+}
+__global__ void k_bin_lut(isscabac_symcfg c, uint4* lut) {
+  const SymCfg cfg = to_cfg(c);
+  const LutGeom g = lut_geom(cfg.profile, cfg.method, cfg.Nq);
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.entries) return;
+  uint32_t v, u = 0;
+  bool has_up = false;
+  SymCode uc = {0, 0, 0};
+  if (cfg.profile == PROFILE_ISS) {
+    v = e / (g.dom + 1u);
+    const uint32_t r = e % (g.dom + 1u);
+    has_up = r != 0;
+    u = has_up ? r - 1u : 0u;
+    uc = sym_code(u, cfg.Nq, cfg.method);
+  } else if (cfg.profile == PROFILE_DEMO) {
+    v = e % g.dom;
+    const uint32_t t = e / g.dom;
+    has_up = t != 0;
+    uc = SymCode{1u, t == 1 ? 2u : 1u, 0u};      // only the neighbour's first bin matters: 1 (np > 1) or 0 (np == 1)
+  } else {
+    v = e;
+  }
+  const SymCode code = sym_code(v, cfg.Nq, cfg.method);
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (code.len <= 15u) {
+    for (uint32_t b = 1; b <= code.len; ++b) {
+      const int cx = select_ctx(cfg, b, code.np, uc, has_up);
+      const uint32_t cd = cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx;
+      const uint32_t byte = (cd << 1) | sym_bin(code, b);
+      const uint32_t at = b - 1u;
+      if (at < 4) w[0] |= byte << (8 * at);
+      else if (at < 8) w[1] |= byte << (8 * (at - 4));
+      else if (at < 12) w[2] |= byte << (8 * (at - 8));
+      else w[3] |= byte << (8 * (at - 12));
+    }
+    w[3] |= code.len << 24;
+  }
+  lut[e] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Pass 2, op-parallel.  Phase A (symbol-parallel, 8 symbols per thread): codes, block scan, the
+// op_off entries of the streams that start in this tile, and per symbol in shared memory its first
+// op position, its table key (index | length << 10) and its value.  Phase B (op-parallel): the
+// tile's ops are cut into the 16-byte pieces of their place in HBM; every piece is produced by one
+// thread -- it starts at the symbol that owns the piece's first op (each symbol writes its index
+// into the owner slot of the pieces that begin inside it: disjoint, no atomics) and walks on from
+// there, one table byte per op -- and leaves as ONE aligned 16-byte store.  A warp therefore does
+// not pay for the longest of 32 threads' 8-symbol runs, and no op is staged in shared memory.
+constexpr uint32_t BIN_ROUND = 1024;     // 16-byte pieces per round (a tile of EG0 symbols has ~300)
+
+template <int W, int PROF, int METH>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, const void* sym, uint64_t n,
                                                            const uint64_t* sym_off, uint32_t n_streams,
                                                            const uint32_t* tile_stream,
                                                            const uint64_t* tile_prefix, uint64_t* op_off, uint8_t* ops,
-                                                           uint64_t cap) {
+                                                           uint64_t cap, const uint4* lut) {
   __shared__ uint32_t s_warp[BIN_THREADS / 32];
-  __shared__ __align__(16) uint8_t s_ops[BIN_STAGE + 16];
-  const SymCfg cfg = to_cfg(c);
+  __shared__ uint32_t s_pos[BIN_TILE + 1];
+  __shared__ uint32_t s_sym[BIN_TILE + 2];        // [0] = the symbol in front of the tile, [i + 1] = symbol i of the tile
+  __shared__ uint16_t s_key[BIN_TILE + 2];
+  __shared__ uint8_t s_up[BIN_THREADS];           // bit k of byte t: symbol 8t + k has an up / previous neighbour
+  __shared__ uint16_t s_owner[BIN_ROUND];
+  __shared__ __align__(16) uint4 s_lut[LUT_MAX];
+  const SymCfg cfg = fixed_cfg<PROF, METH>(c);
+  const LutGeom geom = lut_geom(cfg.profile, cfg.method, cfg.Nq);
   const uint64_t t0 = (uint64_t)blockIdx.x * BIN_TILE;
   const uint64_t i0 = t0 + (uint64_t)threadIdx.x * BIN_ITEMS;
   // streams this tile touches: [s_lo, s_hi] (the next tile's first stream bounds this tile's last)
   const uint32_t s_lo = tile_stream[blockIdx.x], s_hi = tile_stream[blockIdx.x + 1];
+  if (ops)
+    for (uint32_t e = threadIdx.x; e < geom.entries; e += BIN_THREADS) s_lut[e] = __ldg(lut + e);
   uint32_t v[BIN_ITEMS];
   load_syms8<W>(sym, i0, n, v);
   SymCode code[BIN_ITEMS];
@@ -171,74 +261,150 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, con
   uint32_t block_total;
   const uint32_t lo = block_exclusive_scan(tot, s_warp, block_total);
   const uint64_t tile_base = tile_prefix[blockIdx.x];
-  SymCode prev0 = {0, 0, 0};
   uint32_t up_mask = 0;
   if (i0 < n) {
     uint32_t s = find_stream(sym_off, s_lo, s_hi + 1, i0);
     uint64_t start = sym_off[s], next = sym_off[s + 1];
-    if (i0 > start) prev0 = sym_code(load_sym(sym, W, i0 - 1), cfg.Nq, cfg.method);
-    uint64_t o = tile_base + lo;
+    if (i0 > start && i0 + BIN_ITEMS <= next && i0 + BIN_ITEMS < n) {
+      // the whole run lies inside one stream, away from its first symbol and from the end of the input:
+      // no offset to record, the neighbour flags follow from the row of the run's first symbol
+      if (cfg.profile == PROFILE_DEMO || (cfg.profile == PROFILE_ISS && cfg.rows == 0)) {
+        up_mask = 0xffu;
+      } else if (cfg.profile == PROFILE_ISS) {
+        const uint64_t rel = i0 - start;
+        uint32_t r = rel >> 32 ? (uint32_t)(rel % cfg.rows) : (uint32_t)rel % cfg.rows;
 #pragma unroll
-    for (int k = 0; k < BIN_ITEMS; ++k) {
-      const uint64_t i = i0 + k;
-      if (i >= n) break;
-      if (i == next) {   // next non-empty stream
-        ++s;
-        while (s + 1 < n_streams && sym_off[s + 1] == i) ++s;
-        start = i;
-        next = sym_off[s + 1];
-      }
-      if (i == start) {  // first symbol of stream s: record where its ops begin (also for empty streams in front of it)
-        for (uint32_t e = s;; --e) {
-          op_off[e] = o;
-          if (e == 0 || sym_off[e - 1] != i) break;
+        for (int k = 0; k < BIN_ITEMS; ++k) {
+          if (r != 0) up_mask |= 1u << k;
+          if (++r == cfg.rows) r = 0;
         }
       }
-      if (sym_has_up(cfg, i - start)) up_mask |= 1u << k;
-      o += code[k].len;
-      if (i == n - 1) {  // streams that start at the very end are empty; op_off[n_streams] = total
-        for (uint32_t e = s + 1; e <= n_streams; ++e) op_off[e] = o;
+    } else {
+      uint64_t o = tile_base + lo;
+#pragma unroll
+      for (int k = 0; k < BIN_ITEMS; ++k) {
+        const uint64_t i = i0 + k;
+        if (i >= n) break;
+        if (i == next) {   // next non-empty stream
+          ++s;
+          while (s + 1 < n_streams && sym_off[s + 1] == i) ++s;
+          start = i;
+          next = sym_off[s + 1];
+        }
+        if (i == start) {  // first symbol of stream s: record where its ops begin (also for empty streams in front of it)
+          for (uint32_t e = s;; --e) {
+            op_off[e] = o;
+            if (e == 0 || sym_off[e - 1] != i) break;
+          }
+        }
+        if (sym_has_up(cfg, i - start)) up_mask |= 1u << k;
+        o += code[k].len;
+        if (i == n - 1) {  // streams that start at the very end are empty; op_off[n_streams] = total
+          for (uint32_t e = s + 1; e <= n_streams; ++e) op_off[e] = o;
+        }
       }
     }
   }
   if (!ops) return;      // offsets only (first of the two calls)
-  // ops: staged in shared memory at the same offset modulo 16 as in HBM, copied out in 16-byte pieces
+  {
+    // the symbol in front of this thread's run (the neighbour of its first symbol)
+    uint32_t before = 0;
+    if ((up_mask & 1u) || threadIdx.x == 0) before = i0 > 0 && i0 <= n ? load_sym(sym, W, i0 - 1) : 0u;
+    uint32_t pos = lo;
+#pragma unroll
+    for (int k = 0; k < BIN_ITEMS; ++k) {
+      const uint32_t li = threadIdx.x * BIN_ITEMS + k;
+      const uint32_t idx = lut_index(cfg, geom.dom, v[k], k ? v[k - 1] : before, (up_mask >> k) & 1u);
+      s_pos[li] = pos;
+      s_sym[li + 1] = v[k];
+      s_key[li] = (uint16_t)((idx == LUT_ESC || code[k].len > 15u) ? LUT_ESC : (idx | (code[k].len << 10)));
+      pos += code[k].len;
+    }
+    s_up[threadIdx.x] = (uint8_t)up_mask;
+    if (threadIdx.x == 0) {
+      s_sym[0] = before;
+      s_sym[BIN_TILE + 1] = 0;
+      s_key[BIN_TILE] = 0;
+      s_pos[BIN_TILE] = block_total;
+    }
+  }
   const uint32_t skew = (uint32_t)((reinterpret_cast<uintptr_t>(ops) + tile_base) & 15u);
-  for (uint32_t r0 = 0; r0 < block_total; r0 += BIN_STAGE) {
-    if (lo < r0 + BIN_STAGE && lo + tot > r0) {
+  const uint32_t npieces = (block_total + skew + 15u) >> 4;   // piece j = tile positions [16j - skew, 16j - skew + 16)
+  // ops the caller's buffer has room for (a too small buffer is filled up to its capacity)
+  const uint32_t room = tile_base >= cap ? 0u : (cap - tile_base < block_total ? (uint32_t)(cap - tile_base) : block_total);
+  const uint32_t lut0 = (uint32_t)__cvta_generic_to_shared(s_lut);
+  for (uint32_t r0 = 0; r0 < npieces; r0 += BIN_ROUND) {
+    __syncthreads();     // records complete (first round) / owner slots free again (later rounds)
+    {
       uint32_t pos = lo;
-      SymCode prev = prev0;
 #pragma unroll
       for (int k = 0; k < BIN_ITEMS; ++k) {
-        const bool up = (up_mask >> k) & 1u;
-        for (uint32_t b = 1; b <= code[k].len; ++b) {
-          const uint32_t at = pos + b - 1 - r0;   // wraps for positions before this round: fails the test
-          if (at < BIN_STAGE) {
-            const int cx = select_ctx(cfg, b, code[k].np, prev, up);
-            const uint32_t cd = cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx;
-            s_ops[at + skew] = (uint8_t)((cd << 1) | sym_bin(code[k], b));
-          }
+        const uint32_t len = code[k].len;
+        if (len) {
+          // pieces whose first op lies inside this symbol; piece 0 starts with the tile's op 0
+          uint32_t j_lo = pos == 0 ? 0u : (pos + skew + 15u) >> 4;
+          const uint32_t j_hi = (pos + len - 1u + skew) >> 4;
+          if (j_lo < r0) j_lo = r0;
+          for (uint32_t j = j_lo; j <= j_hi && j < r0 + BIN_ROUND; ++j) s_owner[j - r0] = (uint16_t)(threadIdx.x * BIN_ITEMS + k);
         }
-        pos += code[k].len;
-        prev = code[k];
+        pos += len;
       }
     }
     __syncthreads();
-    uint32_t cnt = block_total - r0 < BIN_STAGE ? block_total - r0 : BIN_STAGE;
-    const uint64_t g0 = tile_base + r0;                 // first op of this round
-    if (g0 >= cap) cnt = 0;
-    else if (g0 + cnt > cap) cnt = (uint32_t)(cap - g0);
-    uint8_t* dst = ops + g0;
-    // bytes up to the first 16-byte boundary, whole 16-byte pieces, the rest
-    const uint32_t head = cnt < ((16u - skew) & 15u) ? cnt : ((16u - skew) & 15u);
-    if (threadIdx.x < head) dst[threadIdx.x] = s_ops[skew + threadIdx.x];
-    const uint32_t nvec = (cnt - head) >> 4;
-    const uint4* sv = reinterpret_cast<const uint4*>(s_ops + skew + head);   // (skew + head) % 16 == 0
-    uint4* dv = reinterpret_cast<uint4*>(dst + head);
-    for (uint32_t j = threadIdx.x; j < nvec; j += BIN_THREADS) dv[j] = sv[j];
-    const uint32_t done = head + (nvec << 4);
-    if (threadIdx.x < cnt - done) dst[done + threadIdx.x] = s_ops[skew + done + threadIdx.x];
-    __syncthreads();
+    const uint32_t r1 = r0 + BIN_ROUND < npieces ? r0 + BIN_ROUND : npieces;
+    for (uint32_t j = r0 + threadIdx.x; j < r1; j += BIN_THREADS) {
+      const int32_t pbeg = (int32_t)(16u * j) - (int32_t)skew;           // tile position of byte 0 of the piece
+      const uint32_t e0 = pbeg < 0 ? (uint32_t)(-pbeg) : 0u;             // valid bytes: [e0, e1)
+      const int32_t left = (int32_t)room - pbeg;
+      const uint32_t e1 = left <= 0 ? 0u : (left < 16 ? (uint32_t)left : 16u);
+      if (e0 >= e1) continue;
+      uint32_t i = s_owner[j - r0];
+      uint32_t b = (uint32_t)(pbeg + (int32_t)e0) - s_pos[i];            // ops of symbol i already out (0-based position)
+      uint32_t a = 0, len = 0;      // table route: shared-window address of the symbol's string, its length
+      bool esc = false;             // closed-form route
+      SymCode cur = {0, 0, 0}, prev = {0, 0, 0};
+      bool up = false;
+      auto enter = [&]() {
+        const uint32_t key = s_key[i];
+        esc = key == LUT_ESC;
+        a = lut0 + ((key & 1023u) << 4);
+        len = key >> 10;
+        if (esc) {
+          cur = sym_code(s_sym[i + 1], cfg.Nq, cfg.method);
+          prev = sym_code(s_sym[i], cfg.Nq, cfg.method);
+          up = (s_up[i >> 3] >> (i & 7u)) & 1u;
+          len = cur.len;
+        }
+      };
+      enter();
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (uint32_t e = 0; e < 16; ++e) {
+        if (e >= e0 && e < e1) {
+          uint32_t byte;
+          if (!esc) {
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(byte) : "r"(a + b));
+          } else {
+            const int cx = select_ctx(cfg, b + 1u, cur.np, prev, up);
+            byte = ((cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx) << 1) | sym_bin(cur, b + 1u);
+          }
+          w[e >> 2] |= byte << (8u * (e & 3u));
+          if (++b == len) {
+            ++i;
+            b = 0;
+            enter();
+          }
+        }
+      }
+      uint8_t* dst = ops + tile_base + pbeg;       // 16-byte aligned by the choice of skew
+      if (e0 == 0 && e1 == 16) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+#pragma unroll
+        for (uint32_t e = 0; e < 16; ++e)
+          if (e >= e0 && e < e1) dst[e] = (uint8_t)(w[e >> 2] >> (8u * (e & 3u)));
+      }
+    }
   }
 }
 
@@ -397,15 +563,6 @@ struct LaneCtx {
   }
 };
 
-// PROF / METH: profile and binarization fixed at compile time for the combinations the
-// applications use (the closed-form helpers then fold to a few instructions); -1 = read from cfg.
-template <int PROF, int METH>
-__device__ __forceinline__ SymCfg fixed_cfg(const isscabac_symcfg& c) {
-  SymCfg cfg = to_cfg(c);
-  if (PROF >= 0) cfg.profile = PROF;
-  if (METH >= 0) cfg.method = METH;
-  return cfg;
-}
 // "has an up / previous neighbour" without a division: r = row of the symbol inside its column
 __device__ __forceinline__ bool has_up_row(const SymCfg& cfg, uint32_t i_rel, uint32_t r) {
   if (cfg.profile == PROFILE_ISS) return cfg.rows ? r != 0 : i_rel > 0;
@@ -610,7 +767,7 @@ size_t cabac_binarize_scratch_bytes(uint64_t n_symbols, uint32_t n_streams) {
   const size_t sums = ((size_t)tiles * 4 + 255) & ~(size_t)255;
   const size_t pref = (((size_t)tiles + 1) * 8 + 255) & ~(size_t)255;
   const size_t tstr = (((size_t)tiles + 1) * 4 + 255) & ~(size_t)255;
-  return sums + pref + tstr + cabac_compact_scratch_bytes((uint32_t)tiles) + 256;
+  return sums + pref + tstr + ((cabac_compact_scratch_bytes((uint32_t)tiles) + 255) & ~(size_t)255) + LUT_MAX * sizeof(uint4) + 256;
 }
 
 int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_sym_off,
@@ -637,16 +794,31 @@ int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const
   uint32_t* tile_stream = reinterpret_cast<uint32_t*>(scr + sums_b + pref_b);
   void* scan_scr = scr + sums_b + pref_b + tstr_b;
   k_bin_tile_streams<<<(tiles + 1 + 255) / 256, 256, 0, st>>>(d_sym_off, n_streams, n_symbols, tiles, tile_stream);
-  if (sym_width == 1) k_bin_count<1><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, tile_sums);
-  else if (sym_width == 2) k_bin_count<2><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, tile_sums);
-  else k_bin_count<4><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, tile_sums);
+  uint4* lut = reinterpret_cast<uint4*>(static_cast<uint8_t*>(scan_scr) + ((cabac_compact_scratch_bytes(tiles) + 255) & ~(size_t)255));
+  const LutGeom geom = lut_geom(cfg->profile, cfg->method, cfg->Nq);
+  if (d_ops && geom.entries) k_bin_lut<<<(geom.entries + 127) / 128, 128, 0, st>>>(*cfg, lut);
+#define BIN_COUNT(WW, ME) k_bin_count<WW, ME><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, tile_sums)
+  if (sym_width == 1 && cfg->method == ISSCABAC_BIN_EG0) BIN_COUNT(1, ISSCABAC_BIN_EG0);
+  else if (sym_width == 1 && cfg->method == ISSCABAC_BIN_EG2) BIN_COUNT(1, ISSCABAC_BIN_EG2);
+  else if (sym_width == 1 && cfg->method == ISSCABAC_BIN_TU) BIN_COUNT(1, ISSCABAC_BIN_TU);
+  else if (sym_width == 1) BIN_COUNT(1, -1);
+  else if (sym_width == 2) BIN_COUNT(2, -1);
+  else BIN_COUNT(4, -1);
+#undef BIN_COUNT
   if ((rc = exclusive_scan_u32_u64(tile_sums, tile_prefix, tiles, scan_scr, st))) return rc;
-  if (sym_width == 1)
-    k_bin_emit<1><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, d_sym_off, n_streams, tile_stream, tile_prefix, d_op_off, d_ops, ops_cap);
-  else if (sym_width == 2)
-    k_bin_emit<2><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, d_sym_off, n_streams, tile_stream, tile_prefix, d_op_off, d_ops, ops_cap);
-  else
-    k_bin_emit<4><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, d_sym_off, n_streams, tile_stream, tile_prefix, d_op_off, d_ops, ops_cap);
+#define BIN_EMIT(WW, PR, ME) \
+  k_bin_emit<WW, PR, ME><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, d_sym_off, n_streams, tile_stream, tile_prefix, d_op_off, d_ops, ops_cap, lut)
+#define BIN_EMIT_CASE(PR, ME) if (sym_width == 1 && cfg->profile == PR && cfg->method == ME) BIN_EMIT(1, PR, ME); else
+  BIN_EMIT_CASE(ISSCABAC_PROFILE_ISS, ISSCABAC_BIN_EG0)
+  BIN_EMIT_CASE(ISSCABAC_PROFILE_FLAT, ISSCABAC_BIN_EG0)
+  BIN_EMIT_CASE(ISSCABAC_PROFILE_FLAT_EPSUF, ISSCABAC_BIN_EG2)
+  BIN_EMIT_CASE(ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_TU)
+  BIN_EMIT_CASE(ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_EG0)
+  if (sym_width == 1) BIN_EMIT(1, -1, -1);
+  else if (sym_width == 2) BIN_EMIT(2, -1, -1);
+  else BIN_EMIT(4, -1, -1);
+#undef BIN_EMIT_CASE
+#undef BIN_EMIT
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "cabac_binarize_symbols");
 }

@@ -155,3 +155,37 @@ def test_baseline_symbol_configs_properties(I, name, scale):
     if name == "c5":   # the empty stream is the two bytes of start(); finish() (KAT K0)
         b = p1.payload[int(p1.byte_off[0].item()):int(p1.byte_off[1].item())].cpu().numpy()
         assert bytes(b) == bytes.fromhex("fe80")
+
+
+@pytest.mark.parametrize("shift,short", [(0, 0), (1, 0), (7, 5), (13, 40000), (15, 1)])
+def test_binarizer_unaligned_and_short_buffers(I, shift, short):
+    """The op-parallel binarizer writes aligned 16-byte pieces: an op buffer at any byte alignment and one
+    that is too small (filled up to its capacity, nothing written behind it) give the oracle's ops."""
+    import ctypes as C
+    from isscabac_b200 import engine as E
+    rng = np.random.default_rng(23 + shift)
+    n_streams = 300
+    counts = rng.integers(0, 500, size=n_streams)
+    off = np.zeros(n_streams + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    n = int(off[-1])
+    sym = np.minimum(np.floor(rng.exponential(3.0, size=n)), 15).astype(np.uint8)
+    cfg = I.make_cfg(O.PROFILE_FLAT, O.BIN_EG0, 16, 3, 0, 0)
+    ocfg = O.make_cfg(O.PROFILE_FLAT, O.BIN_EG0, 16, 3, 0, 0)
+    want = np.concatenate([O.symbols_to_ops(ocfg, sym[int(off[s]):int(off[s + 1])]) for s in range(n_streams)])
+    total = len(want)
+    cap = total - short
+    dev = torch.device("cuda")
+    L = I.lib()
+    sym_t, off_t = torch.as_tensor(sym, device=dev), torch.as_tensor(off, device=dev)
+    scratch = torch.empty(int(L.cabac_binarize_scratch_bytes(C.c_uint64(n), C.c_uint32(n_streams))), dtype=torch.uint8, device=dev)
+    op_off = torch.empty(n_streams + 1, dtype=torch.int64, device=dev)
+    buf = torch.full((total + 64,), 0xAB, dtype=torch.uint8, device=dev)
+    ops = buf[shift:]
+    E.check(L.cabac_binarize_symbols(C.byref(cfg), C.c_uint32(n_streams), E.vp(off_t), E.vp(sym_t), 1, C.c_uint64(n),
+                                     E.vp(op_off), E.vp(ops), C.c_uint64(cap), E.vp(scratch), E._stream_ptr()))
+    torch.cuda.synchronize()
+    got = buf.cpu().numpy()
+    assert int(op_off[-1].item()) == total
+    assert (got[shift:shift + cap] == want[:cap]).all()
+    assert (got[:shift] == 0xAB).all() and (got[shift + cap:] == 0xAB).all()
