@@ -169,6 +169,15 @@ CB_HD uint32_t encw_bin(EncWide& E, uint32_t w, bool is_ep, const WRow& row) {
   return is_lps ? row.next_lps : row.next_mps;
 }
 
+// encodeBinsEP (Encoder.cpp:278-319; byte-identical to n single encodeBinEP calls) in
+// one step: low' = (low << n) + range * bits.  The caller keeps the window budget: E.n + n <= 53
+// (the fused symbol kernels emit before and after a run, so n <= kEpRunMax with E.n < 32 on entry).
+constexpr uint32_t kEpRunMax = 16;
+CB_HD void encw_ep_run(EncWide& E, uint32_t bits, uint32_t n) {
+  E.W = (E.W << n) + ((uint64_t)(E.range * bits) << 1);
+  E.n += (int32_t)n;
+}
+
 // encodeBinTrm, Encoder.cpp:326-367 (the only op that is a real branch; a handful per stream)
 CB_HD void encw_trm(EncWide& E, uint32_t bin) {
   E.range -= 2;
@@ -290,6 +299,22 @@ CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, uint32_t& tok, const WRow& row) 
   D.f += ns;
   tok = is_lps ? row.next_lps : row.next_mps;
   return (row.mps4 ^ (is_lps ? 0xffffffffu : 0u)) & (1u << (8 * B));   // bin = mps ^ isLPS
+}
+
+// decodeBinsEP (Decoder.cpp:333-421 == n single decodeBinEP calls) in one step.  n bypass decisions
+// are a long division: with R the window, every step is bin = R >= (range << 53); R = (R - bin *
+// (range << 53)) << 1, so after n steps the bins are q = (R >> (54 - n)) / range (R < range << 54
+// on entry keeps q < 2^n) and R' = (rem << 54) + ((R mod 2^(54-n)) << n).  Reads the top 10 + n
+// bits of the window: needs f <= 54 - n, i.e. n <= kEpRunMax after a refill (f < 32).
+CB_HD uint32_t decw_ep_run(DecWide& D, uint32_t n) {
+  const uint32_t A = D.hi >> (22u - n);
+  const uint32_t q = A / D.range;
+  const uint32_t rem = A - q * D.range;
+  const uint32_t h = D.hi & ((1u << (22u - n)) - 1u);
+  D.hi = (rem << 22) | cb_funnel_l(D.lo, h, n);   // (h:lo) << n, n in 1..16
+  D.lo <<= n;
+  D.f += (int32_t)n;
+  return q;
 }
 
 // decodeBinTrm, Decoder.cpp:423-472

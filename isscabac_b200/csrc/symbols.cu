@@ -619,6 +619,20 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
         const int cx = select_ctx(cfg, b, cur.np, prev, up);
         encw_op<0>(E, cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx, sym_bin(cur, b), ctx, tab, n_ctx);
         ++b;
+        if (cfg.profile == PROFILE_FLAT_EPSUF && b > cur.np && b <= cur.len) {
+          // the prefix is out and everything behind it is bypass-coded: the whole suffix in one step per 16 bins
+          // (encodeBinsEP); a word leaves before and after, so the run never meets a full window and the
+          // step ends with fewer than 32 pending bits like any other
+          uint32_t left = cur.len + 1u - b;
+          do {
+            const uint32_t c = left < kEpRunMax ? left : kEpRunMax;
+            encw_emit(E);
+            encw_ep_run(E, (cur.suf >> (left - c)) & ((1u << c) - 1u), c);
+            left -= c;
+          } while (left);
+          encw_emit(E);
+          b = cur.len + 1u;
+        }
       }
     }
     if (__any_sync(0xffffffffu, E.n >= kLazy)) encw_emit(E);   // lazy, voted: all 32 lanes are here
@@ -671,7 +685,24 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_symbols_wide(Sym
         const int cx = select_ctx(cfg, sd.n + 1, sd.np, prev, up);
         const uint32_t bin = decw_op<0>(D, cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx, ctx, tab, n_ctx);
         uint32_t v = 0;
-        if (symdec_push(sd, bin, cfg, v)) {
+        bool done = symdec_push(sd, bin, cfg, v);
+        if (cfg.profile == PROFILE_FLAT_EPSUF && cfg.method >= BIN_EG0 && cfg.method <= BIN_EG2 && !done && sd.np != 0xffffffffu) {
+          // the prefix just ended and its suffix is bypass-coded: all of it in one step per 16 bins (decodeBinsEP),
+          // the window topped up before (the run reads up to 26 bits) and after (the next decisions need theirs)
+          uint32_t left = sd.ns_left;
+          do {
+            const uint32_t c = left < kEpRunMax ? left : kEpRunMax;
+            decw_refill(D);
+            sd.suf = (sd.suf << c) | decw_ep_run(D, c);
+            left -= c;
+          } while (left);
+          decw_refill(D);
+          sd.n += sd.ns_left;
+          sd.ns_left = 0;
+          v = (uint32_t)((((uint64_t)1 << (cfg.method - BIN_EG0)) * ((((uint64_t)1) << (sd.np - 1)) - 1u)) + sd.suf);
+          done = true;
+        }
+        if (done) {
           store_sym(dst, P.sym_width, i, v);
           // the finished symbol's bin string as the next symbol's neighbour: its length, the
           // position of its first zero (length + 1 when it has none) and its suffix bits

@@ -195,6 +195,74 @@ int emul_decode_ops_wide(uint32_t n_streams, const uint64_t* byte_off, const uin
   return 0;
 }
 
+// the same op arrays with every run of bypass ops coded by the multi-bin steps (encw_ep_run /
+// decw_ep_run, chunks of up to kEpRunMax bins, emission / refill before and after a run as in the
+// fused symbol kernels); everything else goes down the general path
+int emul_encode_ops_wide_runs(uint32_t n_streams, const uint64_t* op_off, const uint8_t* ops,
+                              const uint8_t* ctx_init, uint32_t n_ctx, int per_stream,
+                              uint8_t* slab, uint64_t stride, uint32_t* lens, uint32_t max_run) {
+  std::vector<uint32_t> cs(n_ctx + 1);
+  int ovf = 0;
+  for (uint32_t s = 0; s < n_streams; ++s) {
+    for (uint32_t c = 0; c < n_ctx; ++c) cs[c] = ctx_init[(per_stream ? (uint64_t)s * n_ctx : 0) + c] & 127u;
+    cs[n_ctx] = kEpState;
+    HostCtx ctx{cs.data()};
+    HostTab tab;
+    EncWide E;
+    encw_start(E, slab + s * stride, (uint32_t)stride);
+    const uint8_t* p = ops + op_off[s];
+    const uint64_t n = op_off[s + 1] - op_off[s];
+    for (uint64_t i = 0; i < n;) {
+      if ((p[i] >> 1) > kOpTrmCode) {
+        uint32_t c = 0, bits = 0;
+        while (i < n && (p[i] >> 1) > kOpTrmCode && c < max_run) { bits = (bits << 1) | (p[i] & 1u); ++c; ++i; }
+        encw_emit(E);
+        encw_ep_run(E, bits, c);
+        encw_emit(E);
+      } else {
+        encw_general(E, p[i++], ctx, tab, n_ctx);
+      }
+    }
+    lens[s] = encw_finish(E);
+    ovf |= lens[s] > stride;
+  }
+  return ovf;
+}
+
+int emul_decode_ops_wide_runs(uint32_t n_streams, const uint64_t* byte_off, const uint8_t* bytes,
+                              const uint64_t* op_off, const uint8_t* ops,
+                              const uint8_t* ctx_init, uint32_t n_ctx, int per_stream,
+                              uint8_t* bins, uint8_t* ok, uint32_t max_run) {
+  std::vector<uint32_t> cs(n_ctx + 1);
+  for (uint32_t s = 0; s < n_streams; ++s) {
+    for (uint32_t c = 0; c < n_ctx; ++c) cs[c] = ctx_init[(per_stream ? (uint64_t)s * n_ctx : 0) + c] & 127u;
+    cs[n_ctx] = kEpState;
+    HostCtx ctx{cs.data()};
+    HostTab tab;
+    DecWide D;
+    decw_start(D, bytes + byte_off[s], (uint32_t)(byte_off[s + 1] - byte_off[s]));
+    const uint8_t* p = ops + op_off[s];
+    uint8_t* q = bins + op_off[s];
+    const uint64_t n = op_off[s + 1] - op_off[s];
+    for (uint64_t i = 0; i < n;) {
+      if ((p[i] >> 1) > kOpTrmCode) {
+        uint32_t c = 0;
+        while (i + c < n && (p[i + c] >> 1) > kOpTrmCode && c < max_run) ++c;
+        decw_refill(D);
+        const uint32_t v = decw_ep_run(D, c);
+        decw_refill(D);
+        for (uint32_t k = 0; k < c; ++k) q[i + k] = (uint8_t)((v >> (c - 1 - k)) & 1u);
+        i += c;
+      } else {
+        q[i] = (uint8_t)decw_general(D, p[i], ctx, tab, n_ctx);
+        ++i;
+      }
+    }
+    ok[s] = (uint8_t)decw_finish(D);
+  }
+  return 0;
+}
+
 // direct hook for the (practically unreachable) carry walk past a 0xFFFFFFFF pending word
 void emul_carry_walk(uint32_t* row, uint32_t wp, uint32_t cap_words) { encw_carry_walk(wp, cap_words, row + wp); }
 

@@ -195,3 +195,39 @@ def test_wide_carry_walk(emul):
     row = be([0xFFFFFFFF, 0xFFFFFFFF, 7])
     emul.emul_carry_walk(p(row, u32p), C.c_uint32(2), C.c_uint32(1))       # capacity 1 word: word 1 is not in memory
     assert list(row.view(np.uint8).view(">u4")) == [0, 0xFFFFFFFF, 7]
+
+
+@pytest.mark.parametrize("max_run", [1, 2, 7, 16])
+def test_wide_bypass_runs(emul, max_run):
+    """encodeBinsEP / decodeBinsEP as ONE step of the wide formulation (encw_ep_run: low' = (low << n) +
+    range * bits; decw_ep_run: long division of the window by range) give the bytes / bins of n single
+    bypass steps -- the reference's own equivalence, here against the oracle."""
+    rng = np.random.default_rng(31 + max_run)
+    n_streams, n_ctx = 300, 5
+    lens = rng.integers(0, 900, size=n_streams)
+    off = np.zeros(n_streams + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    n = int(off[-1])
+    code = rng.integers(0, n_ctx, size=n).astype(np.uint8)
+    # long runs of bypass ops between context-coded stretches, bins of either skew
+    run = np.repeat(rng.random(n // 8 + 1) < 0.55, 8)[:n]
+    code[run] = O.OP8_EP
+    bins = (rng.random(n) < rng.choice([0.1, 0.5, 0.9], size=n)).astype(np.uint8)
+    ops = ((code << 1) | bins).astype(np.uint8)
+    ci = rng.integers(0, 126, size=(n_streams, n_ctx)).astype(np.uint8)
+    slab_ref, lens_ref = O.encode_ops(ops, off, ci, out_stride=1024)
+    slab = np.zeros((n_streams, 1024), dtype=np.uint8)
+    ln = np.zeros(n_streams, dtype=np.uint32)
+    ovf = emul.emul_encode_ops_wide_runs(C.c_uint32(n_streams), p(off, u64p), p(ops, u8p), p(ci.reshape(-1), u8p),
+                                         C.c_uint32(n_ctx), 1, p(slab, u8p), C.c_uint64(1024), p(ln, u32p), C.c_uint32(max_run))
+    assert ovf == 0 and (ln == lens_ref).all()
+    live = np.arange(1024)[None, :] < lens_ref[:, None]
+    assert (slab[live] == slab_ref[live]).all()
+    payload, boff = O.compact(slab_ref, lens_ref)
+    pb = np.concatenate([payload, np.full(64, 0xA5, np.uint8)])
+    out = np.zeros(n + 1, dtype=np.uint8)
+    ok = np.zeros(n_streams, dtype=np.uint8)
+    emul.emul_decode_ops_wide_runs(C.c_uint32(n_streams), p(np.ascontiguousarray(boff, dtype=np.uint64), u64p), p(pb, u8p),
+                                   p(off, u64p), p(ops, u8p), p(ci.reshape(-1), u8p), C.c_uint32(n_ctx), 1,
+                                   p(out, u8p), p(ok, u8p), C.c_uint32(max_run))
+    assert ok.all() and (out[:n] == bins).all()
