@@ -172,6 +172,32 @@ int cabac_iss_ctx_stats(const isscabac_symcfg* cfg, uint32_t n_streams, const ui
 int cabac_iss_ctx_from_counters(const isscabac_symcfg* cfg, const uint64_t* h_counters, uint32_t n_groups,
                                 int equal_prob, double* h_p0, uint8_t* h_ctx_quant, uint8_t* h_ctx_state);
 
+/* ---- quantiser in front of the coder (ISS/quantizeWrapper.m, ISS/quantize.m) -- */
+/* Replaces quantizeWrapper(x, qParam) (quantizeWrapper.m:1-88) for a batch of matrices: dead zone
+ * below the data's deadzone_quant quantile (:22-36; negative = none), then Lloyd-Max (quantizeLloyd,
+ * :91-176; qParam.GMM = 1), uniformly spaced (quantize.m:59-75 between the q_lo / q_hi quantiles) or
+ * caller-given centroids (qParam.fixedCentroids) on the rest.  Matrix m is d_x[elem_off[m] ..
+ * elem_off[m+1]) in double precision (the transformed values, ISS.m:104-105).  Outputs: d_groups =
+ * group index - 1 per element (u8: the coder's symbols, ISS.m:108-110), d_centroids[m * N ..] = the N
+ * centroids (dead-zone mean first), d_iters (optional) = Lloyd iterations run.  Sums are taken over
+ * the sorted data, so centroids agree with the reference formulation to rounding, not bit for bit. */
+enum { ISSCABAC_QUANT_UNIFORM = 0, ISSCABAC_QUANT_LLOYD = 1, ISSCABAC_QUANT_FIXED = 2 };
+typedef struct isscabac_quantcfg {
+  int32_t N;               /* number of centroids including the dead zone's (qParam.N, ISS.m:42), 1..32 */
+  int32_t mode;            /* ISSCABAC_QUANT_* */
+  double deadzone_quant;   /* qParam.deadzoneQuant (ISS.m:44: 0.7); < 0 = no dead zone */
+  double q_lo, q_hi;       /* qParam.quantileprob for the uniform mode (default [0 1]) */
+  double tol;              /* Lloyd stop: mean squared centroid change (quantizeWrapper.m:102: eps) */
+  int32_t max_iter;        /* quantizeWrapper.m:103: 100 */
+  int32_t reserved;
+} isscabac_quantcfg;
+/* d_scratch: cabac_quantize_scratch_bytes(n_matrices, max_elems) bytes (only used when a matrix has
+ * more than 8192 elements); max_elems = the largest matrix of the batch. */
+size_t cabac_quantize_scratch_bytes(uint32_t n_matrices, uint64_t max_elems);
+int cabac_quantize_matrices(const isscabac_quantcfg* cfg, uint32_t n_matrices, const uint64_t* d_elem_off,
+                            uint64_t max_elems, const double* d_x, const double* d_fixed_centroids,
+                            uint8_t* d_groups, double* d_centroids, uint32_t* d_iters, void* d_scratch, void* stream);
+
 /* ---- host-buffer API (what a reference-side caller binds) ------------------ */
 /* Same semantics with HOST pointers; all host<->device copies happen inside the call.
  * Encode returns the compacted payload and the offset table: h_payload (capacity

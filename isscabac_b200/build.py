@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libisscabac.so")
-SOURCES = ["kernels.cu", "symbols.cu", "iss_stats.cu", "stats.cu", "host_api.cu", "handle.cu", "dispatch.cpp", "container.cpp"]
+SOURCES = ["kernels.cu", "symbols.cu", "iss_stats.cu", "stats.cu", "quantize.cu", "host_api.cu", "handle.cu", "dispatch.cpp", "container.cpp"]
 HEADERS = ["cabac_lane.cuh", "cabac_wide.cuh", "wide_common.cuh", "internal.h", os.path.join("..", "..", "include", "isscabac.h"),
            os.path.join("..", "..", "include", "SimpleCABAC.hpp")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",

@@ -1,0 +1,295 @@
+// quantize.cu -- the quantiser in front of the coder on the device:
+// ISS/quantizeWrapper.m:1-88 (dead zone by a data quantile, then Lloyd-Max / uniform / fixed
+// centroids on the rest) with quantizeLloyd (:91-176) and ISS/quantize.m:59-84 behind it.
+// Output per matrix: the group index of every element minus one -- the symbols the coder takes
+// (ISS.m:108-110: param.gW = miscW.group-1) -- and the N centroids.
+//
+// One CTA per matrix (W 400x20, H 109x20 in ISS.m; a batch of tracks = thousands of matrices).
+// The reference walks masks over the unsorted data on every Lloyd iteration; here the data is sorted
+// once (bitonic, shared memory), a prefix sum over the sorted values gives any group's mean as a
+// difference of two entries, and a group is an interval of the sorted array found by binary search,
+// so one iteration costs one warp a few dozen instructions whatever the matrix size.  Double
+// precision throughout like the reference.  The sums are taken in sorted order, the reference's in
+// storage order: centroids agree to rounding (1e-12 relative in tests/test_gpu_quantize.py), group
+// indices are identical except for elements that sit within rounding of a decision threshold.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/isscabac.h"
+#include "internal.h"
+
+using namespace isscabac_internal;
+
+namespace {
+
+constexpr int QT = 512;            // threads per CTA
+constexpr int QMAXN = 32;          // centroids: one lane per group
+constexpr uint32_t QSMEM_ELEMS = 8192;   // largest padded matrix whose sort + prefix arrays fit shared memory
+
+struct QParams {
+  isscabac_quantcfg cfg;
+  uint32_t n_mat, npad_max;
+  const uint64_t* off;
+  const double* x;
+  const double* fixed;
+  uint8_t* groups;
+  double* centroids;
+  uint32_t* iters;
+  double* scratch;   // (2 * npad_max + 2) doubles per CTA when the arrays do not fit shared memory
+};
+
+// first index in [0, n) with a[idx] >= v (n when there is none)
+__device__ __forceinline__ uint32_t lower_bound(const double* a, uint32_t n, double v) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// MATLAB quantile of a sorted vector (prctile: sample i is the (i - 0.5)/n quantile); quantizeWrapper.m:23, quantize.m:61
+__device__ __forceinline__ double sorted_quantile(const double* xs, uint32_t n, double p) {
+  double r = p * (double)n;
+  long long k = (long long)floor(r + 0.5);
+  long long kp1 = k + 1;
+  r -= (double)k;
+  if (k < 1) k = 1;
+  if (k > (long long)n) k = n;
+  if (kp1 > (long long)n) kp1 = n;
+  return (0.5 + r) * xs[kp1 - 1] + (0.5 - r) * xs[k - 1];
+}
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sorted copy of c[0..N) over the lanes (quantize.m:79 `centroids = sort(centroids)`): rank sort, N <= 32
+__device__ __forceinline__ double warp_sort(double c, int g, int N) {
+  int rank = 0;
+  for (int h = 0; h < N; ++h) {
+    const double o = __shfl_sync(0xffffffffu, c, h);
+    if (g < N && (o < c || (o == c && h < g))) ++rank;
+  }
+  double out = 0.0;
+  for (int h = 0; h < N; ++h) {
+    const double o = __shfl_sync(0xffffffffu, c, h);
+    const int r = __shfl_sync(0xffffffffu, rank, h);
+    if (r == g) out = o;
+  }
+  return out;
+}
+
+__global__ void __launch_bounds__(QT) k_quantize(QParams P) {
+  extern __shared__ __align__(16) uint8_t q_smem[];
+  __shared__ double s_part[QT / 32];
+  __shared__ double s_cent[QMAXN];       // final centroids of the part outside the dead zone (sorted)
+  __shared__ uint32_t s_iters;
+  const bool in_smem = P.npad_max <= QSMEM_ELEMS;
+  double* xs = in_smem ? reinterpret_cast<double*>(q_smem) : P.scratch + (size_t)blockIdx.x * (2ull * P.npad_max + 2);
+  double* ps = xs + P.npad_max;          // ps[j] = sum of the j smallest values
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int N = P.cfg.N;
+
+  for (uint32_t m = blockIdx.x; m < P.n_mat; m += gridDim.x) {
+    const uint64_t o0 = P.off[m];
+    const uint32_t n = (uint32_t)(P.off[m + 1] - o0);
+    const double* xin = P.x + o0;
+    uint8_t* gout = P.groups + o0;
+    double* cout = P.centroids + (size_t)m * N;
+    __syncthreads();   // the previous matrix is done with the arrays
+    if (n == 0) {
+      if (tid < N) cout[tid] = 0.0;
+      if (tid == 0 && P.iters) P.iters[m] = 0;
+      continue;
+    }
+    uint32_t npad = 2;
+    while (npad < n) npad <<= 1;
+    for (uint32_t i = tid; i < npad; i += QT) xs[i] = i < n ? xin[i] : INFINITY;
+    __syncthreads();
+    // ---- bitonic sort, ascending
+    for (uint32_t k = 2; k <= npad; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t t = tid; t < (npad >> 1); t += QT) {
+          const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+          const double a = xs[i], b = xs[l];
+          if ((a > b) == ((i & k) == 0)) { xs[i] = b; xs[l] = a; }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- prefix sums of the sorted values: a contiguous run per thread, block scan of the run sums
+    const uint32_t per = (n + QT - 1) / QT;
+    const uint32_t r0 = min((uint32_t)tid * per, n), r1 = min(r0 + per, n);
+    double run = 0.0;
+    for (uint32_t i = r0; i < r1; ++i) run += xs[i];
+    double inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_part[wid] = inc;
+    __syncthreads();
+    double base = inc - run;
+    for (int w = 0; w < wid; ++w) base += s_part[w];
+    for (uint32_t i = r0; i < r1; ++i) { ps[i] = base; base += xs[i]; }
+    if (r1 == n && r0 < n) ps[n] = base;
+    __syncthreads();
+
+    // ---- dead zone (quantizeWrapper.m:22-36): everything below the data's deadzone_quant quantile
+    double thr = -INFINITY;
+    uint32_t m_dz = 0;
+    if (P.cfg.deadzone_quant >= 0.0) {
+      thr = sorted_quantile(xs, n, P.cfg.deadzone_quant);
+      m_dz = lower_bound(xs, n, thr);
+    }
+    const bool has_dz = m_dz != 0;
+    const int Nr = has_dz ? N - 1 : N;           // centroids for the rest
+    const double* xr = xs + m_dz;
+    const double* pr = ps + m_dz;
+    const uint32_t nr = n - m_dz;                 // > 0: the quantile never exceeds the maximum
+
+    // ---- centroids of the rest: one warp, lane g = group g
+    if (wid == 0) {
+      const int g = lane;
+      const double mn = xr[0], mx = xr[nr - 1];
+      double c = 0.0;
+      uint32_t iters = 0;
+      if (P.cfg.mode == ISSCABAC_QUANT_FIXED) {                       // quantizeWrapper.m:39-40
+        c = g < Nr ? P.fixed[g + (has_dz ? 1 : 0)] : 0.0;
+        c = warp_sort(c, g, Nr);
+      } else {
+        // quantize.m:61-75: linspace between the border quantiles ([0 1] = min and max for Lloyd's start)
+        double a = mn, b = mx;
+        if (P.cfg.mode == ISSCABAC_QUANT_UNIFORM) {
+          a = sorted_quantile(xr, nr, P.cfg.q_lo);
+          b = sorted_quantile(xr, nr, P.cfg.q_hi);
+        }
+        c = (Nr == 1 || g == Nr - 1) ? b : a + (double)g * (b - a) / (double)(Nr - 1);
+        if (a > b) c = warp_sort(c, g, Nr);
+      }
+      if (P.cfg.mode == ISSCABAC_QUANT_LLOYD) {                       // quantizeLloyd, quantizeWrapper.m:121-171
+        // group g = the sorted values in [lo, hi): edges(k) <= x < edges(k+1) (quantize.m:81)
+        double up = __shfl_down_sync(0xffffffffu, c, 1);
+        double mid = 0.5 * (c + up);                                   // edge between groups g and g+1
+        uint32_t hi = g < Nr - 1 ? lower_bound(xr, nr, mid) : nr;
+        uint32_t lo = __shfl_up_sync(0xffffffffu, hi, 1);
+        if (g == 0) lo = 0;
+        // edges = [min(min(x),min(c)), mids, max(max(x),max(c))] (:135): e_lo / e_hi = this group's two edges
+        double cmin = warp_min(g < Nr ? c : INFINITY), cmax = warp_max(g < Nr ? c : -INFINITY);
+        double e_hi = g < Nr - 1 ? mid : fmax(mx, cmax);
+        double e_lo = __shfl_up_sync(0xffffffffu, e_hi, 1);
+        if (g == 0) e_lo = fmin(mn, cmin);
+        double old = c;
+        for (int it = 0; it < P.cfg.max_iter; ++it) {
+          ++iters;
+          double cn = 0.5 * (e_lo + e_hi);                             // :143
+          if (g < Nr && hi > lo) cn = (pr[hi] - pr[lo]) / (double)(hi - lo);   // :146-151, mean of the group
+          // edges from the updated centroids in group order (:156), groups from the sorted ones (:159-161)
+          up = __shfl_down_sync(0xffffffffu, cn, 1);
+          cmin = warp_min(g < Nr ? cn : INFINITY);
+          cmax = warp_max(g < Nr ? cn : -INFINITY);
+          e_hi = g < Nr - 1 ? 0.5 * (cn + up) : fmax(mx, cmax);
+          e_lo = __shfl_up_sync(0xffffffffu, e_hi, 1);
+          if (g == 0) e_lo = fmin(mn, cmin);
+          c = warp_sort(cn, g, Nr);
+          up = __shfl_down_sync(0xffffffffu, c, 1);
+          mid = 0.5 * (c + up);
+          hi = g < Nr - 1 ? lower_bound(xr, nr, mid) : nr;
+          lo = __shfl_up_sync(0xffffffffu, hi, 1);
+          if (g == 0) lo = 0;
+          const double d = g < Nr ? (c - old) * (c - old) : 0.0;
+          if (warp_sum(d) / (double)Nr < P.cfg.tol) break;            // :167
+          old = c;
+        }
+      }
+      if (g < Nr) s_cent[g] = c;
+      if (g == 0) s_iters = iters;
+    }
+    __syncthreads();
+    // ---- outputs: centroids (dead-zone mean first, :57) and the group of every element minus one
+    if (tid < N) cout[tid] = has_dz ? (tid == 0 ? ps[m_dz] / (double)m_dz : s_cent[tid - 1]) : s_cent[tid];
+    if (tid == 0 && P.iters) P.iters[m] = s_iters;
+    for (uint32_t i = tid; i < n; i += QT) {
+      const double v = xin[i];
+      uint32_t grp;
+      if (has_dz && v < thr) {
+        grp = 0;
+      } else {
+        uint32_t cnt = 0;                                              // number of group edges <= v
+        for (int k = 0; k + 1 < Nr; ++k) cnt += (0.5 * (s_cent[k] + s_cent[k + 1]) <= v) ? 1u : 0u;
+        grp = cnt + (has_dz ? 1u : 0u);
+      }
+      gout[i] = (uint8_t)grp;
+    }
+  }
+}
+
+uint32_t pad_pow2(uint64_t n) {
+  uint32_t p = 2;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t cabac_quantize_scratch_bytes(uint32_t n_matrices, uint64_t max_elems) {
+  const uint32_t npad = pad_pow2(max_elems);
+  if (npad <= QSMEM_ELEMS) return 16;
+  const uint32_t grid = (uint32_t)sm_count() * 2u < n_matrices ? (uint32_t)sm_count() * 2u : n_matrices;
+  return (size_t)(grid ? grid : 1) * (2ull * npad + 2) * sizeof(double);
+}
+
+int cabac_quantize_matrices(const isscabac_quantcfg* cfg, uint32_t n_matrices, const uint64_t* d_elem_off,
+                            uint64_t max_elems, const double* d_x, const double* d_fixed_centroids,
+                            uint8_t* d_groups, double* d_centroids, uint32_t* d_iters, void* d_scratch, void* stream) {
+  if (!cfg) { set_error("quantcfg is NULL"); return ISSCABAC_ERR_INVALID; }
+  if (cfg->N < 1 || cfg->N > QMAXN) { set_error("N must be 1..%d", QMAXN); return ISSCABAC_ERR_INVALID; }
+  if (cfg->mode != ISSCABAC_QUANT_UNIFORM && cfg->mode != ISSCABAC_QUANT_LLOYD && cfg->mode != ISSCABAC_QUANT_FIXED) {
+    set_error("unknown quantiser mode %d", cfg->mode);
+    return ISSCABAC_ERR_INVALID;
+  }
+  if (cfg->deadzone_quant >= 0.0 && cfg->N < 2) { set_error("a dead zone needs N >= 2"); return ISSCABAC_ERR_INVALID; }
+  if (cfg->deadzone_quant > 1.0) { set_error("deadzone_quant must be a probability (or negative for none)"); return ISSCABAC_ERR_INVALID; }
+  if (cfg->mode == ISSCABAC_QUANT_FIXED && !d_fixed_centroids) { set_error("fixed mode needs centroids"); return ISSCABAC_ERR_INVALID; }
+  if (n_matrices == 0) return ISSCABAC_OK;
+  if (!d_elem_off || !d_x || !d_groups || !d_centroids) { set_error("cabac_quantize_matrices: null pointer"); return ISSCABAC_ERR_INVALID; }
+  if (max_elems > (1ull << 26)) { set_error("matrix too large for one CTA"); return ISSCABAC_ERR_UNSUPPORTED; }
+  QParams P;
+  memset(&P, 0, sizeof P);
+  P.cfg = *cfg; P.n_mat = n_matrices; P.npad_max = pad_pow2(max_elems);
+  P.off = d_elem_off; P.x = d_x; P.fixed = d_fixed_centroids; P.groups = d_groups; P.centroids = d_centroids;
+  P.iters = d_iters; P.scratch = static_cast<double*>(d_scratch);
+  size_t smem = 0;
+  uint32_t grid = n_matrices;
+  if (P.npad_max <= QSMEM_ELEMS) {
+    smem = (2ull * P.npad_max + 2) * sizeof(double);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_quantize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  } else {
+    if (!d_scratch) { set_error("matrices of more than %u elements need the scratch buffer", QSMEM_ELEMS); return ISSCABAC_ERR_INVALID; }
+    const uint32_t cap = (uint32_t)sm_count() * 2u;
+    if (grid > cap) grid = cap;
+  }
+  k_quantize<<<grid, QT, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_quantize");
+}
+
+}  // extern "C"
