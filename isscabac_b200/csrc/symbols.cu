@@ -425,6 +425,8 @@ struct SymParams {
   const uint8_t* bytes;
   void* out_symbols;
   uint8_t* finish_ok;
+  const uint4* lut;        // op strings by table (k_bin_lut) for the fused encoder, or NULL
+  uint32_t lut_entries, lut_dom;
 };
 
 __device__ __forceinline__ uint32_t* setup_smem(const SymParams& P, uint8_t* smem, uint32_t s, bool valid) {
@@ -580,12 +582,26 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
   const LaneCtx lc{ctx, tab, n_ctx, P.ctx_init, P.per_stream_init};
   const SymCfg cfg = fixed_cfg<PROF, METH>(P.cfg);
   const uint32_t cap = (uint32_t)(P.slab_stride > 0xfffffffcull ? 0xfffffffcull : P.slab_stride);
+  // op strings by table (see k_bin_lut): behind the context blocks in shared memory; a symbol whose key is
+  // in the table yields its ops with one byte load each, any other symbol takes the closed-form route
+  // (compiled in only where it pays: the neighbour-conditioned profiles; the FLAT rules fold to a few instructions anyway)
+  constexpr bool kLutProfile = PROF == PROFILE_ISS || PROF == PROFILE_DEMO || PROF < 0;
+  const bool lut_on = kLutProfile && (cfg.profile == PROFILE_ISS || cfg.profile == PROFILE_DEMO) && P.lut != nullptr;
+  uint32_t lut0 = 0;
+  if (lut_on) {
+    uint8_t* lp = smem + WIDE_TAB_BYTES + (size_t)(blockDim.x >> 5) * (P.n_ctx + 1) * 32 * 4;
+    for (uint32_t e = threadIdx.x; e < P.lut_entries; e += blockDim.x) reinterpret_cast<uint4*>(lp)[e] = __ldg(P.lut + e);
+    lut0 = (uint32_t)__cvta_generic_to_shared(lp);
+    __syncthreads();
+  }
   EncWide E;
   encw_start(E, nullptr, 0);
   const uint8_t* src = nullptr;     // first symbol of the stream
   uint32_t i = 0, cnt = 0, row = 0; // next symbol to fetch (stream-relative), symbols in the stream, row in the column
   SymCode cur = {0, 0, 0}, prev = {0, 0, 0};
-  uint32_t b = 1;                   // next bin of `cur`; b > cur.len: fetch the next symbol first
+  uint32_t b = 1, len = 0;          // next bin of the current symbol and its bin count; b > len: fetch the next symbol first
+  uint32_t abase = 0;               // table route: shared-window address of the current symbol's op string (0 = closed form)
+  uint32_t curv = 0, prevv = 0;     // values of the current symbol and of the one before it
   uint32_t nextv = 0;               // value of symbol i, loaded one symbol ahead
   bool up = false, active = false, have = s < P.n_streams;
   if (have && order) s = order[s];
@@ -596,18 +612,18 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
       cnt = (uint32_t)(P.sym_off[s + 1] - s0);
       src = static_cast<const uint8_t*>(P.symbols) + s0 * (uint64_t)P.sym_width;
       encw_start(E, P.slab + (uint64_t)s * P.slab_stride, cap);
-      i = 0; row = 0; cur = SymCode{0, 0, 0}; prev = cur; b = 1; up = false;
+      i = 0; row = 0; cur = SymCode{0, 0, 0}; prev = cur; b = 1; len = 0; abase = 0; curv = 0; prevv = 0; up = false;
       nextv = cnt ? load_sym(src, P.sym_width, 0) : 0u;
       active = true;
     }
     if (!__any_sync(0xffffffffu, active)) break;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (active && (b <= cur.len || i < cnt)) {
+      if (active && (b <= len || i < cnt)) {
         if (j == 2 && E.n >= kLazy) encw_emit(E);   // window budget of a 4-bin group, see kLazy
-        if (b > cur.len) {
-          prev = cur;
-          cur = sym_code(nextv, cfg.Nq, cfg.method);
+        if (b > len) {
+          prevv = curv;
+          curv = nextv;
           // the symbol after this one is requested now and used a symbol (several bins) later: a lane
           // that runs alone at the end of a ragged job must not wait for HBM once per symbol
           if (i + 1 < cnt) nextv = load_sym(src, P.sym_width, i + 1);
@@ -615,9 +631,30 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
           ++i;
           if (++row == cfg.rows) row = 0;
           b = 1;
+          const bool cur_is_code = abase == 0;   // `cur` still describes the symbol before this one
+          abase = 0;
+          if (lut_on) {
+            const uint32_t key = lut_index(cfg, P.lut_dom, curv, prevv, up);
+            if (key != LUT_ESC) {
+              const uint32_t e = lut0 + (key << 4);
+              asm volatile("ld.shared.u8 %0, [%1];" : "=r"(len) : "r"(e + 15u));
+              if (len) abase = e;   // 0 = the string has more than 15 ops
+            }
+          }
+          if (!abase) {
+            prev = cur_is_code ? cur : sym_code(prevv, cfg.Nq, cfg.method);
+            cur = sym_code(curv, cfg.Nq, cfg.method);
+            len = cur.len;
+          }
         }
-        const int cx = select_ctx(cfg, b, cur.np, prev, up);
-        encw_op<0>(E, cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx, sym_bin(cur, b), ctx, tab, n_ctx);
+        uint32_t op;
+        if (abase) {
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(op) : "r"(abase + b - 1u));
+        } else {
+          const int cx = select_ctx(cfg, b, cur.np, prev, up);
+          op = ((cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx) << 1) | sym_bin(cur, b);
+        }
+        encw_op<0>(E, op >> 1, op, ctx, tab, n_ctx);
         ++b;
         if (cfg.profile == PROFILE_FLAT_EPSUF && b > cur.np && b <= cur.len) {
           // the prefix is out and everything behind it is bypass-coded: the whole suffix in one step per 16 bins
@@ -636,7 +673,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
       }
     }
     if (__any_sync(0xffffffffu, E.n >= kLazy)) encw_emit(E);   // lazy, voted: all 32 lanes are here
-    if (active && !(b <= cur.len || i < cnt)) {   // stream complete: finish(), then take the next unclaimed one
+    if (active && !(b <= len || i < cnt)) {   // stream complete: finish(), then take the next unclaimed one
       const uint32_t len = encw_finish(E);
       P.lengths[s] = len;
       if (len > cap && P.overflow) atomicOr(P.overflow, 1u);
@@ -728,11 +765,24 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_symbols_wide(Sym
 
 // persistent launch: as many warps as the streams need, at most what is resident on the device
 template <class K>
-int launch_sym_wide(K kernel, const SymParams& P, cudaStream_t st, const char* name, bool& done) {
+int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char* name, bool& done, bool want_lut = false) {
+  SymParams P = P_in;
   uint32_t nw, grid;
   size_t smem;
   done = false;
   if (!wide_geometry(P.n_streams, P.n_ctx, nw, grid, smem)) return ISSCABAC_OK;
+  // op strings by table for the encoder when they fit shared memory behind the context blocks
+  const LutGeom geom = lut_geom(P.cfg.profile, P.cfg.method, P.cfg.Nq);
+  uint4* lut = nullptr;
+  if (want_lut && geom.entries && (P.cfg.profile == ISSCABAC_PROFILE_ISS || P.cfg.profile == ISSCABAC_PROFILE_DEMO) &&
+      smem + geom.entries * sizeof(uint4) <= smem_limit()) {
+    int rc = keep_pool_cached();
+    if (rc) return rc;
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&lut), geom.entries * sizeof(uint4), st));
+    k_bin_lut<<<(geom.entries + 127) / 128, 128, 0, st>>>(P.cfg, lut);
+    P.lut = lut; P.lut_entries = geom.entries; P.lut_dom = geom.dom;
+    smem += geom.entries * sizeof(uint4);
+  }
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(nw * 32), smem));
@@ -755,6 +805,7 @@ int launch_sym_wide(K kernel, const SymParams& P, cudaStream_t st, const char* n
   kernel<<<grid, nw * 32, smem, st>>>(P, counter, order);
   cudaError_t e = cudaGetLastError();
   if (order) cudaFreeAsync(order, st);
+  if (lut) cudaFreeAsync(lut, st);
   done = true;
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, name);
 }
@@ -875,14 +926,15 @@ int cabac_encode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const u
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d_bits_after_symbol) return launch_sym(k_encode_symbols<true>, P, st, "k_encode_symbols");   // getNumBits() trace
   bool done;
+  constexpr bool kWantLut = true;
 #define SYM_WIDE_CASE(K, PR, ME) \
-  if (cfg->profile == PR && cfg->method == ME) rc = launch_sym_wide(K<PR, ME>, P, st, #K, done); else
+  if (cfg->profile == PR && cfg->method == ME) rc = launch_sym_wide(K<PR, ME>, P, st, #K, done, kWantLut); else
   SYM_WIDE_CASE(k_encode_symbols_wide, ISSCABAC_PROFILE_ISS, ISSCABAC_BIN_EG0)
   SYM_WIDE_CASE(k_encode_symbols_wide, ISSCABAC_PROFILE_FLAT, ISSCABAC_BIN_EG0)
   SYM_WIDE_CASE(k_encode_symbols_wide, ISSCABAC_PROFILE_FLAT_EPSUF, ISSCABAC_BIN_EG2)
   SYM_WIDE_CASE(k_encode_symbols_wide, ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_TU)
   SYM_WIDE_CASE(k_encode_symbols_wide, ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_EG0)
-  rc = launch_sym_wide(k_encode_symbols_wide<-1, -1>, P, st, "k_encode_symbols_wide", done);
+  rc = launch_sym_wide(k_encode_symbols_wide<-1, -1>, P, st, "k_encode_symbols_wide", done, kWantLut);
   if (rc || done) return rc;
   return launch_sym(k_encode_symbols<false>, P, st, "k_encode_symbols");
 }
@@ -901,6 +953,7 @@ int cabac_decode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const u
   P.sym_off = d_sym_off; P.ctx_init = d_ctx_init; P.byte_off = d_byte_off; P.bytes = d_bytes;
   P.out_symbols = d_symbols; P.finish_ok = d_finish_ok;
   bool done;
+  constexpr bool kWantLut = false;   // the decoder's contexts depend on the bins it decodes
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SYM_WIDE_CASE(k_decode_symbols_wide, ISSCABAC_PROFILE_ISS, ISSCABAC_BIN_EG0)
   SYM_WIDE_CASE(k_decode_symbols_wide, ISSCABAC_PROFILE_FLAT, ISSCABAC_BIN_EG0)
