@@ -59,11 +59,24 @@ def run(name, cfg, sym, sym_off, ctx, n_ctx):
 
 
 def main():
-    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c2", "c4", "c5"]
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["q", "c2", "c4", "c5"]
     scale = float(sys.argv[sys.argv.index("--scale") + 1]) if "--scale" in sys.argv else 1.0
     dev = torch.device("cuda")
     g = torch.Generator(device=dev)
     T = I.CM_COND0 | I.CM_COND1 | I.CM_CONDS0 | I.CM_CONDS1
+    if "q" in which:    # the quantiser in front of C2: 1,638 tracks x (W 400 x 20, H 109 x 20), N = 8, dead zone 0.7, Lloyd-Max
+        from isscabac_b200 import quantizer as QZ
+        g.manual_seed(5)
+        sizes = np.tile(np.array([400 * 20, 109 * 20], dtype=np.int64), int(1638 * scale))
+        off = np.zeros(len(sizes) + 1, dtype=np.int64)
+        np.cumsum(sizes, out=off[1:])
+        # log(theta + eps) of gamma(0.6)-distributed factors (theta = Gamma(1)^(1/0.6) is close enough for a timing input)
+        x = torch.log(torch.empty(int(off[-1]), dtype=torch.float64, device=dev).exponential_(1.0, generator=g) ** (1 / 0.6) + 1e-5)
+        cfg = QZ.make_quant_cfg(N=8, GMM=1, deadzoneQuant=0.7)
+        ms_q, (grp, cent, it) = timed(lambda: QZ.quantize_matrices((x, off), cfg, want_iters=True))
+        print(json.dumps({"config": "quantiser for C2 (quantizeWrapper: dead zone 0.7 + Lloyd-Max, N = 8)", "matrices": len(sizes),
+                          "elements": int(off[-1]), "ms": ms_q, "gelem_per_s": int(off[-1]) / (ms_q * 1e-3) / 1e9,
+                          "lloyd_iterations_mean": float(it.float().mean().item()), "p_symbol0": float((grp == 0).float().mean().item())}))
     if "c2" in which:   # 65,520 column streams of 400 symbols, ISS profile, Nq = 8, P(0) = 0.7
         g.manual_seed(1)
         n_streams, rows = int(65520 * scale), 400
