@@ -437,7 +437,14 @@ def run_b200(a):
 
 if __name__ == "__main__":
     args = parse()
+    # stdout carries exactly ONE line, the JSON result: whatever libraries print there (NCCL's version banner at communicator
+    # creation, for one) is sent to stderr; the result line is written to the real stdout at the end
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    _real_stdout.flush()
