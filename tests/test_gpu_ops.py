@@ -42,6 +42,14 @@ def script_to_ops(script, wide=False):
     return np.array(ops, dtype=np.uint16 if wide else np.uint8)
 
 
+@pytest.fixture(params=["fused", "split"])
+def enc_kernel(request, monkeypatch):
+    """The op encoder has two formulations (one warp per 32 streams / a context warp + a coder warp per 32 streams,
+    picked by the number of tiles per SM): run the test with each one forced."""
+    monkeypatch.setenv("ISSCABAC_ENC_SPLIT", "1" if request.param == "split" else "0")
+    return request.param
+
+
 def gpu_roundtrip(I, ops, off, ci, stride=None):
     enc = I.encode_ops(ops, np.asarray(off, dtype=np.int64), ci, slab_stride=stride)
     pay = I.compact(enc)
@@ -53,7 +61,7 @@ def gpu_roundtrip(I, ops, off, ci, stride=None):
 
 
 @pytest.mark.parametrize("wide", [False, True])
-def test_kats_batched(I, golden_dir, wide):
+def test_kats_batched(I, golden_dir, wide, enc_kernel):
     """All KATs (K0-K8 of SURVEY 4.1 + extras) as ONE ragged batch with per-stream context init."""
     with open(os.path.join(golden_dir, "kat.json")) as f:
         kat = json.load(f)
@@ -76,7 +84,7 @@ def test_kats_batched(I, golden_dir, wide):
 
 
 @pytest.mark.parametrize("fname", ["random_ops.npz", "random_ops16.npz"])
-def test_golden_random_ops(I, golden_dir, fname):
+def test_golden_random_ops(I, golden_dir, fname, enc_kernel):
     z = np.load(os.path.join(golden_dir, fname))
     ops, off = z["ops"], z["op_off"]
     for tag, ci in (("shared", z["ctx_shared"]), ("per", z["ctx_per"])):
@@ -110,7 +118,7 @@ def rand_ops(seed, n_streams, n_ops, n_ctx, p_ep, ragged=False):
     (5, 1000, 4096, 1, 1.0, False),     # bypass only
     (6, 129, 5000, 124, 0.1, True),     # many contexts (u8 op format limit region)
 ])
-def test_random_vs_oracle(I, seed, n_streams, n_ops, n_ctx, p_ep, ragged):
+def test_random_vs_oracle(I, seed, n_streams, n_ops, n_ctx, p_ep, ragged, enc_kernel):
     ops, off = rand_ops(seed, n_streams, n_ops, n_ctx, p_ep, ragged)
     ci = np.random.default_rng(seed).integers(0, 126, size=n_ctx).astype(np.uint8)
     stride = ((n_ops // 4 + 80) + 15) & ~15
@@ -140,7 +148,7 @@ def test_many_contexts_global_path(I):
     assert ok.all() and (b == (ops & 1)).all()
 
 
-def test_empty_and_tiny(I):
+def test_empty_and_tiny(I, enc_kernel):
     ci = np.array([1, 1], dtype=np.uint8)
     # zero streams
     enc = I.encode_ops(np.zeros(0, np.uint8), np.array([0], dtype=np.int64), ci, slab_stride=16)
@@ -194,7 +202,7 @@ def test_corrupt_stream_fails_finish_check(I):
     assert okc[0] == 0 and okc[1:].all()
 
 
-def test_full_length_streams_roundtrip(I):
+def test_full_length_streams_roundtrip(I, enc_kernel):
     """BASELINE size per stream (65,536 bins), fewer streams: size-independent properties --
     round trip, every finish() check, and byte parity of a sample against the oracle."""
     ops, off = rand_ops(10, 2048, 65536, 23, 0.25)
