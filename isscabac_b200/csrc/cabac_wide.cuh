@@ -91,6 +91,29 @@ constexpr int kLazy = CABAC_LAZY ? 42 : 32;
 // so the fourth decision of the group still sees f <= 35 + 18 = 53
 constexpr int kLazyDec = CABAC_LAZY_DEC == 2 ? 36 : (CABAC_LAZY_DEC ? 42 : 32);
 
+// renormalisation shift min(clz(rsel) - 23, 6) = 8 - bfind(rsel | 4) (Encoder.cpp:482-492 incl. the state-63 row).
+// CABAC_FMA_RENORM: the subtraction as a multiply-add, i.e. on the FMA pipe instead of the ALU pipe, which is the one
+// that binds the hot kernels (B200, C3: decode 546 -> 556 Gbins/s, encode 587 -> 590; the same trick for the bit
+// counters -- a 3-input add covers two bins -- and for range >> 6 as a high multiply measured slower).
+#ifndef CABAC_FMA_RENORM
+#define CABAC_FMA_RENORM 1
+#endif
+#if defined(__CUDACC__)
+// a multiplier ptxas cannot fold: with a literal -1 it turns x * -1 + 8 back into an ALU-pipe subtraction
+static __constant__ int c_cb_neg1 = -1;
+#endif
+CB_HD int cb_renorm(uint32_t rsel) {
+#if defined(__CUDA_ARCH__) && CABAC_FMA_RENORM
+  uint32_t fl;
+  int nn;
+  asm("bfind.u32 %0, %1;" : "=r"(fl) : "r"(rsel | 4u));
+  asm("mad.lo.s32 %0, %1, %2, 8;" : "=r"(nn) : "r"(fl), "r"(c_cb_neg1));
+  return nn;
+#else
+  return cb_clz(rsel | 4u) - 23;
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // encoder
 // ---------------------------------------------------------------------------
@@ -159,7 +182,7 @@ CB_HD uint32_t encw_bin(EncWide& E, uint32_t w, bool is_ep, const WRow& row) {
   const uint32_t is_lps = cb_xor_and<(1u << (8 * B))>(row.mps4, w);   // non-zero = LPS
   const uint32_t x2 = is_ep ? E.range : 2u * rmps;
   const uint32_t rsel = is_lps ? lps : rmps;
-  const int nn = cb_clz(rsel | 4u) - 23;     // min(clz(rsel)-23, 6): Encoder.cpp:482-492 incl. the state-63 row
+  const int nn = cb_renorm(rsel);
   const int ns = is_ep ? 1 : nn;
   uint64_t W = E.W;
   if (is_lps) W += x2;                       // predicated 64-bit add
@@ -290,7 +313,7 @@ CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, uint32_t& tok, const WRow& row) 
   const uint32_t scaled = x2 << 21;                        // reference: scaledRange << 15 (bypass: compare before the shift)
   const bool is_lps = D.hi >= scaled;
   const uint32_t rsel = is_lps ? lps : rmps;
-  const int nn = cb_clz(rsel | 4u) - 23;
+  const int nn = cb_renorm(rsel);
   const int ns = is_ep ? 1 : nn;
   const uint32_t h = D.hi - (is_lps ? scaled : 0u);
   D.hi = cb_funnel_l(D.lo, h, (uint32_t)ns);                // (h:lo) << ns, ns in 0..6

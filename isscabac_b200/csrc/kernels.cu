@@ -419,7 +419,7 @@ __device__ __forceinline__ void split_bin(EncWide& E, uint32_t lps4, uint32_t f)
   const bool is_lps = (f & (SF_LPS << (8 * B))) != 0, is_ep = (f & (SF_EP << (8 * B))) != 0;
   const uint32_t x2 = is_ep ? E.range : 2u * rmps;
   const uint32_t rsel = is_lps ? lps : rmps;
-  const int nn = cb_clz(rsel | 4u) - 23;
+  const int nn = cb_renorm(rsel);
   const int ns = is_ep ? 1 : nn;
   uint64_t W = E.W;
   if (is_lps) W += x2;
