@@ -174,7 +174,7 @@ CB_HD void encw_emit(EncWide& E) {
 }
 
 // One bin, context-coded or bypass (see the file header).  row = the row of the slot the op
-// addresses (the bypass row for a bypass op); the bin is bit 8*B of `w`.  Returns the new token.
+// addresses (the bypass row for a bypass op); the bin is bit 8*B of `w`.  Returns non-zero when the bin was the LPS.
 template <int B>
 CB_HD uint32_t encw_bin(EncWide& E, uint32_t w, bool is_ep, const WRow& row) {
   const uint32_t lps = cb_prmt(0, row.lps4, E.range >> 6);   // selector 4..7 = lps4 byte q (range is 256..510)
@@ -189,7 +189,7 @@ CB_HD uint32_t encw_bin(EncWide& E, uint32_t w, bool is_ep, const WRow& row) {
   E.W = W << ns;
   E.range = is_ep ? E.range : (rsel << nn);
   E.n += ns;
-  return is_lps ? row.next_lps : row.next_mps;
+  return is_lps;
 }
 
 // encodeBinsEP (Encoder.cpp:278-319; byte-identical to n single encodeBinEP calls) in
@@ -304,9 +304,9 @@ CB_HD void decw_start(DecWide& D, const uint8_t* in, uint32_t len) {
   decw_refill(D);   // bytes 3..6
 }
 
-// One bin, context-coded or bypass; returns the bin in bit 8*B (all other bits 0), tok = the new token.
+// One bin, context-coded or bypass; returns the bin in bit 8*B (all other bits 0), lps_out = the bin was the LPS.
 template <int B>
-CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, uint32_t& tok, const WRow& row) {
+CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, bool& lps_out, const WRow& row) {
   const uint32_t lps = cb_prmt(0, row.lps4, D.range >> 6);
   const uint32_t rmps = D.range - lps;
   const uint32_t x2 = is_ep ? D.range : 2u * rmps;
@@ -320,7 +320,7 @@ CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, uint32_t& tok, const WRow& row) 
   D.lo <<= ns;
   D.range = is_ep ? D.range : (rsel << nn);
   D.f += ns;
-  tok = is_lps ? row.next_lps : row.next_mps;
+  lps_out = is_lps;
   return (row.mps4 ^ (is_lps ? 0xffffffffu : 0u)) & (1u << (8 * B));   // bin = mps ^ isLPS
 }
 
@@ -393,7 +393,8 @@ template <int B, class Ctx, class Tab>
 CB_HD void encw_op(EncWide& E, uint32_t code, uint32_t w, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
   const bool is_ep = code > kOpTrmCode;
   const uint32_t c = code < n_ctx ? code : n_ctx;
-  ctx.store(c, encw_bin<B>(E, w, is_ep, tab.row(ctx.load(c))));
+  const WRow row = tab.row(ctx.load(c));
+  ctx.store_sel(c, encw_bin<B>(E, w, is_ep, row), row.next_lps, row.next_mps);
 }
 
 // 16 ops without a terminate op: 4 x (2 bins, guard, 2 bins, voted emit); see kLazy for the
@@ -426,9 +427,10 @@ template <int B, class Ctx, class Tab>
 CB_HD uint32_t decw_op(DecWide& D, uint32_t code, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
   const bool is_ep = code > kOpTrmCode;
   const uint32_t c = code < n_ctx ? code : n_ctx;
-  uint32_t tok = ctx.load(c);
-  const uint32_t bin = decw_bin<B>(D, is_ep, tok, tab.row(tok));
-  ctx.store(c, tok);
+  const WRow row = tab.row(ctx.load(c));
+  bool is_lps;
+  const uint32_t bin = decw_bin<B>(D, is_ep, is_lps, row);
+  ctx.store_sel(c, is_lps, row.next_lps, row.next_mps);
   return bin;
 }
 

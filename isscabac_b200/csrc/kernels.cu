@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(2 * SPLIT_MAX_PAIRS * 32) k_encode_ops_split(C
             const uint32_t c = code < n_ctx ? code : n_ctx;                                           \
             const WRow row = tab.row(ctx.load(c));                                                    \
             const uint32_t lb = cb_xor_and<(1u << (8 * K))>(row.mps4, w[g]);                          \
-            ctx.store(c, lb ? row.next_lps : row.next_mps);                                           \
+            ctx.store_sel(c, lb, row.next_lps, row.next_mps);                                         \
             fl |= lb;                                                                                 \
             l4[K] = row.lps4;                                                                         \
           }

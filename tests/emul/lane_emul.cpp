@@ -117,6 +117,7 @@ struct HostCtx {
   uint32_t* p;
   uint32_t load(uint32_t c) const { return p[c]; }
   void store(uint32_t c, uint32_t v) const { p[c] = v; }
+  void store_sel(uint32_t c, uint32_t sel, uint32_t a, uint32_t b) const { p[c] = sel ? a : b; }
 };
 struct HostTab {   // host tokens are the state bytes themselves
   uint32_t token(uint32_t st) const { return st; }
