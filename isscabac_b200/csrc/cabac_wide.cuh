@@ -114,6 +114,22 @@ CB_HD int cb_renorm(uint32_t rsel) {
 #endif
 }
 
+// x -= p ? y : 0.  CABAC_PRED_SUB: as a PREDICATED multiply-add (x = y * -1 + x, the multiplier in constant memory so
+// that ptxas keeps the IMAD form): the select leaves the ALU pipe (B200, C3: decode 556 -> 561 Gbins/s).  The encoder's
+// 64-bit "low += p ? y : 0" did not gain from the same treatment: 590 -> 541 as a predicated IMAD.WIDE, -> 566 as a
+// predicated add / add-with-carry pair.
+#ifndef CABAC_PRED_SUB
+#define CABAC_PRED_SUB 1
+#endif
+CB_HD uint32_t cb_sub_if(uint32_t x, bool p, uint32_t y) {
+#if defined(__CUDA_ARCH__) && CABAC_PRED_SUB
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mad.lo.u32 %0, %2, %3, %0;\n\t}" : "+r"(x) : "r"((uint32_t)p), "r"(y), "r"(c_cb_neg1));
+  return x;
+#else
+  return x - (p ? y : 0u);
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // encoder
 // ---------------------------------------------------------------------------
@@ -315,7 +331,7 @@ CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, bool& lps_out, const WRow& row) 
   const uint32_t rsel = is_lps ? lps : rmps;
   const int nn = cb_renorm(rsel);
   const int ns = is_ep ? 1 : nn;
-  const uint32_t h = D.hi - (is_lps ? scaled : 0u);
+  const uint32_t h = cb_sub_if(D.hi, is_lps, scaled);
   D.hi = cb_funnel_l(D.lo, h, (uint32_t)ns);                // (h:lo) << ns, ns in 0..6
   D.lo <<= ns;
   D.range = is_ep ? D.range : (rsel << nn);
