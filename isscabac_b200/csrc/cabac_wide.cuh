@@ -130,6 +130,32 @@ CB_HD uint32_t cb_sub_if(uint32_t x, bool p, uint32_t y) {
 #endif
 }
 
+// p ? a : b.  CABAC_SEL_FMA (bit mask, one bit per use site): as "r = b; @p r = a * 1 + 0" with the multiplier in constant
+// memory, i.e. the select on the FMA pipe instead of the ALU pipe.  Sites: 0 / 4 = the bypass override of the added term
+// (encoder / decoder), 1 / 5 = LPS or MPS sub-range, 2 / 6 = the bypass override of the shift, 3 = next token.  Measured on
+// B200 at C3 against none (590 / 561 Gbins/s): sites 0 + 4: 593 / 574 (kept); 2 + 6: 585 / 565; 1 + 5: 570 / 552 (the
+// sub-range select sits on the range chain); 3: 577 / 561; all: 573 / 563.  TP = the caller is a throughput-bound kernel
+// (the 16-op blocks of the op-array kernels): where a launch is bound by the latency of one chain -- the two-warp encoder at
+// low occupancy, the fused symbol kernels -- the extra pipe crossing costs more than the ALU slot saves (4.39 -> 4.62 ms, C5
+// decode 24.2 -> 25.8 ms), so those keep the plain select.
+#ifndef CABAC_SEL_FMA
+#define CABAC_SEL_FMA 0x11
+#endif
+#if defined(__CUDACC__)
+static __constant__ uint32_t c_cb_one = 1u;
+#endif
+template <int SITE, bool TP = true>
+CB_HD uint32_t cb_sel(uint32_t p, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  if (TP && ((CABAC_SEL_FMA >> SITE) & 1)) {
+    uint32_t r = b;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mad.lo.u32 %0, %2, %3, 0;\n\t}" : "+r"(r) : "r"(p), "r"(a), "r"(c_cb_one));
+    return r;
+  }
+#endif
+  return p ? a : b;
+}
+
 // ---------------------------------------------------------------------------
 // encoder
 // ---------------------------------------------------------------------------
@@ -191,15 +217,15 @@ CB_HD void encw_emit(EncWide& E) {
 
 // One bin, context-coded or bypass (see the file header).  row = the row of the slot the op
 // addresses (the bypass row for a bypass op); the bin is bit 8*B of `w`.  Returns non-zero when the bin was the LPS.
-template <int B>
+template <int B, bool TP = false>
 CB_HD uint32_t encw_bin(EncWide& E, uint32_t w, bool is_ep, const WRow& row) {
   const uint32_t lps = cb_prmt(0, row.lps4, E.range >> 6);   // selector 4..7 = lps4 byte q (range is 256..510)
   const uint32_t rmps = E.range - lps;
   const uint32_t is_lps = cb_xor_and<(1u << (8 * B))>(row.mps4, w);   // non-zero = LPS
-  const uint32_t x2 = is_ep ? E.range : 2u * rmps;
-  const uint32_t rsel = is_lps ? lps : rmps;
+  const uint32_t x2 = cb_sel<0, TP>(is_ep, E.range, 2u * rmps);
+  const uint32_t rsel = cb_sel<1, TP>(is_lps, lps, rmps);
   const int nn = cb_renorm(rsel);
-  const int ns = is_ep ? 1 : nn;
+  const int ns = (int)cb_sel<2, TP>(is_ep, 1u, (uint32_t)nn);
   uint64_t W = E.W;
   if (is_lps) W += x2;                       // predicated 64-bit add
   E.W = W << ns;
@@ -321,16 +347,16 @@ CB_HD void decw_start(DecWide& D, const uint8_t* in, uint32_t len) {
 }
 
 // One bin, context-coded or bypass; returns the bin in bit 8*B (all other bits 0), lps_out = the bin was the LPS.
-template <int B>
+template <int B, bool TP = false>
 CB_HD uint32_t decw_bin(DecWide& D, bool is_ep, bool& lps_out, const WRow& row) {
   const uint32_t lps = cb_prmt(0, row.lps4, D.range >> 6);
   const uint32_t rmps = D.range - lps;
-  const uint32_t x2 = is_ep ? D.range : 2u * rmps;
+  const uint32_t x2 = cb_sel<4, TP>(is_ep, D.range, 2u * rmps);
   const uint32_t scaled = x2 << 21;                        // reference: scaledRange << 15 (bypass: compare before the shift)
   const bool is_lps = D.hi >= scaled;
-  const uint32_t rsel = is_lps ? lps : rmps;
+  const uint32_t rsel = cb_sel<5, TP>(is_lps, lps, rmps);
   const int nn = cb_renorm(rsel);
-  const int ns = is_ep ? 1 : nn;
+  const int ns = (int)cb_sel<6, TP>(is_ep, 1u, (uint32_t)nn);
   const uint32_t h = cb_sub_if(D.hi, is_lps, scaled);
   D.hi = cb_funnel_l(D.lo, h, (uint32_t)ns);                // (h:lo) << ns, ns in 0..6
   D.lo <<= ns;
@@ -405,12 +431,12 @@ CB_HD bool block_has_trm(const uint32_t cw[4]) {
 // Context storage as the kernels see it: slot c of this lane holds a token, c == n_ctx is the
 // bypass slot.  Tab::token(st) = token of a state byte, Tab::row(tok) = its row.  `code` = op >> 1,
 // the bin is bit 8*B of `w`.
-template <int B, class Ctx, class Tab>
+template <int B, bool TP = false, class Ctx, class Tab>
 CB_HD void encw_op(EncWide& E, uint32_t code, uint32_t w, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
   const bool is_ep = code > kOpTrmCode;
   const uint32_t c = code < n_ctx ? code : n_ctx;
   const WRow row = tab.row(ctx.load(c));
-  ctx.store_sel(c, encw_bin<B>(E, w, is_ep, row), row.next_lps, row.next_mps);
+  ctx.store_sel(c, encw_bin<B, TP>(E, w, is_ep, row), row.next_lps, row.next_mps);
 }
 
 // 16 ops without a terminate op: 4 x (2 bins, guard, 2 bins, voted emit); see kLazy for the
@@ -421,11 +447,11 @@ CB_HD void encw_block16(EncWide& E, const uint32_t w[4], const uint32_t cw[4],
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const uint32_t codes = cw[g];   // the four op codes, one per byte
-    encw_op<0>(E, cb_prmt(codes, 0, 0x4440u), w[g], ctx, tab, n_ctx);
-    encw_op<1>(E, cb_prmt(codes, 0, 0x4441u), w[g], ctx, tab, n_ctx);
+    encw_op<0, true>(E, cb_prmt(codes, 0, 0x4440u), w[g], ctx, tab, n_ctx);
+    encw_op<1, true>(E, cb_prmt(codes, 0, 0x4441u), w[g], ctx, tab, n_ctx);
     if (E.n >= kLazy) encw_emit(E);
-    encw_op<2>(E, cb_prmt(codes, 0, 0x4442u), w[g], ctx, tab, n_ctx);
-    encw_op<3>(E, cb_prmt(codes, 0, 0x4443u), w[g], ctx, tab, n_ctx);
+    encw_op<2, true>(E, cb_prmt(codes, 0, 0x4442u), w[g], ctx, tab, n_ctx);
+    encw_op<3, true>(E, cb_prmt(codes, 0, 0x4443u), w[g], ctx, tab, n_ctx);
     if (cb_any<VOTE>(E.n >= kLazy)) encw_emit(E);
   }
 }
@@ -439,13 +465,13 @@ CB_HD void encw_general(EncWide& E, uint32_t o, const Ctx& ctx, const Tab& tab, 
   encw_emit(E);
 }
 
-template <int B, class Ctx, class Tab>
+template <int B, bool TP = false, class Ctx, class Tab>
 CB_HD uint32_t decw_op(DecWide& D, uint32_t code, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
   const bool is_ep = code > kOpTrmCode;
   const uint32_t c = code < n_ctx ? code : n_ctx;
   const WRow row = tab.row(ctx.load(c));
   bool is_lps;
-  const uint32_t bin = decw_bin<B>(D, is_ep, is_lps, row);
+  const uint32_t bin = decw_bin<B, TP>(D, is_ep, is_lps, row);
   ctx.store_sel(c, is_lps, row.next_lps, row.next_mps);
   return bin;
 }
@@ -458,11 +484,11 @@ CB_HD void decw_block16(DecWide& D, const uint32_t cw[4], uint32_t r[4],
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const uint32_t codes = cw[g];
-    uint32_t acc = decw_op<0>(D, cb_prmt(codes, 0, 0x4440u), ctx, tab, n_ctx);
-    acc |= decw_op<1>(D, cb_prmt(codes, 0, 0x4441u), ctx, tab, n_ctx);
+    uint32_t acc = decw_op<0, true>(D, cb_prmt(codes, 0, 0x4440u), ctx, tab, n_ctx);
+    acc |= decw_op<1, true>(D, cb_prmt(codes, 0, 0x4441u), ctx, tab, n_ctx);
     if (CABAC_LAZY_DEC == 1 && D.f >= kLazyDec) decw_refill(D);
-    acc |= decw_op<2>(D, cb_prmt(codes, 0, 0x4442u), ctx, tab, n_ctx);
-    acc |= decw_op<3>(D, cb_prmt(codes, 0, 0x4443u), ctx, tab, n_ctx);
+    acc |= decw_op<2, true>(D, cb_prmt(codes, 0, 0x4442u), ctx, tab, n_ctx);
+    acc |= decw_op<3, true>(D, cb_prmt(codes, 0, 0x4443u), ctx, tab, n_ctx);
     r[g] = acc;
     if (cb_any<(VOTE && CABAC_LAZY_DEC)>(D.f >= kLazyDec)) decw_refill(D);
   }
