@@ -766,8 +766,20 @@ __global__ void __launch_bounds__(256) k_compact_copy(const uint8_t* slab, uint6
   const uint32_t* sw = reinterpret_cast<const uint32_t*>(src);
   uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
   const uint32_t sh = 8 * head;  // source byte offset of destination word 0 is `head` (0..3)
-  for (uint32_t w = lane; w < nwords; w += 32) {
-    uint32_t lo = sw[w], hi = sh ? sw[w + 1] : 0u;  // sw[w+1] stays inside the slab row: head>0 => bytes remain
+  // four independent word pairs in flight per lane: the copy is bound by the loads a warp keeps outstanding
+  uint32_t w = lane;
+  for (; w + 96 < nwords; w += 128) {
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      lo[k] = sw[w + 32 * k];
+      hi[k] = sh ? sw[w + 32 * k + 1] : 0u;   // sw[.. + 1] stays inside the slab row: head > 0 => bytes remain
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dw[w + 32 * k] = sh ? __funnelshift_r(lo[k], hi[k], sh) : lo[k];
+  }
+  for (; w < nwords; w += 32) {
+    uint32_t lo = sw[w], hi = sh ? sw[w + 1] : 0u;
     dw[w] = sh ? __funnelshift_r(lo, hi, sh) : lo;
   }
   const uint32_t done = head + (nwords << 2);
