@@ -548,9 +548,17 @@ __global__ void k_order_scatter(const uint64_t* off, uint32_t n, const uint32_t*
   }
   __syncthreads();
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  const int b = 64 - __clzll((long long)(off[s + 1] - off[s]));
-  order[base[b] + atomicAdd(&cursor[b], 1u)] = s;
+  const bool live = s < n;
+  const int b = live ? 64 - __clzll((long long)(off[s + 1] - off[s])) : -1;
+  // one atomic per (warp, bucket) instead of one per stream: with equal-length streams every stream lands in the same
+  // bucket and a million atomics on one counter took 0.68 ms
+  const uint32_t peers = __match_any_sync(0xffffffffu, b);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t leader = __ffs(peers) - 1;
+  uint32_t first = 0;
+  if (live && lane == leader) first = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
+  first = __shfl_sync(0xffffffffu, first, leader);
+  if (live) order[base[b] + first + __popc(peers & ((1u << lane) - 1u))] = s;
 }
 
 struct LaneCtx {
