@@ -18,6 +18,12 @@
  *   cabacBinarizer.m / cabacDebinarizer.m /                          cabac_binarize_symbols,
  *     cabacDecodeSymbolFinished.m / cabacContextSelection.m /        cabac_encode_symbols,
  *     cabacEncode.m:45-70 / cabacDecode.m:29-55 / cabacDemo.m:101-186  cabac_decode_symbols
+ *   cabacInitContextModel.m:15-129, cabacEncode.m:30-31              cabac_iss_ctx_stats / _from_counters
+ *   cabacEncode.m:40-67 (ctxHist, ctxCost, H), ContextModel.cpp:97-134,  cabac_ctx_trace_ops, simplecabac_get_stats,
+ *     SimpleCABACMex.cpp:231-241,356-466 (trace statistics)              cabac_encode_symbols(.., d_bits_after_symbol)
+ *   one file per stream + .mat side info (SimpleCABACMex.cpp:195,288,    cabac_container_*
+ *     ISS.m:197-201)
+ *   quantizeWrapper.m:1-88, quantizeLloyd :91-176, quantize.m:59-84     cabac_quantize_matrices
  *
  * Conventions
  *   - every function returns 0 (ISSCABAC_OK) or a negative ISSCABAC_ERR_* code; no
