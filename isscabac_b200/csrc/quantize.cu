@@ -50,6 +50,32 @@ __device__ __forceinline__ uint32_t lower_bound(const double* a, uint32_t n, dou
   return lo;
 }
 
+// the same, starting from where the boundary was in the previous iteration (it moves by a few elements late in
+// Lloyd's iteration): exponential bracket around the hint, then bisection inside it
+__device__ __forceinline__ uint32_t lower_bound_from(const double* a, uint32_t n, double v, uint32_t hint) {
+  if (hint > n) hint = n;
+  uint32_t lo, hi;
+  if (hint < n && a[hint] < v) {          // answer is to the right of the hint
+    uint32_t step = 1;
+    lo = hint + 1;
+    hi = n;
+    while (lo + step <= n && a[lo + step - 1] < v) { lo += step; step <<= 1; }
+    if (lo + step < hi) hi = lo + step;
+    if (hi > n) hi = n;
+  } else {                                // a[hint] >= v (or hint == n): answer is at the hint or to its left
+    uint32_t step = 1;
+    hi = hint;
+    lo = 0;
+    while (hi >= step && !(a[hi - step] < v)) { hi -= step; step <<= 1; }
+    if (hi >= step) lo = hi - step + 1;   // a[hi - step] < v
+  }
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 // MATLAB quantile of a sorted vector (prctile: sample i is the (i - 0.5)/n quantile); quantizeWrapper.m:23, quantize.m:61
 __device__ __forceinline__ double sorted_quantile(const double* xs, uint32_t n, double p) {
   double r = p * (double)n;
@@ -119,17 +145,86 @@ __global__ void __launch_bounds__(QT) k_quantize(QParams P) {
     }
     uint32_t npad = 2;
     while (npad < n) npad <<= 1;
-    for (uint32_t i = tid; i < npad; i += QT) xs[i] = i < n ? xin[i] : INFINITY;
-    __syncthreads();
-    // ---- bitonic sort, ascending
-    for (uint32_t k = 2; k <= npad; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t t = tid; t < (npad >> 1); t += QT) {
-          const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-          const double a = xs[i], b = xs[l];
-          if ((a > b) == ((i & k) == 0)) { xs[i] = b; xs[l] = a; }
+    if (in_smem && npad >= 16) {
+      // ---- bitonic sort, ascending, register-blocked: a thread owns chunks of 16 consecutive elements, so the stages
+      // whose partner distance is below 16 (four per phase, and all of the first four phases) run in registers without a
+      // barrier, and only distances >= 16 -- conflict-free runs of consecutive doubles -- go through shared memory.
+      // One double of padding per 16 keeps the chunk loads of a warp off a single bank; the workspace overlays xs and
+      // the (not yet used) prefix array, the sorted values are moved to xs unpadded at the end.
+      double* wsp = xs;
+      auto PADX = [](uint32_t i) { return i + (i >> 4); };
+      for (uint32_t i = tid; i < npad; i += QT) wsp[PADX(i)] = i < n ? xin[i] : INFINITY;
+      __syncthreads();
+      auto cx = [](double& a, double& b, bool asc) {
+        if ((a > b) == asc) { const double t = a; a = b; b = t; }
+      };
+      const uint32_t nchunks = npad >> 4;
+      for (uint32_t c = tid; c < nchunks; c += QT) {        // phases k = 2, 4, 8, 16 entirely in registers
+        double v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = wsp[17u * c + e];
+#pragma unroll
+        for (int k = 2; k <= 16; k <<= 1)
+#pragma unroll
+          for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if ((e & j) == 0) cx(v[e], v[e | j], k < 16 ? (e & k) == 0 : (c & 1u) == 0);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) wsp[17u * c + e] = v[e];
+      }
+      __syncthreads();
+      for (uint32_t k = 32; k <= npad; k <<= 1) {
+        for (uint32_t j = k >> 1; j >= 16; j >>= 1) {
+          for (uint32_t t = tid; t < (npad >> 1); t += QT) {
+            const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+            const double a = wsp[PADX(i)], b = wsp[PADX(l)];
+            if ((a > b) == ((i & k) == 0)) { wsp[PADX(i)] = b; wsp[PADX(l)] = a; }
+          }
+          __syncthreads();
+        }
+        for (uint32_t c = tid; c < nchunks; c += QT) {      // distances 8, 4, 2, 1 of this phase
+          double v[16];
+          const bool asc = ((c << 4) & k) == 0;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = wsp[17u * c + e];
+#pragma unroll
+          for (int j = 8; j > 0; j >>= 1)
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if ((e & j) == 0) cx(v[e], v[e | j], asc);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) wsp[17u * c + e] = v[e];
         }
         __syncthreads();
+      }
+      // unpadded copy: through registers, the two layouts overlap
+      double r[QSMEM_ELEMS / QT];
+#pragma unroll
+      for (uint32_t m = 0; m < QSMEM_ELEMS / QT; ++m) {
+        const uint32_t i = tid + m * QT;
+        r[m] = i < npad ? wsp[PADX(i)] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (uint32_t m = 0; m < QSMEM_ELEMS / QT; ++m) {
+        const uint32_t i = tid + m * QT;
+        if (i < npad) xs[i] = r[m];
+      }
+      __syncthreads();
+    } else {
+      for (uint32_t i = tid; i < npad; i += QT) xs[i] = i < n ? xin[i] : INFINITY;
+      __syncthreads();
+      // ---- bitonic sort, ascending (matrices beyond the shared-memory budget, in global scratch; tiny ones)
+      for (uint32_t k = 2; k <= npad; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t t = tid; t < (npad >> 1); t += QT) {
+            const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+            const double a = xs[i], b = xs[l];
+            if ((a > b) == ((i & k) == 0)) { xs[i] = b; xs[l] = a; }
+          }
+          __syncthreads();
+        }
       }
     }
     // ---- prefix sums of the sorted values: a contiguous run per thread, block scan of the run sums
@@ -202,15 +297,23 @@ __global__ void __launch_bounds__(QT) k_quantize(QParams P) {
           if (g < Nr && hi > lo) cn = (pr[hi] - pr[lo]) / (double)(hi - lo);   // :146-151, mean of the group
           // edges from the updated centroids in group order (:156), groups from the sorted ones (:159-161)
           up = __shfl_down_sync(0xffffffffu, cn, 1);
-          cmin = warp_min(g < Nr ? cn : INFINITY);
-          cmax = warp_max(g < Nr ? cn : -INFINITY);
+          // the updated centroids are ordered in practice (means of ordered groups, midpoints of their edges): then the
+          // sort is the identity and min / max are the two ends
+          const bool ordered = __all_sync(0xffffffffu, g >= Nr - 1 || !(up < cn));
+          if (ordered) {
+            cmin = __shfl_sync(0xffffffffu, cn, 0);
+            cmax = __shfl_sync(0xffffffffu, cn, Nr - 1);
+          } else {
+            cmin = warp_min(g < Nr ? cn : INFINITY);
+            cmax = warp_max(g < Nr ? cn : -INFINITY);
+          }
           e_hi = g < Nr - 1 ? 0.5 * (cn + up) : fmax(mx, cmax);
           e_lo = __shfl_up_sync(0xffffffffu, e_hi, 1);
           if (g == 0) e_lo = fmin(mn, cmin);
-          c = warp_sort(cn, g, Nr);
+          c = ordered ? cn : warp_sort(cn, g, Nr);
           up = __shfl_down_sync(0xffffffffu, c, 1);
           mid = 0.5 * (c + up);
-          hi = g < Nr - 1 ? lower_bound(xr, nr, mid) : nr;
+          hi = g < Nr - 1 ? lower_bound_from(xr, nr, mid, hi) : nr;
           lo = __shfl_up_sync(0xffffffffu, hi, 1);
           if (g == 0) lo = 0;
           const double d = g < Nr ? (c - old) * (c - old) : 0.0;
