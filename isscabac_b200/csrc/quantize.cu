@@ -227,24 +227,38 @@ __global__ void __launch_bounds__(QT) k_quantize(QParams P) {
         }
       }
     }
-    // ---- prefix sums of the sorted values: a contiguous run per thread, block scan of the run sums
-    const uint32_t per = (n + QT - 1) / QT;
-    const uint32_t r0 = min((uint32_t)tid * per, n), r1 = min(r0 + per, n);
-    double run = 0.0;
-    for (uint32_t i = r0; i < r1; ++i) run += xs[i];
-    double inc = run;
+    // ---- prefix sums of the sorted values (ps[i] = sum of the i smallest).  Every warp takes a contiguous span and walks it
+    // in rows of 32 consecutive elements -- lane = element, so shared memory is read and written without bank conflicts (a
+    // contiguous run per THREAD put all 32 lanes of an access on one bank) -- with a shuffle scan per row and a running carry.
+    {
+      const uint32_t span = ((n + QT - 1) / QT) * 32u;        // elements per warp, a multiple of 32
+      const uint32_t w0 = min((uint32_t)wid * span, n), w1 = min(w0 + span, n);
+      double tot = 0.0;
+      for (uint32_t i = w0 + lane; i < w1; i += 32) tot += xs[i];
+      tot = warp_sum(tot);
+      if (lane == 0) s_part[wid] = tot;
+      __syncthreads();
+      double carry = 0.0;
+      for (int w = 0; w < wid; ++w) carry += s_part[w];
+      for (uint32_t row = w0; row < w1; row += 32) {
+        const uint32_t i = row + lane;
+        const double v = i < w1 ? xs[i] : 0.0;
+        double inc = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const double t = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += t;
+        for (int d = 1; d < 32; d <<= 1) {
+          const double t = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += t;
+        }
+        if (i < w1) ps[i] = carry + (inc - v);
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (tid == 0) {
+        double all = 0.0;
+        for (int w = 0; w < QT / 32; ++w) all += s_part[w];
+        ps[n] = all;
+      }
+      __syncthreads();
     }
-    if (lane == 31) s_part[wid] = inc;
-    __syncthreads();
-    double base = inc - run;
-    for (int w = 0; w < wid; ++w) base += s_part[w];
-    for (uint32_t i = r0; i < r1; ++i) { ps[i] = base; base += xs[i]; }
-    if (r1 == n && r0 < n) ps[n] = base;
-    __syncthreads();
 
     // ---- dead zone (quantizeWrapper.m:22-36): everything below the data's deadzone_quant quantile
     double thr = -INFINITY;
