@@ -84,6 +84,10 @@ def main():
         sym = torch.where(u < 0.7, torch.zeros_like(u), 1 + torch.floor(torch.log(torch.rand(u.shape, generator=g, device=dev)) / np.log(0.6))).clamp_(0, 7).to(torch.uint8)
         off = torch.arange(n_streams + 1, dtype=torch.int64, device=dev) * rows
         cfg = I.make_cfg(I.PROFILE_ISS, I.BIN_EG0, 8, 3, T, rows=rows)
+        # the context-init statistics in front of the encoder (cabacInitContextModel.m): counters per matrix (20 column streams)
+        ms_st, cnt = timed(lambda: I.iss_ctx_stats(cfg, sym, off, streams_per_group=20))
+        print(json.dumps({"config": "C2 context-init statistics (cabacInitContextModel: counters per matrix, 20 column streams each)",
+                          "groups": int(cnt.shape[0]), "counters_per_group": int(cnt.shape[1]), "ms": ms_st}))
         run("C2 ISS column streams", cfg, sym, off, torch.full((23,), 1, dtype=torch.uint8, device=dev), 23)
     if "c4" in which:   # 2^20 segments x 1024 symbols, Nq = 16, geometric, FLAT profile (8 contexts reset per segment)
         g.manual_seed(3)
