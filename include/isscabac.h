@@ -177,6 +177,12 @@ int cabac_iss_ctx_stats(const isscabac_symcfg* cfg, uint32_t n_streams, const ui
  * param.equalProb (cabacEncode.m:25-27).  Output pointers may be NULL. */
 int cabac_iss_ctx_from_counters(const isscabac_symcfg* cfg, const uint64_t* h_counters, uint32_t n_groups,
                                 int equal_prob, double* h_p0, uint8_t* h_ctx_quant, uint8_t* h_ctx_state);
+/* The same on the device, stream-ordered (no host round trip between the statistics and the encoder): d_counters as
+ * cabac_iss_ctx_stats leaves them, outputs are device arrays [n_groups][7*Nlbp+2].  Bit-identical to the host function:
+ * the divisions are IEEE double on both sides and the probability -> state step is a 256-entry table filled from
+ * cabac_ctx_from_prob(q / 255) (the side information has only 256 values). */
+int cabac_iss_ctx_from_counters_device(const isscabac_symcfg* cfg, const uint64_t* d_counters, uint32_t n_groups,
+                                       int equal_prob, double* d_p0, uint8_t* d_ctx_quant, uint8_t* d_ctx_state, void* stream);
 
 /* ---- quantiser in front of the coder (ISS/quantizeWrapper.m, ISS/quantize.m) -- */
 /* Replaces quantizeWrapper(x, qParam) (quantizeWrapper.m:1-88) for a batch of matrices: dead zone

@@ -52,8 +52,9 @@ def encode_matrices(Gs, Nq, param, per_column: bool = False, want_heat: bool = F
     mat_off = np.zeros(len(Gs) + 1, dtype=np.int64)
     np.cumsum([rows * c for c in cols], out=mat_off[1:])
     cnt = E.iss_ctx_stats(cfg, d_sym, torch.as_tensor(mat_off, device="cuda"), 1)
-    _, q, st = E.iss_ctx_from_counters(cfg, cnt, bool(param.get("equalProb", False)))
-    ctx_rows = st[group_of_stream]                          # per-stream context init
+    # counters -> uint8 side information -> state bytes on the device (no host round trip in front of the encoder)
+    _, d_q, d_st = E.iss_ctx_from_counters_device(cfg, cnt, bool(param.get("equalProb", False)))
+    ctx_rows = d_st[torch.as_tensor(group_of_stream, device="cuda")]   # per-stream context init
     bins_bound = int(counts.max()) * (67 if cfg.method != E.BIN_TU else max(int(Nq), 2))
     stride = E.slab_stride_bound(bins_bound)
     res = E.encode_symbols(cfg, d_sym, d_off, ctx_rows, slab_stride=stride, want_bits=want_heat)
@@ -61,6 +62,7 @@ def encode_matrices(Gs, Nq, param, per_column: bool = False, want_heat: bool = F
     pay = E.compact(enc)
     torch.cuda.synchronize()
     enc.check_overflow()
+    q, st = d_q.cpu().numpy(), d_st.cpu().numpy()
     out = dict(payload=pay.payload, byte_off=pay.byte_off, ctxInit0=q, ctx_state=st, sym_off=sym_off, cfg=cfg,
                group_of_stream=group_of_stream)
     if want_heat:

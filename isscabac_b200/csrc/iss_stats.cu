@@ -127,7 +127,62 @@ __global__ void __launch_bounds__(256) k_iss_ctx_stats(isscabac_symcfg c, const 
   add_counter(cr + RS_HIT, rs_hit, uniform);
 }
 
-double frac(unsigned long long hit, unsigned long long tot) { return tot ? (double)hit / (double)tot : 0.0; }
+__host__ __device__ inline double frac(unsigned long long hit, unsigned long long tot) { return tot ? (double)hit / (double)tot : 0.0; }
+
+// counters of one group -> p(0) of its 7*Nlbp+2 contexts (cabacInitContextModel.m:128); host and device run this same code:
+// two IEEE double divisions per context, so the results are identical
+__host__ __device__ inline void group_p0(const isscabac_symcfg& cfg, const unsigned long long* c, double* p) {
+  const int N = cfg.Nlbp;
+  const int nctx = 7 * N + 2;
+  for (int i = 0; i < nctx; ++i) p[i] = 0.0;
+  for (int n = 0; n < N; ++n) {
+    const unsigned long long* cn = c + PER_N * n;
+    p[n] = frac(cn[PRE_HIT], cn[PRE_TOT]);
+    // joint / marginal, the marginal replaced by 1 when it is empty or zero (:41-45 etc.)
+    auto cond = [&](unsigned long long hit, unsigned long long norm_hit, unsigned long long tot) {
+      const double nr = norm_hit > 0 ? frac(norm_hit, tot) : 1.0;
+      return frac(hit, tot) / nr;
+    };
+    if (cfg.types & ISSCABAC_CM_COND0) p[N + n] = cond(cn[C0_HIT], cn[C0N_HIT], cn[C_TOT]);
+    if (cfg.types & ISSCABAC_CM_COND1) p[2 * N + n] = cond(cn[C1_HIT], cn[C1N_HIT], cn[C_TOT]);
+    if (cfg.types & ISSCABAC_CM_CONDBINLFT) p[3 * N + n] = cond(cn[BL_HIT], cn[BLN_HIT], cn[BL_TOT]);
+    p[4 * N + n] = frac(cn[SUF_HIT], cn[SUF_TOT]);
+    if (cfg.types & ISSCABAC_CM_CONDS0) p[5 * N + n] = cond(cn[S0_HIT], cn[S0N_HIT], cn[CS_TOT]);
+    if (cfg.types & ISSCABAC_CM_CONDS1) p[6 * N + n] = cond(cn[S1_HIT], cn[S1N_HIT], cn[CS_TOT]);
+  }
+  const unsigned long long* cr = c + PER_N * N;
+  p[7 * N] = frac(cr[RP_HIT], cr[RP_TOT]);
+  p[7 * N + 1] = frac(cr[RS_HIT], cr[RS_TOT]);
+}
+
+// uint8(v * 255) as MATLAB does it: round half away from zero (v >= 0), saturate; one expression for host and device
+// (NaN from degenerate counters -> 0 on both)
+__host__ __device__ inline double quant255(double v) {
+  double q = floor(v * 255.0 + 0.5);
+  q = (255.0 < q) ? 255.0 : q;
+  return (0.0 < q) ? q : 0.0;
+}
+
+// state byte of every uint8 side-information value q (p0 = q / 255): filled once per process from the host function that is
+// pinned to the reference (cabac_ctx_from_prob), so the device never evaluates log10 itself
+__constant__ uint8_t c_state_of_q[256];
+
+__global__ void k_iss_ctx_finalise(isscabac_symcfg cfg, const unsigned long long* counters, uint32_t n_groups, int equal_prob,
+                                   double* p0, uint8_t* ctx_quant, uint8_t* ctx_state) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const int nctx = 7 * cfg.Nlbp + 2;
+  const int K = PER_N * cfg.Nlbp + N_REST;
+  double p[7 * MAX_NLBP + 2];
+  group_p0(cfg, counters + (size_t)g * K, p);
+  for (int i = 0; i < nctx; ++i) {
+    const double v = equal_prob ? 0.5 : p[i];
+    const double q = quant255(v);
+    if (p0) p0[(size_t)g * nctx + i] = v;
+    if (ctx_quant) ctx_quant[(size_t)g * nctx + i] = (uint8_t)q;
+    if (ctx_state) ctx_state[(size_t)g * nctx + i] = c_state_of_q[(int)q];
+  }
+}
 
 }  // namespace
 
@@ -172,30 +227,11 @@ int cabac_iss_ctx_from_counters(const isscabac_symcfg* cfg, const uint64_t* h_co
   for (uint32_t g = 0; g < n_groups; ++g) {
     const unsigned long long* c = reinterpret_cast<const unsigned long long*>(h_counters) + (size_t)g * K;
     double p[7 * MAX_NLBP + 2];
-    for (int i = 0; i < nctx; ++i) p[i] = 0.0;
-    for (int n = 0; n < N; ++n) {
-      const unsigned long long* cn = c + PER_N * n;
-      p[n] = frac(cn[PRE_HIT], cn[PRE_TOT]);
-      // joint / marginal, the marginal replaced by 1 when it is empty or zero (:41-45 etc.)
-      auto cond = [&](unsigned long long hit, unsigned long long norm_hit, unsigned long long tot) {
-        const double nr = norm_hit > 0 ? frac(norm_hit, tot) : 1.0;
-        return frac(hit, tot) / nr;
-      };
-      if (cfg->types & ISSCABAC_CM_COND0) p[N + n] = cond(cn[C0_HIT], cn[C0N_HIT], cn[C_TOT]);
-      if (cfg->types & ISSCABAC_CM_COND1) p[2 * N + n] = cond(cn[C1_HIT], cn[C1N_HIT], cn[C_TOT]);
-      if (cfg->types & ISSCABAC_CM_CONDBINLFT) p[3 * N + n] = cond(cn[BL_HIT], cn[BLN_HIT], cn[BL_TOT]);
-      p[4 * N + n] = frac(cn[SUF_HIT], cn[SUF_TOT]);
-      if (cfg->types & ISSCABAC_CM_CONDS0) p[5 * N + n] = cond(cn[S0_HIT], cn[S0N_HIT], cn[CS_TOT]);
-      if (cfg->types & ISSCABAC_CM_CONDS1) p[6 * N + n] = cond(cn[S1_HIT], cn[S1N_HIT], cn[CS_TOT]);
-    }
-    const unsigned long long* cr = c + PER_N * N;
-    p[7 * N] = frac(cr[RP_HIT], cr[RP_TOT]);
-    p[7 * N + 1] = frac(cr[RS_HIT], cr[RS_TOT]);
+    group_p0(*cfg, c, p);
     double pq[7 * MAX_NLBP + 2];
     for (int i = 0; i < nctx; ++i) {
       const double v = equal_prob ? 0.5 : p[i];
-      double q = floor(v * 255.0 + 0.5);            // uint8(): round half away from zero (v >= 0), saturate
-      q = std::max(0.0, std::min(q, 255.0));
+      const double q = quant255(v);
       if (h_p0) h_p0[(size_t)g * nctx + i] = v;
       if (h_ctx_quant) h_ctx_quant[(size_t)g * nctx + i] = (uint8_t)q;
       pq[i] = q / 255.0;
@@ -206,6 +242,33 @@ int cabac_iss_ctx_from_counters(const isscabac_symcfg* cfg, const uint64_t* h_co
     }
   }
   return ISSCABAC_OK;
+}
+
+// The same on the device (no host round trip between the statistics and the encoder): d_counters as cabac_iss_ctx_stats
+// leaves them; outputs are device arrays [n_groups][7*Nlbp+2], any of them may be NULL.
+int cabac_iss_ctx_from_counters_device(const isscabac_symcfg* cfg, const uint64_t* d_counters, uint32_t n_groups,
+                                       int equal_prob, double* d_p0, uint8_t* d_ctx_quant, uint8_t* d_ctx_state, void* stream) {
+  if (!cfg || (n_groups && !d_counters)) { set_error("cabac_iss_ctx_from_counters_device: null pointer"); return ISSCABAC_ERR_INVALID; }
+  if (cabac_iss_num_counters(cfg->Nlbp) < 0) { set_error("Nlbp must be 1..%d", MAX_NLBP); return ISSCABAC_ERR_INVALID; }
+  if (n_groups == 0) return ISSCABAC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool lut_ready[64] = {};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("device index out of range"); return ISSCABAC_ERR_UNSUPPORTED; }
+  if (!lut_ready[dev]) {
+    double pq[256];
+    uint8_t lut[256];
+    for (int q = 0; q < 256; ++q) pq[q] = q / 255.0;
+    int rc = cabac_ctx_from_prob(pq, 256, lut);
+    if (rc) return rc;
+    CK(cudaMemcpyToSymbol(c_state_of_q, lut, sizeof lut));
+    lut_ready[dev] = true;
+  }
+  k_iss_ctx_finalise<<<(n_groups + 127) / 128, 128, 0, st>>>(*cfg, reinterpret_cast<const unsigned long long*>(d_counters), n_groups,
+                                                             equal_prob, d_p0, d_ctx_quant, d_ctx_state);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_iss_ctx_finalise");
 }
 
 }  // extern "C"

@@ -387,6 +387,21 @@ def iss_ctx_from_counters(cfg: SymCfg, counters, equal_prob: bool = False):
     return p0, q, st
 
 
+def iss_ctx_from_counters_device(cfg: SymCfg, counters: torch.Tensor, equal_prob: bool = False, want_p0: bool = False):
+    """Device-side twin of iss_ctx_from_counters: -> (p0 or None, ctxInit0 uint8 [g, 7N+2], state bytes uint8 [g, 7N+2]) as
+    device tensors, stream-ordered, no host synchronisation."""
+    dev = _require_cuda()
+    cnt = _dev(counters, torch.int64, dev)
+    g = cnt.shape[0]
+    nctx = 7 * int(cfg.Nlbp) + 2
+    q = torch.empty((max(g, 1), nctx), dtype=torch.uint8, device=dev)
+    st = torch.empty((max(g, 1), nctx), dtype=torch.uint8, device=dev)
+    p0 = torch.empty((max(g, 1), nctx), dtype=torch.float64, device=dev) if want_p0 else None
+    check(lib().cabac_iss_ctx_from_counters_device(C.byref(cfg), vp(cnt), C.c_uint32(g), int(bool(equal_prob)), vp(p0), vp(q), vp(st),
+                                                   _stream_ptr()))
+    return (p0[:g] if want_p0 else None), q[:g], st[:g]
+
+
 # ------------------------------------------------------------------------------------
 # statistics outputs (ctxHist / ctxCost of cabacEncode.m:40-65, trace members of ContextModel.cpp:97-134)
 # ------------------------------------------------------------------------------------

@@ -51,6 +51,31 @@ def test_ctx_stats_match_oracle(types, method, Nq):
     # equalProb: every context starts at p = 0.5 -> uint8 128 -> (mps 0, state 0)
     _, qe, ste = I.iss_ctx_from_counters(cfg, cnt, equal_prob=True)
     assert (qe == 128).all() and (ste == 0).all()
+    # the device-side finalisation (no host round trip) gives the same doubles, side information and states
+    p0d, qd, std = I.iss_ctx_from_counters_device(cfg, cnt, want_p0=True)
+    assert np.array_equal(p0d.cpu().numpy(), p0) and np.array_equal(qd.cpu().numpy(), q) and np.array_equal(std.cpu().numpy(), st)
+    _, qde, stde = I.iss_ctx_from_counters_device(cfg, cnt, equal_prob=True)
+    assert (qde.cpu().numpy() == 128).all() and (stde.cpu().numpy() == 0).all()
+
+
+def test_ctx_finalise_device_equals_host_on_random_counters():
+    """counters -> p(0) -> uint8 side info -> state bytes on the device against the host function (which is pinned to the
+    reference's xMapProbabilityToState): random counter tables incl. empty and degenerate contexts."""
+    import isscabac_b200 as I
+    rng = np.random.default_rng(31)
+    for Nlbp, types in ((3, ALLT), (1, 0), (8, ALLT | O.CM_CONDBINLFT)):
+        cfg = I.make_cfg(I.PROFILE_ISS, I.BIN_EG0, 8, Nlbp, types, rows=0)
+        K = int(I.lib().cabac_iss_num_counters(Nlbp))
+        g = 500
+        tot = rng.integers(0, 5000, size=(g, K))
+        cnt = (tot * rng.random((g, K))).astype(np.int64)
+        cnt[rng.random((g, K)) < 0.1] = 0
+        # hits never exceed their totals in real data; keep a few arbitrary rows too (the formulas must still agree)
+        cnt[:400] = np.minimum(cnt[:400], tot[:400])
+        p0, q, st = I.iss_ctx_from_counters(cfg, cnt)
+        p0d, qd, std = I.iss_ctx_from_counters_device(cfg, torch.as_tensor(cnt, device="cuda"), want_p0=True)
+        assert np.array_equal(p0d.cpu().numpy(), p0, equal_nan=True)
+        assert np.array_equal(qd.cpu().numpy(), q) and np.array_equal(std.cpu().numpy(), st)
 
 
 def test_cabacEncode_cabacDecode_like_the_reference(tmp_path):
