@@ -5,8 +5,9 @@
 //
 // Every counter of the MATLAB code is a sum over symbols of a 0/1 term that depends only on
 // the symbol's own bin string and on the string of the symbol above it in the same column
-// (Gbin_up1, :16), so one thread per symbol evaluates the terms from the closed-form codes
-// (sym_code / sym_bin) and the warp adds them up with REDUX before touching global memory.
+// (Gbin_up1, :16), so a thread evaluates the terms of four consecutive symbols from the closed-form codes
+// (sym_code / sym_bin), keeps them as packed 8-bit counters in registers, and the warp adds them up with REDUX
+// before touching global memory.
 // Quirks kept on purpose: the first row's neighbour is a NaN cell of length 1 with np = 0
 // (:16,:21,:23), so it takes part in the conds0/conds1 denominators for n = 1; the conds
 // normalisers index the neighbour at the absolute position n, not n + np_up1 (:90,:102); the
@@ -39,92 +40,149 @@ __device__ __forceinline__ uint32_t load_sym(const void* p, int width, uint64_t 
   return static_cast<const uint32_t*>(p)[i];
 }
 
-__device__ __forceinline__ void add_counter(unsigned long long* dst, uint32_t v, bool uniform) {
-  if (uniform) {
-    const uint32_t s = __reduce_add_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst, (unsigned long long)s);
-  } else if (v) {
-    atomicAdd(dst, (unsigned long long)v);
-  }
-}
-
-__global__ void __launch_bounds__(256) k_iss_ctx_stats(isscabac_symcfg c, const void* sym, int width, uint64_t n_sym,
-                                                        const uint64_t* sym_off, uint32_t n_streams, uint32_t per_group,
-                                                        unsigned long long* counters) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n_sym;
-  const int N = c.Nlbp;
-  const uint32_t K = (uint32_t)(PER_N * N + N_REST);
-  uint32_t group = 0xffffffffu;
-  SymCode x = {0, 0, 0}, u = {0, 0, 0};
-  bool hasup = false;
-  if (live) {
-    uint32_t lo = 0, hi = n_streams;   // stream of symbol i: last s with sym_off[s] <= i
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (sym_off[mid] <= i) lo = mid; else hi = mid;
-    }
-    group = lo / per_group;
-    const uint64_t in_stream = i - sym_off[lo];
-    hasup = c.rows ? (in_stream % c.rows) != 0 : in_stream > 0;
-    x = sym_code(load_sym(sym, width, i), c.Nq, c.method);
-    if (hasup) u = sym_code(load_sym(sym, width, i - 1), c.Nq, c.method);
-  }
-  // whole warp in one group -> warp-aggregated adds (dead lanes contribute zeros)
-  const uint32_t g0 = __shfl_sync(0xffffffffu, group, 0);
-  const bool uniform = __all_sync(0xffffffffu, group == g0 || !live) && g0 != 0xffffffffu;
-  if (!uniform && !live) return;
-  unsigned long long* cnt = counters + (size_t)(uniform ? g0 : group) * K;
+// The 0/1 terms of one symbol (x = its code, u = the code of the symbol above it, hasup = there is one): add(k, v) adds v
+// to counter k of the symbol's group.  The loop over the modelled positions is unrolled with constant counter indices, so
+// that a caller may keep the counters in registers.
+template <class F>
+__device__ __forceinline__ void iss_terms(const SymCode& x, const SymCode& u, bool hasup, bool live, int N, F&& add) {
   // np = position of the first 0, or the length when there is none (:18-20)
   const uint32_t L = x.len, np = x.np <= x.len ? x.np : x.len;
   const uint32_t L_up = hasup ? u.len : 1u;                                  // :23
   const uint32_t np_up = hasup ? (u.np <= u.len ? u.np : u.len) : 0u;        // :21
   const uint32_t lv = live ? 1u : 0u;
-  for (int n = 1; n <= N; ++n) {
-    unsigned long long* cn = cnt + PER_N * (n - 1);
+#pragma unroll
+  for (int n = 1; n <= MAX_NLBP; ++n) {
+    if (n > N) break;
+    const int k0 = PER_N * (n - 1);
     const uint32_t un = (uint32_t)n;
     const bool in_pre = lv && un <= np;
     const uint32_t xn = in_pre ? sym_bin(x, un) : 1u;
-    add_counter(cn + PRE_TOT, in_pre, uniform);                               // :31-33
-    add_counter(cn + PRE_HIT, in_pre && xn == 0, uniform);
+    add(k0 + PRE_TOT, (uint32_t)in_pre);                                      // :31-33
+    add(k0 + PRE_HIT, (uint32_t)(in_pre && xn == 0));
     const bool csel = in_pre && un <= np_up;                                  // :38,:50
     const uint32_t yn = (lv && hasup && un <= L_up) ? sym_bin(u, un) : 2u;    // 2 = NaN / out of range
-    add_counter(cn + C_TOT, csel, uniform);
-    add_counter(cn + C0_HIT, csel && xn == 0 && yn == 0, uniform);
-    add_counter(cn + C0N_HIT, csel && yn == 0, uniform);
-    add_counter(cn + C1_HIT, csel && xn == 0 && yn == 1, uniform);
-    add_counter(cn + C1N_HIT, csel && yn == 1, uniform);
+    add(k0 + C_TOT, (uint32_t)csel);
+    add(k0 + C0_HIT, (uint32_t)(csel && xn == 0 && yn == 0));
+    add(k0 + C0N_HIT, (uint32_t)(csel && yn == 0));
+    add(k0 + C1_HIT, (uint32_t)(csel && xn == 0 && yn == 1));
+    add(k0 + C1N_HIT, (uint32_t)(csel && yn == 1));
     const bool bsel = lv && un + 1 <= np && np_up < un + 1;                   // :62-72
-    add_counter(cn + BL_TOT, bsel, uniform);
-    add_counter(cn + BL_HIT, bsel && sym_bin(x, un + 1) == 0 && xn == 1, uniform);
-    add_counter(cn + BLN_HIT, bsel && xn == 1, uniform);
+    add(k0 + BL_TOT, (uint32_t)bsel);
+    add(k0 + BL_HIT, (uint32_t)(bsel && sym_bin(x, un + 1) == 0 && xn == 1));
+    add(k0 + BLN_HIT, (uint32_t)(bsel && xn == 1));
     const bool ssel = lv && un + np <= L;                                     // :77-80
     const uint32_t xs = ssel ? sym_bin(x, un + np) : 1u;
-    add_counter(cn + SUF_TOT, ssel, uniform);
-    add_counter(cn + SUF_HIT, ssel && xs == 0, uniform);
+    add(k0 + SUF_TOT, (uint32_t)ssel);
+    add(k0 + SUF_HIT, (uint32_t)(ssel && xs == 0));
     const bool cssel = ssel && un + np_up <= L_up;                            // :84-106
     const uint32_t ys = (cssel && hasup) ? sym_bin(u, un + np_up) : 2u;
-    add_counter(cn + CS_TOT, cssel, uniform);
-    add_counter(cn + S0_HIT, cssel && xs == 0 && ys == 0, uniform);
-    add_counter(cn + S0N_HIT, cssel && yn == 0, uniform);
-    add_counter(cn + S1_HIT, cssel && xs == 0 && ys == 1, uniform);
-    add_counter(cn + S1N_HIT, cssel && yn == 1, uniform);
+    add(k0 + CS_TOT, (uint32_t)cssel);
+    add(k0 + S0_HIT, (uint32_t)(cssel && xs == 0 && ys == 0));
+    add(k0 + S0N_HIT, (uint32_t)(cssel && yn == 0));
+    add(k0 + S1_HIT, (uint32_t)(cssel && xs == 0 && ys == 1));
+    add(k0 + S1N_HIT, (uint32_t)(cssel && yn == 1));
   }
-  // rest contexts (:111-126): bins from absolute position Nlbp+1 on
-  unsigned long long* cr = cnt + PER_N * N;
+}
+// the two "rest" contexts (:111-126): bins from absolute position Nlbp+1 on -> {RP_HIT, RP_TOT, RS_HIT, RS_TOT}
+__device__ __forceinline__ void iss_rest(const SymCode& x, bool live, int N, uint32_t r[N_REST]) {
+  const uint32_t L = x.len, np = x.np <= x.len ? x.np : x.len;
   const uint32_t n0 = (uint32_t)N + 1u;
-  uint32_t rp_tot = 0, rp_hit = 0, rs_tot = 0, rs_hit = 0;
-  if (lv && n0 <= np) {
-    rp_tot = np - (uint32_t)N;
-    rp_hit = sym_bin(x, np) == 0 ? 1u : 0u;   // bins n0..np-1 are prefix ones
-  } else if (lv && n0 <= L) {
-    rs_tot = L - (uint32_t)N;
-    for (uint32_t b = n0; b <= L; ++b) rs_hit += sym_bin(x, b) == 0;
+  r[RP_HIT] = r[RP_TOT] = r[RS_HIT] = r[RS_TOT] = 0;
+  if (live && n0 <= np) {
+    r[RP_TOT] = np - (uint32_t)N;
+    r[RP_HIT] = sym_bin(x, np) == 0 ? 1u : 0u;   // bins n0..np-1 are prefix ones
+  } else if (live && n0 <= L) {
+    r[RS_TOT] = L - (uint32_t)N;
+    for (uint32_t b = n0; b <= L; ++b) r[RS_HIT] += sym_bin(x, b) == 0;
   }
-  add_counter(cr + RP_TOT, rp_tot, uniform);
-  add_counter(cr + RP_HIT, rp_hit, uniform);
-  add_counter(cr + RS_TOT, rs_tot, uniform);
-  add_counter(cr + RS_HIT, rs_hit, uniform);
+}
+
+// Four consecutive symbols per thread; the 0/1 counters are kept in registers as 8-bit fields (four counters per word: a
+// thread adds at most 4, a warp at most 128 per field), so a warp of 128 symbols needs one REDUX per word and one global
+// atomic per counter -- a thirteenth of the reductions and a quarter of the atomics of one symbol per thread.  A warp whose
+// symbols span two groups (one in 8,000 symbols for an ISS matrix) adds its non-zero terms one by one.
+constexpr int ISS_SPT = 4;
+__global__ void __launch_bounds__(256) k_iss_ctx_stats(isscabac_symcfg c, const void* sym, int width, uint64_t n_sym,
+                                                        const uint64_t* sym_off, uint32_t n_streams, uint32_t per_group,
+                                                        unsigned long long* counters) {
+  const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * ISS_SPT;
+  const int N = c.Nlbp;
+  const uint32_t K = (uint32_t)(PER_N * N + N_REST);
+  uint32_t s = 0;
+  uint64_t s_begin = 0, s_end = 0;
+  if (i0 < n_sym) {
+    uint32_t lo = 0, hi = n_streams;   // stream of symbol i0: last s with sym_off[s] <= i0
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (sym_off[mid] <= i0) lo = mid; else hi = mid;
+    }
+    s = lo;
+    s_begin = sym_off[s];
+    s_end = sym_off[s + 1];
+  }
+  // groups of this thread's first and last live symbol
+  uint32_t g_first = 0xffffffffu, g_last = 0xffffffffu;
+  if (i0 < n_sym) {
+    g_first = s / per_group;
+    uint64_t il = i0 + ISS_SPT - 1 < n_sym ? i0 + ISS_SPT - 1 : n_sym - 1;
+    uint32_t sl = s;
+    while (sl + 1 < n_streams && sym_off[sl + 1] <= il) ++sl;
+    g_last = sl / per_group;
+  }
+  const uint32_t g0 = __shfl_sync(0xffffffffu, g_first, 0);
+  const bool uniform = g0 != 0xffffffffu && __all_sync(0xffffffffu, i0 >= n_sym || (g_first == g0 && g_last == g0));
+  uint32_t acc[PER_N * MAX_NLBP / 4 + 1];
+#pragma unroll
+  for (int w = 0; w < PER_N * MAX_NLBP / 4 + 1; ++w) acc[w] = 0;
+  uint32_t rest[N_REST] = {0, 0, 0, 0};
+  uint32_t prev_v = 0;
+  if (i0 < n_sym && i0 > 0) prev_v = load_sym(sym, width, i0 - 1);
+#pragma unroll
+  for (int j = 0; j < ISS_SPT; ++j) {
+    const uint64_t i = i0 + j;
+    const bool live = i < n_sym;
+    uint32_t v = 0;
+    bool hasup = false;
+    if (live) {
+      while (i >= s_end && s + 1 < n_streams) { ++s; s_begin = s_end; s_end = sym_off[s + 1]; }
+      const uint64_t in_stream = i - s_begin;
+      hasup = c.rows ? (in_stream % c.rows) != 0 : in_stream > 0;
+      v = load_sym(sym, width, i);
+    }
+    const SymCode x = live ? sym_code(v, c.Nq, c.method) : SymCode{0, 0, 0};
+    const SymCode u = hasup ? sym_code(prev_v, c.Nq, c.method) : SymCode{0, 0, 0};
+    prev_v = v;
+    uint32_t r[N_REST];
+    iss_rest(x, live, N, r);
+    if (uniform) {
+      iss_terms(x, u, hasup, live, N, [&](int k, uint32_t t) { acc[k >> 2] += t << (8 * (k & 3)); });
+#pragma unroll
+      for (int q = 0; q < N_REST; ++q) rest[q] += r[q];
+    } else if (live) {
+      unsigned long long* cnt = counters + (size_t)(s / per_group) * K;
+      iss_terms(x, u, hasup, live, N, [&](int k, uint32_t t) { if (t) atomicAdd(cnt + k, (unsigned long long)t); });
+      for (int q = 0; q < N_REST; ++q) if (r[q]) atomicAdd(cnt + PER_N * N + q, (unsigned long long)r[q]);
+    }
+  }
+  if (!uniform) return;
+  unsigned long long* cnt = counters + (size_t)g0 * K;
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int w = 0; w < PER_N * MAX_NLBP / 4 + 1; ++w) {
+    if (4 * w >= PER_N * N) break;
+    // fields cannot carry into each other: <= 128 per field
+    const uint32_t sum = __reduce_add_sync(0xffffffffu, acc[w]);
+    if (lane < 4) {
+      const uint32_t f = (sum >> (8 * lane)) & 0xffu;
+      const int k = 4 * w + (int)lane;
+      if (f && k < PER_N * N) atomicAdd(cnt + k, (unsigned long long)f);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < N_REST; ++q) {
+    const uint32_t sum = __reduce_add_sync(0xffffffffu, rest[q]);
+    if (lane == 0 && sum) atomicAdd(cnt + PER_N * N + q, (unsigned long long)sum);
+  }
 }
 
 __host__ __device__ inline double frac(unsigned long long hit, unsigned long long tot) { return tot ? (double)hit / (double)tot : 0.0; }
@@ -206,7 +264,7 @@ int cabac_iss_ctx_stats(const isscabac_symcfg* cfg, uint32_t n_streams, const ui
   const size_t K = (size_t)cabac_iss_num_counters(cfg->Nlbp);
   CK(cudaMemsetAsync(d_counters, 0, groups * K * sizeof(uint64_t), st));
   if (n_symbols == 0 || n_streams == 0) return ISSCABAC_OK;
-  const uint32_t blocks = (uint32_t)((n_symbols + 255) / 256);
+  const uint32_t blocks = (uint32_t)((n_symbols + 256ull * ISS_SPT - 1) / (256ull * ISS_SPT));
   k_iss_ctx_stats<<<blocks, 256, 0, st>>>(*cfg, d_symbols, sym_width, n_symbols, d_sym_off, n_streams, streams_per_group,
                                           reinterpret_cast<unsigned long long*>(d_counters));
   cudaError_t e = cudaGetLastError();
