@@ -2,7 +2,7 @@
 """Randomised GPU-vs-oracle sweep (test infrastructure, like tests/): many small random jobs with random shapes --
 ragged and empty streams, terminate ops in the middle, misaligned op buffers, per-stream context inits, both encoder
 formulations, every symbol profile / binarization -- each compared bit for bit with the oracle.
-  python tools/fuzz_gpu.py [--iters N] [--seed S]      (on a GPU box; prints one JSON line)"""
+  python tests/gpu_tools/fuzz_gpu.py [--iters N] [--seed S]      (on a GPU box; prints one JSON line)"""
 import json
 import os
 import sys
@@ -11,7 +11,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import isscabac_b200 as I  # noqa: E402
 import oracle as O  # noqa: E402

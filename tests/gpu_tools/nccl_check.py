@@ -1,7 +1,7 @@
 """N-GPU check of the sharded path over NCCL (run under torchrun, one rank per GPU):
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-      --master-port 29511 tools/nccl_check.py
+      --master-port 29511 tests/gpu_tools/nccl_check.py
 
 Every rank encodes its contiguous range of streams on its own GPU (isscabac_b200.multi_gpu),
 the ranks all-gather the lengths, assemble ONE payload, and every rank decodes its own streams
@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import isscabac_b200 as I  # noqa: E402

@@ -1,4 +1,4 @@
-"""GPU: a short run of the randomised GPU-vs-oracle sweep (tools/fuzz_gpu.py: ragged / empty streams, terminate ops in the
+"""GPU: a short run of the randomised GPU-vs-oracle sweep (tests/gpu_tools/fuzz_gpu.py: ragged / empty streams, terminate ops in the
 middle, misaligned op buffers, per-stream context inits, both encoder formulations, every symbol profile and binarization)."""
 import os
 import sys
@@ -9,7 +9,7 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_tools"))
 
 
 @pytest.mark.parametrize("seed", [11, 12])
