@@ -136,6 +136,53 @@ int cabac_compact(uint32_t n_streams, const uint8_t* d_slab, uint64_t slab_strid
                   const uint32_t* d_lengths, uint8_t* d_payload, uint64_t payload_cap,
                   uint64_t* d_byte_off, void* d_scratch, uint32_t* d_overflow, void* stream);
 
+/* ---- multi-GPU: streams sharded over the GPUs of one box ------------------------------------------------ */
+/* One process per GPU; rank r codes the contiguous global stream range [h_first[r], h_first[r+1]) with the
+ * single-GPU entry points above -- the coding loop never communicates.  What the ranks exchange afterwards is
+ * what turns N local bitstreams into one: per-stream byte lengths (-> the global offset table on every rank) and,
+ * when one contiguous bitstream is wanted on every rank, the payload bytes.  NCCL over NVLink / NVSwitch; the
+ * library binds libnccl.so.2 at run time (the one already loaded in the process, e.g. PyTorch's, else the system
+ * one), so single-GPU users have no NCCL dependency.
+ * What it replaces in the reference: nothing is parallel there -- one matrix = one stream = one FILE
+ * (ISS/+coder/cabacEncode.m:34-37,97; CABAC/SimpleCABACMex.cpp:195 writes it, :288 reads it), the "hand-off" is the
+ * file system.  SURVEY.md 8(b).3 / 8(e) name these entry points.
+ * All calls are collective over the communicator's ranks and stream-ordered on `stream`. */
+typedef struct isscabac_mgpu isscabac_mgpu;
+#define ISSCABAC_MGPU_ID_BYTES 128
+/* rank 0: ncclGetUniqueId; ship the 128 bytes to the other ranks by any means (torch.distributed, MPI, a file) */
+int cabac_multi_gpu_unique_id(uint8_t* h_id);
+/* every rank, on its own current device: ncclCommInitRank */
+int cabac_multi_gpu_init(const uint8_t* h_id, int rank, int world, isscabac_mgpu** out);
+/* or wrap a communicator the application already has (ncclComm_t passed as void*; not destroyed by _destroy) */
+int cabac_multi_gpu_attach(void* nccl_comm, int rank, int world, isscabac_mgpu** out);
+int cabac_multi_gpu_destroy(isscabac_mgpu* mg);
+int cabac_multi_gpu_info(const isscabac_mgpu* mg, int* rank, int* world);
+/* Length exchange + global offset table, no host synchronisation: all-gather-v of the per-stream lengths (one grouped
+ * ncclBroadcast per rank; the counts are the host-known partition h_first[0..world]) into d_all_lengths[n_total],
+ * then the device-wide exclusive scan -> d_byte_off[n_total + 1] (u64), the same on every rank.
+ * d_scratch: cabac_compact_scratch_bytes(n_total) bytes. */
+int cabac_multi_gpu_gather_table(isscabac_mgpu* mg, const uint32_t* h_first, const uint32_t* d_local_lengths,
+                                 uint32_t* d_all_lengths, uint64_t* d_byte_off, void* d_scratch, void* stream);
+/* Payload exchange: rank r's compacted local payload lands at d_byte_off[h_first[r]] of d_payload on EVERY rank (one
+ * grouped ncclBroadcast per rank).  NCCL wants the byte counts on the host: the world + 1 boundary offsets are read
+ * back first (8 * (world + 1) bytes, one stream synchronisation -- the only one of the multi-GPU path); they are
+ * returned in h_rank_byte_first[0..world] when that is not NULL.  ISSCABAC_ERR_OVERFLOW if the total exceeds payload_cap. */
+int cabac_multi_gpu_assemble(isscabac_mgpu* mg, const uint32_t* h_first, const uint64_t* d_byte_off,
+                             const uint8_t* d_local_payload, uint8_t* d_payload, uint64_t payload_cap,
+                             uint64_t* h_rank_byte_first, void* stream);
+/* Compaction FUSED with the payload exchange over NVLink peer memory, no host synchronisation at all: every rank owns
+ * one buffer of a symmetric allocation (cudaMalloc + CUDA IPC, opened by every peer); the compaction kernel reads each
+ * local slab row once and stores it at its GLOBAL offset d_byte_off[h_first[rank] + s] into the buffer of EVERY rank
+ * (peer stores through NVSwitch), so the assembled bitstream exists on all ranks when the kernels and the closing
+ * barrier (cabac_multi_gpu_barrier) have run.  cap = the size given to _symmetric_alloc (bit 1 of *d_overflow on excess). */
+int cabac_multi_gpu_symmetric_alloc(isscabac_mgpu* mg, uint64_t bytes, uint8_t** d_local);
+int cabac_multi_gpu_symmetric_free(isscabac_mgpu* mg);
+int cabac_multi_gpu_compact_p2p(isscabac_mgpu* mg, const uint32_t* h_first, const uint8_t* d_slab, uint64_t slab_stride,
+                                const uint32_t* d_local_lengths, const uint64_t* d_byte_off, uint32_t* d_overflow,
+                                void* stream);
+/* all ranks' work enqueued on `stream` before this call is complete on every rank when work after it starts */
+int cabac_multi_gpu_barrier(isscabac_mgpu* mg, void* stream);
+
 /* ---- symbol level: binarizer + context selection on device ---------------- */
 /* symbols -> ops (u8 op format).  Two calls: with d_ops == NULL only d_op_off[0..n_streams]
  * (u64, exclusive scan of bins per stream) is produced; then call again with a d_ops buffer of

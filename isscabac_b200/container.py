@@ -71,9 +71,14 @@ def pack(payload, byte_off, ctx_init, unit_off=None, cfg: SymCfg | None = None, 
     boff = _host(byte_off, np.uint64)
     n = boff.size - 1
     total = int(boff[-1]) if n >= 0 else 0
-    pay = _host(payload, np.uint8).reshape(-1)[:total]
-    ctx = _host(ctx_init, np.uint8)
+    pay = _host(payload, np.uint8).reshape(-1)
+    if pay.size < total:
+        raise ValueError(f"payload holds {pay.size} bytes but byte_off[-1] = {total}")
+    pay = pay[:total]
     units = _host(unit_off, np.uint64)
+    if units is not None and units.size != boff.size:
+        raise ValueError("unit_off must have one entry per byte_off entry")
+    ctx = _host(ctx_init, np.uint8)
     v = ContainerView()
     v.n_streams = n
     v.n_ctx = int(ctx.shape[-1]) if ctx.ndim else 0

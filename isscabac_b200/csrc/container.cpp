@@ -164,7 +164,20 @@ int cabac_container_parse(const uint8_t* buf, uint64_t n, int verify_payload_crc
   v->cfg.profile = (int32_t)get32(buf + 32); v->cfg.method = (int32_t)get32(buf + 36); v->cfg.Nq = get32(buf + 40);
   v->cfg.Nlbp = (int32_t)get32(buf + 44); v->cfg.types = get32(buf + 48); v->cfg.rows = get32(buf + 52);
   v->payload_bytes = get64(buf + 56);
-  // the section offsets are recomputed from the counts and must agree with the stored ones
+  // The header checksum is no defence against a crafted header (anyone can recompute it), so every section is
+  // bounded against the buffer BEFORE anything is read or any pointer is derived: tables first (their size follows
+  // from the counts alone and cannot overflow 64 bits: n_streams < 2^32, n_ctx <= 999), then the payload against
+  // what is left.  Only then is the layout recomputed and compared with the stored section table.
+  if (v->n_ctx > ISSCABAC_MAX_CTX) { set_error("container: n_ctx %u > %u", v->n_ctx, ISSCABAC_MAX_CTX); return ISSCABAC_ERR_CORRUPT; }
+  {
+    const uint64_t tab = ((uint64_t)v->n_streams + 1) * 8;
+    const uint64_t ctx_bytes = (uint64_t)v->n_ctx * (v->per_stream_init ? v->n_streams : 1);
+    const uint64_t off_payload = align8(kHeaderBytes + tab * ((flags & F_HAS_UNITS) ? 2 : 1) + ctx_bytes);
+    if (off_payload > n || v->payload_bytes > n - off_payload || align8(v->payload_bytes) > n - off_payload) {
+      set_error("container truncated or section sizes exceed the buffer (%llu bytes)", (unsigned long long)n);
+      return ISSCABAC_ERR_CORRUPT;
+    }
+  }
   isscabac_container_view probe = *v;
   static const uint64_t dummy = 0;
   probe.unit_off = (flags & F_HAS_UNITS) ? &dummy : nullptr;
@@ -185,6 +198,7 @@ int cabac_container_parse(const uint8_t* buf, uint64_t n, int verify_payload_crc
   v->payload = buf + S.off_payload;
   const uint32_t ns = v->n_streams;
   if (v->byte_off[0] != 0 || v->byte_off[ns] != v->payload_bytes) { set_error("container offset table does not span the payload"); return ISSCABAC_ERR_CORRUPT; }
+  if (v->unit_off && v->unit_off[0] != 0) { set_error("container unit table does not start at 0"); return ISSCABAC_ERR_CORRUPT; }
   for (uint32_t s = 0; s < ns; ++s)
     if (v->byte_off[s + 1] < v->byte_off[s] || (v->unit_off && v->unit_off[s + 1] < v->unit_off[s])) {
       set_error("container offsets not monotone at stream %u", s);

@@ -130,7 +130,27 @@ struct Pipeline {
     return ISSCABAC_OK;
   }
 };
-thread_local Pipeline g_pipe;
+// one pipeline per (host thread, device): streams and events belong to the device that was current when they were made
+constexpr int kMaxDevs = 64;
+thread_local Pipeline g_pipes[kMaxDevs];
+Pipeline* current_pipe() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevs) {
+    set_error("no current CUDA device (or device index out of range)");
+    return nullptr;
+  }
+  return &g_pipes[dev];
+}
+// Declared AFTER the DevBufs of a host entry point, so it is destroyed BEFORE them: whatever path leaves the
+// function -- an error in the middle of the chunk loop included -- every lane is idle before a buffer is handed
+// back to the pool on lane 0 (no stream-ordered use-after-free on error paths).
+struct Drain {
+  Pipeline& p;
+  ~Drain() {
+    for (int l = 0; l < kLanes; ++l)
+      if (p.s[l]) cudaStreamSynchronize(p.s[l]);
+  }
+};
 
 struct DevBuf {
   void* p = nullptr;
@@ -169,6 +189,9 @@ int cabac_encode_ops_host(uint32_t n_streams, const uint64_t* h_op_off, const vo
   if (!h_op_off || !h_byte_off || (n_streams && !h_payload)) { set_error("cabac_encode_ops_host: null pointer"); return ISSCABAC_ERR_INVALID; }
   if (op_width != 1 && op_width != 2) { set_error("op_width must be 1 or 2"); return ISSCABAC_ERR_INVALID; }
   if (n_streams == 0) { h_byte_off[0] = 0; return ISSCABAC_OK; }
+  Pipeline* pipe = current_pipe();
+  if (!pipe) return ISSCABAC_ERR_CUDA;
+  Pipeline& g_pipe = *pipe;
   int rc = g_pipe.init();
   if (rc) return rc;
   cudaStream_t s0 = g_pipe.s[0];
@@ -180,6 +203,7 @@ int cabac_encode_ops_host(uint32_t n_streams, const uint64_t* h_op_off, const vo
   const size_t ctx_bytes = (size_t)n_ctx * (per_stream_init ? n_streams : 1);
 
   DevBuf d_ops, d_off, d_ctx, d_len, d_boff, d_scr, d_flag;
+  Drain drain{g_pipe};
   if ((rc = d_ops.alloc(total * op_width, s0)) || (rc = d_off.alloc((n_streams + 1ull) * 8, s0)) ||
       (rc = d_ctx.alloc(ctx_bytes, s0)) || (rc = d_len.alloc(n_streams * 4ull, s0)) ||
       (rc = d_boff.alloc((n_streams + 1ull) * 8, s0)) ||
@@ -201,6 +225,7 @@ int cabac_encode_ops_host(uint32_t n_streams, const uint64_t* h_op_off, const vo
 
   for (int attempt = 0; attempt < 2; ++attempt) {
     DevBuf d_slab, d_payload;
+    Drain drain_inner{g_pipe};
     if ((rc = d_slab.alloc((size_t)n_streams * stride, s0))) return rc;
     CK(cudaMemsetAsync(d_flag.p, 0, 16, s0));
     CK(cudaEventRecord(g_pipe.done[0], s0));
@@ -257,6 +282,9 @@ int cabac_decode_ops_host(uint32_t n_streams, const uint64_t* h_byte_off, const 
   if (!h_op_off || !h_byte_off) { set_error("cabac_decode_ops_host: null pointer"); return ISSCABAC_ERR_INVALID; }
   if (op_width != 1 && op_width != 2) { set_error("op_width must be 1 or 2"); return ISSCABAC_ERR_INVALID; }
   if (n_streams == 0) return ISSCABAC_OK;
+  Pipeline* pipe = current_pipe();
+  if (!pipe) return ISSCABAC_ERR_CUDA;
+  Pipeline& g_pipe = *pipe;
   int rc = g_pipe.init();
   if (rc) return rc;
   cudaStream_t s0 = g_pipe.s[0];
@@ -264,6 +292,7 @@ int cabac_decode_ops_host(uint32_t n_streams, const uint64_t* h_byte_off, const 
   const uint64_t bbase = h_byte_off[0], nbytes = h_byte_off[n_streams] - bbase;
   const size_t ctx_bytes = (size_t)n_ctx * (per_stream_init ? n_streams : 1);
   DevBuf d_ops, d_off, d_boff, d_bytes, d_ctx, d_bins, d_ok;
+  Drain drain{g_pipe};
   if ((rc = d_ops.alloc(total * op_width, s0)) || (rc = d_off.alloc((n_streams + 1ull) * 8, s0)) ||
       (rc = d_boff.alloc((n_streams + 1ull) * 8, s0)) || (rc = d_bytes.alloc(nbytes + 16, s0)) ||
       (rc = d_ctx.alloc(ctx_bytes, s0)) || (rc = d_bins.alloc(total, s0)) || (rc = d_ok.alloc(n_streams, s0)))
@@ -327,6 +356,9 @@ int cabac_encode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, co
   if (sym_width != 1 && sym_width != 2 && sym_width != 4) { set_error("sym_width must be 1, 2 or 4"); return ISSCABAC_ERR_INVALID; }
   if (n_streams == 0) { h_byte_off[0] = 0; return ISSCABAC_OK; }
   if (h_sym_off[0] != 0) { set_error("sym_off[0] must be 0"); return ISSCABAC_ERR_INVALID; }
+  Pipeline* pipe = current_pipe();
+  if (!pipe) return ISSCABAC_ERR_CUDA;
+  Pipeline& g_pipe = *pipe;
   int rc = g_pipe.init();
   if (rc) return rc;
   cudaStream_t s0 = g_pipe.s[0];
@@ -335,6 +367,7 @@ int cabac_encode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, co
   for (uint32_t s = 0; s < n_streams; ++s) max_sym = std::max(max_sym, h_sym_off[s + 1] - h_sym_off[s]);
   const size_t ctx_bytes = (size_t)n_ctx * (per_stream_init ? n_streams : 1);
   DevBuf d_sym, d_off, d_ctx, d_len, d_boff, d_scr, d_flag, d_bits;
+  Drain drain{g_pipe};
   if ((rc = d_sym.alloc(n_sym * sym_width, s0)) || (rc = d_off.alloc((n_streams + 1ull) * 8, s0)) ||
       (rc = d_ctx.alloc(ctx_bytes, s0)) || (rc = d_len.alloc(n_streams * 4ull, s0)) ||
       (rc = d_boff.alloc((n_streams + 1ull) * 8, s0)) ||
@@ -349,6 +382,7 @@ int cabac_encode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, co
                         : cfg->method == ISSCABAC_BIN_FL32 ? 32 : (uint64_t)(2 * 8 * sym_width + 3);
   uint64_t stride = cabac_slab_stride_bound(max_sym * bins_per_sym);
   DevBuf d_slab, d_payload;
+  Drain drain_inner{g_pipe};
   if ((rc = d_slab.alloc((size_t)n_streams * stride, s0))) return rc;
   CK(cudaMemsetAsync(d_flag.p, 0, 16, s0));
   rc = cabac_encode_symbols(cfg, n_streams, d_off.as<uint64_t>(), d_sym.p, sym_width, d_ctx.as<uint8_t>(), n_ctx,
@@ -385,12 +419,16 @@ int cabac_decode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, co
   if (sym_width != 1 && sym_width != 2 && sym_width != 4) { set_error("sym_width must be 1, 2 or 4"); return ISSCABAC_ERR_INVALID; }
   if (n_streams == 0) return ISSCABAC_OK;
   if (h_sym_off[0] != 0 || h_byte_off[0] != 0) { set_error("offset tables must start at 0"); return ISSCABAC_ERR_INVALID; }
+  Pipeline* pipe = current_pipe();
+  if (!pipe) return ISSCABAC_ERR_CUDA;
+  Pipeline& g_pipe = *pipe;
   int rc = g_pipe.init();
   if (rc) return rc;
   cudaStream_t s0 = g_pipe.s[0];
   const uint64_t n_sym = h_sym_off[n_streams], nbytes = h_byte_off[n_streams];
   const size_t ctx_bytes = (size_t)n_ctx * (per_stream_init ? n_streams : 1);
   DevBuf d_sym, d_off, d_boff, d_bytes, d_ctx, d_ok;
+  Drain drain{g_pipe};
   if ((rc = d_sym.alloc(n_sym * sym_width, s0)) || (rc = d_off.alloc((n_streams + 1ull) * 8, s0)) ||
       (rc = d_boff.alloc((n_streams + 1ull) * 8, s0)) || (rc = d_bytes.alloc(nbytes + 16, s0)) ||
       (rc = d_ctx.alloc(ctx_bytes, s0)) || (rc = d_ok.alloc(n_streams, s0)))

@@ -13,6 +13,7 @@
 // normalisers index the neighbour at the absolute position n, not n + np_up1 (:90,:102); the
 // "rest" suffix statistic starts at the absolute bin position Nlbp+1 (:121-126).
 #include <cuda_runtime.h>
+#include <mutex>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -311,9 +312,11 @@ int cabac_iss_ctx_from_counters_device(const isscabac_symcfg* cfg, const uint64_
   if (n_groups == 0) return ISSCABAC_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static bool lut_ready[64] = {};
+  static std::mutex lut_mutex;
   int dev = 0;
   CK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) { set_error("device index out of range"); return ISSCABAC_ERR_UNSUPPORTED; }
+  std::lock_guard<std::mutex> lut_lock(lut_mutex);
   if (!lut_ready[dev]) {
     double pq[256];
     uint8_t lut[256];

@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
 #include <type_traits>
 
 #include "../../include/isscabac.h"
@@ -26,8 +28,10 @@
 #include "cabac_wide.cuh"
 #include "wide_common.cuh"
 #include "internal.h"
+#include "codec_params.h"
 
 using namespace cabac;
+using isscabac_internal::CodecParams;
 
 namespace {
 
@@ -73,25 +77,6 @@ struct CtxGmem {
   uint64_t stride;
   __device__ __forceinline__ uint32_t load(uint32_t c) const { return p[c * stride]; }
   __device__ __forceinline__ void store(uint32_t c, uint32_t v) const { p[c * stride] = (uint8_t)v; }
-};
-
-struct CodecParams {
-  uint32_t n_streams, n_ctx;
-  int per_stream_init;
-  const uint64_t* op_off;
-  const void* ops;
-  const uint8_t* ctx_init;
-  uint8_t* ctx_scratch;  // CtxGmem only
-  // encode
-  uint8_t* slab;
-  uint64_t slab_stride;
-  uint32_t* lengths;
-  uint32_t* overflow;
-  // decode
-  const uint64_t* byte_off;
-  const uint8_t* bytes;
-  uint8_t* bins;
-  uint8_t* finish_ok;
 };
 
 template <class Ctx>
@@ -805,34 +790,42 @@ int cuda_fail(cudaError_t e, const char* what) {
   return ISSCABAC_ERR_CUDA;
 }
 
+// per-device attribute caches (a host thread may switch devices between calls)
+constexpr int kMaxDevs = 64;
+static int current_dev() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevs ? dev : -1;
+}
 int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
-      n = v;
-  }
-  return n > 0 ? n : 1;
+  static std::atomic<int> n[kMaxDevs] = {};
+  const int dev = current_dev();
+  if (dev < 0) return 1;
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (!v && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) n[dev].store(v, std::memory_order_relaxed);
+  return v > 0 ? v : 1;
 }
 
 // A zeroed u32 work counter for persistent kernels: slots of a small per-device ring that is
 // allocated once (no stream-ordered allocation on the launch path); the slot is cleared on the
 // caller's stream right before use.  512 launches may be in flight per device.
 int work_counter(cudaStream_t st, uint32_t** out) {
-  constexpr int kDevs = 64, kSlots = 512;
-  static uint32_t* ring[kDevs] = {};
-  static unsigned next[kDevs] = {};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-  if (dev < 0 || dev >= kDevs) { set_error("device index out of range"); return ISSCABAC_ERR_UNSUPPORTED; }
-  if (!ring[dev]) {
-    e = cudaMalloc(reinterpret_cast<void**>(&ring[dev]), kSlots * sizeof(uint32_t));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(work counters)");
+  constexpr int kSlots = 512;
+  static uint32_t* ring[kMaxDevs] = {};
+  static std::atomic<unsigned> next[kMaxDevs] = {};
+  static std::mutex ring_mutex;
+  const int dev = current_dev();
+  if (dev < 0) { set_error("no current CUDA device (or device index out of range)"); return ISSCABAC_ERR_CUDA; }
+  uint32_t* base;
+  {
+    std::lock_guard<std::mutex> lock(ring_mutex);
+    if (!ring[dev]) {
+      cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ring[dev]), kSlots * sizeof(uint32_t));
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(work counters)");
+    }
+    base = ring[dev];
   }
-  uint32_t* slot = ring[dev] + (next[dev]++ % kSlots);
-  e = cudaMemsetAsync(slot, 0, sizeof(uint32_t), st);
+  uint32_t* slot = base + (next[dev].fetch_add(1u, std::memory_order_relaxed) % kSlots);
+  cudaError_t e = cudaMemsetAsync(slot, 0, sizeof(uint32_t), st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(work counter)");
   *out = slot;
   return ISSCABAC_OK;
@@ -842,31 +835,34 @@ int work_counter(cudaStream_t st, uint32_t** out) {
 // default that pool hands its memory back to the driver at every synchronisation, which makes
 // each later cudaMallocAsync a slow driver call.  Keep freed blocks cached instead (once per device).
 int keep_pool_cached() {
-  static bool done[64] = {};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-  if (dev >= 0 && dev < 64 && !done[dev]) {
+  static std::atomic<bool> done[kMaxDevs] = {};
+  const int dev = current_dev();
+  if (dev < 0) return cuda_fail(cudaErrorInvalidDevice, "cudaGetDevice");
+  if (!done[dev].load(std::memory_order_acquire)) {
     cudaMemPool_t pool;
-    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, dev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetDefaultMemPool");
     uint64_t thr = ~0ull;
     e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemPoolSetAttribute");
-    done[dev] = true;
+    done[dev].store(true, std::memory_order_release);
   }
   return ISSCABAC_OK;
 }
 
 size_t smem_limit() {
-  static size_t lim = 0;
-  if (!lim) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess)
-      lim = (size_t)v;
+  static std::atomic<size_t> lim[kMaxDevs] = {};
+  const int dev = current_dev();
+  if (dev < 0) return 0;
+  size_t v = lim[dev].load(std::memory_order_relaxed);
+  if (!v) {
+    int a = 0;
+    if (cudaDeviceGetAttribute(&a, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess) {
+      v = (size_t)a;
+      lim[dev].store(v, std::memory_order_relaxed);
+    }
   }
-  return lim;
+  return v;
 }
 
 }  // namespace isscabac_internal
@@ -888,6 +884,11 @@ int launch_codec(K kernel, const CodecParams& P, size_t smem, cudaStream_t st, c
 }
 
 // picks the context-storage policy; allocates the global scratch when needed
+#ifndef LAT_TILES_PER_SM
+#define LAT_TILES_PER_SM 6
+#endif
+constexpr uint32_t kLatTilesPerSm = LAT_TILES_PER_SM;
+
 template <bool ENC>
 int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   if (op_width != 1 && op_width != 2) { set_error("op_width must be 1 or 2"); return ISSCABAC_ERR_INVALID; }
@@ -907,6 +908,16 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   const uint32_t split_tiles = (P.n_streams + 31) / 32;
   const bool split_on = split_env && (split_env[0] == '0' || split_env[0] == '1') ? split_env[0] == '1'
                                                                                   : split_tiles <= 11u * (uint32_t)sm_count();
+  // Few tiles per SM: the latency kernels (kernels_lat.cu, cabac_spec.cuh), whose per-bin dependent chain is a third of
+  // the wide kernels' at the price of more instructions per bin.  ISSCABAC_LAT=0 / 1 forces the choice.
+  const char* lat_env = getenv("ISSCABAC_LAT");
+  const bool lat_on = lat_env && (lat_env[0] == '0' || lat_env[0] == '1') ? lat_env[0] == '1'
+                                                                           : split_tiles <= kLatTilesPerSm * (uint32_t)sm_count();
+  if (lat_on && op_width == 1 && P.n_ctx <= 125) {
+    bool done = false;
+    const int rc_lat = launch_lat_codec(ENC, P, st, done);
+    if (rc_lat || done) return rc_lat;
+  }
   if (ENC && split_on && op_width == 1 && P.n_ctx <= 125) {
     const uint32_t sms = (uint32_t)sm_count();
     const uint32_t tiles = split_tiles;

@@ -268,3 +268,88 @@ int emul_decode_ops_wide_runs(uint32_t n_streams, const uint64_t* byte_off, cons
 void emul_carry_walk(uint32_t* row, uint32_t wp, uint32_t cap_words) { encw_carry_walk(wp, cap_words, row + wp); }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// latency formulation (cabac_spec.cuh): rows in the context slots, both successor rows loaded ahead,
+// LPS arm by table; driven with the schedule of k_encode_ops_lat / k_decode_ops_lat
+// ---------------------------------------------------------------------------
+#include "../../isscabac_b200/csrc/cabac_spec.cuh"
+
+namespace {
+struct HostSpecMem {
+  SRow* slots;   // n_ctx + 1
+  SRow ldrow(uint32_t tok) const { return spec_row(tok); }
+  SRow ldctx(uint32_t c) const { return slots[c]; }
+  void stctx(uint32_t c, const SRow& r) const { slots[c] = r; }
+};
+}  // namespace
+
+extern "C" {
+
+int emul_encode_ops_spec(uint32_t n_streams, const uint64_t* op_off, const uint8_t* ops,
+                         const uint8_t* ctx_init, uint32_t n_ctx, int per_stream,
+                         uint8_t* slab, uint64_t stride, uint32_t* lens) {
+  std::vector<SRow> cs(n_ctx + 1);
+  int ovf = 0;
+  for (uint32_t s = 0; s < n_streams; ++s) {
+    for (uint32_t c = 0; c < n_ctx; ++c) cs[c] = spec_row(ctx_init[(per_stream ? (uint64_t)s * n_ctx : 0) + c] & 127u);
+    cs[n_ctx] = spec_row(0);
+    HostSpecMem mem{cs.data()};
+    EncWide E;
+    encw_start(E, slab + s * stride, (uint32_t)stride);
+    const uint8_t* p = ops + op_off[s];
+    uint64_t n = op_off[s + 1] - op_off[s], i = 0;
+    uint64_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+    if (head > n) head = n;
+    for (; i < head; ++i) encs_general(E, p[i], mem, n_ctx);
+    for (; i + 16 <= n; i += 16) {
+      const uint32_t w[4] = {ld32(p + i), ld32(p + i + 4), ld32(p + i + 8), ld32(p + i + 12)};
+      const uint32_t cw[4] = {op_codes4(w[0]), op_codes4(w[1]), op_codes4(w[2]), op_codes4(w[3])};
+      if (block_has_trm(cw)) {
+        for (int k = 0; k < 16; ++k) encs_general(E, p[i + k], mem, n_ctx);
+      } else {
+        encs_block16<false>(E, w, cw, mem, n_ctx);
+      }
+    }
+    for (; i < n; ++i) encs_general(E, p[i], mem, n_ctx);
+    lens[s] = encw_finish(E);
+    ovf |= lens[s] > stride;
+  }
+  return ovf;
+}
+
+int emul_decode_ops_spec(uint32_t n_streams, const uint64_t* byte_off, const uint8_t* bytes,
+                         const uint64_t* op_off, const uint8_t* ops,
+                         const uint8_t* ctx_init, uint32_t n_ctx, int per_stream,
+                         uint8_t* bins, uint8_t* ok) {
+  std::vector<SRow> cs(n_ctx + 1);
+  for (uint32_t s = 0; s < n_streams; ++s) {
+    for (uint32_t c = 0; c < n_ctx; ++c) cs[c] = spec_row(ctx_init[(per_stream ? (uint64_t)s * n_ctx : 0) + c] & 127u);
+    cs[n_ctx] = spec_row(0);
+    HostSpecMem mem{cs.data()};
+    DecWide D;
+    decw_start(D, bytes + byte_off[s], (uint32_t)(byte_off[s + 1] - byte_off[s]));
+    const uint8_t* p = ops + op_off[s];
+    uint8_t* q = bins + op_off[s];
+    uint64_t n = op_off[s + 1] - op_off[s], i = 0;
+    uint64_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+    if (head > n) head = n;
+    for (; i < head; ++i) q[i] = (uint8_t)decs_general(D, p[i], mem, n_ctx);
+    for (; i + 16 <= n; i += 16) {
+      const uint32_t cw[4] = {op_codes4(ld32(p + i)), op_codes4(ld32(p + i + 4)), op_codes4(ld32(p + i + 8)),
+                              op_codes4(ld32(p + i + 12))};
+      if (block_has_trm(cw)) {
+        for (int k = 0; k < 16; ++k) q[i + k] = (uint8_t)decs_general(D, p[i + k], mem, n_ctx);
+      } else {
+        uint32_t r[4];
+        decs_block16<false>(D, cw, r, mem, n_ctx);
+        memcpy(q + i, r, 16);
+      }
+    }
+    for (; i < n; ++i) q[i] = (uint8_t)decs_general(D, p[i], mem, n_ctx);
+    ok[s] = (uint8_t)decw_finish(D);
+  }
+  return 0;
+}
+
+}  // extern "C"

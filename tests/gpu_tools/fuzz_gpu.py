@@ -43,8 +43,9 @@ def fuzz_ops(rng):
     buf = torch.zeros(n + 32, dtype=torch.uint8, device="cuda")
     buf[shift:shift + n] = torch.as_tensor(ops, device="cuda")
     d_ops = buf[shift:shift + n] if n else buf[:0]
-    for split in ("0", "1"):
-        os.environ["ISSCABAC_ENC_SPLIT"] = split
+    for split in ("0", "1", "lat"):
+        os.environ["ISSCABAC_ENC_SPLIT"] = "0" if split == "lat" else split
+        os.environ["ISSCABAC_LAT"] = "1" if split == "lat" else "0"
         enc = I.encode_ops(d_ops, off.astype(np.int64), ci, slab_stride=stride)
         pay = I.compact(enc)
         torch.cuda.synchronize()
@@ -55,8 +56,11 @@ def fuzz_ops(rng):
         assert (pay.payload.cpu().numpy()[:len(p_ref)] == p_ref).all(), ("payload", split)
     os.environ.pop("ISSCABAC_ENC_SPLIT")
     if decodable and n:
-        dbins, ok = I.decode_ops(pay, d_ops, off.astype(np.int64), ci)
-        assert bool(ok.all().item()) and (dbins.cpu().numpy() == bins).all(), "decode"
+        for lat in ("0", "1"):
+            os.environ["ISSCABAC_LAT"] = lat
+            dbins, ok = I.decode_ops(pay, d_ops, off.astype(np.int64), ci)
+            assert bool(ok.all().item()) and (dbins.cpu().numpy() == bins).all(), ("decode", lat)
+    os.environ.pop("ISSCABAC_LAT")
     return n
 
 

@@ -102,6 +102,48 @@ def test_corruption_is_detected():
         K.pack(payload, boff[::-1].copy(), ci)
 
 
+def test_crafted_header_cannot_reach_outside_the_buffer():
+    """A header whose sizes were chosen to wrap the 64-bit layout arithmetic, with its checksum recomputed (the header
+    CRC is no defence): parse must refuse before any CRC pass or pointer derivation, with and without the payload CRC."""
+    from isscabac_b200 import container as K
+    import isscabac_b200 as I
+    ops, off, ci = _job(seed=6, n_streams=9)
+    slab, lens = O.encode_ops(ops, off, ci, out_stride=256)
+    payload, boff = O.compact(slab, lens)
+    blob = K.pack(payload, boff, ci, unit_off=off)
+
+    def forge(payload_bytes=None, n_streams=None, total=None):
+        bad = blob.copy()
+        if payload_bytes is not None:
+            bad[56:64] = np.frombuffer(np.uint64(payload_bytes).tobytes(), np.uint8)
+        if n_streams is not None:
+            bad[16:20] = np.frombuffer(np.uint32(n_streams).tobytes(), np.uint8)
+        if total is not None:
+            bad[96:104] = np.frombuffer(np.uint64(total).tobytes(), np.uint8)
+        bad[112:116] = np.frombuffer(np.uint32(zlib.crc32(bad[:112].tobytes())).tobytes(), np.uint8)
+        return bad
+
+    off_payload = int(np.frombuffer(blob[88:96].tobytes(), np.uint64)[0])
+    for verify in (True, False):
+        # off_payload + payload_bytes wraps to a small total that would pass a "total <= n" test
+        wrap = (1 << 64) - off_payload + 64
+        for bad in (forge(payload_bytes=wrap, total=64), forge(payload_bytes=(1 << 64) - 8), forge(payload_bytes=blob.size),
+                    forge(n_streams=0xFFFFFFFF), forge(n_streams=1 << 28)):
+            with pytest.raises(I.CabacError):
+                K.unpack(bad, verify_payload_crc=verify)
+    # a unit table that does not start at 0 is refused as well (tables CRC recomputed)
+    bad = blob.copy()
+    uo = int(np.frombuffer(blob[72:80].tobytes(), np.uint64)[0])
+    bad[uo] = 1
+    bad[104:108] = np.frombuffer(np.uint32(zlib.crc32(bad[128:off_payload].tobytes())).tobytes(), np.uint8)
+    bad[112:116] = np.frombuffer(np.uint32(zlib.crc32(bad[:112].tobytes())).tobytes(), np.uint8)
+    with pytest.raises(I.CabacError):
+        K.unpack(bad)
+    # writer side: a payload shorter than the offset table claims
+    with pytest.raises(ValueError):
+        K.pack(payload[:-3], boff, ci)
+
+
 def test_empty_container():
     from isscabac_b200 import container as K
     blob = K.pack(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(3, np.uint8))

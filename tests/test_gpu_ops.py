@@ -42,10 +42,12 @@ def script_to_ops(script, wide=False):
     return np.array(ops, dtype=np.uint16 if wide else np.uint8)
 
 
-@pytest.fixture(params=["fused", "split"])
+@pytest.fixture(params=["fused", "split", "lat"])
 def enc_kernel(request, monkeypatch):
-    """The op encoder has two formulations (one warp per 32 streams / a context warp + a coder warp per 32 streams,
-    picked by the number of tiles per SM): run the test with each one forced."""
+    """The op kernels have three formulations, picked by the number of tiles per SM: the wide kernels (one warp per 32
+    streams), the two-warp encoder (a context warp + a coder warp per 32 streams) and the latency kernels (kernels_lat.cu:
+    rows in the context slots, successor rows loaded ahead; encoder and decoder).  Run the test with each one forced."""
+    monkeypatch.setenv("ISSCABAC_LAT", "1" if request.param == "lat" else "0")
     monkeypatch.setenv("ISSCABAC_ENC_SPLIT", "1" if request.param == "split" else "0")
     return request.param
 

@@ -21,7 +21,7 @@ u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uin
 def emul():
     src = os.path.join(HERE, "emul", "lane_emul.cpp")
     so = os.path.join(HERE, "emul", "liblane_emul.so")
-    hdrs = [os.path.join(HERE, "..", "isscabac_b200", "csrc", h) for h in ("cabac_lane.cuh", "cabac_wide.cuh")]
+    hdrs = [os.path.join(HERE, "..", "isscabac_b200", "csrc", h) for h in ("cabac_lane.cuh", "cabac_wide.cuh", "cabac_spec.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src], check=True)
     L = C.CDLL(so)

@@ -13,7 +13,19 @@ import oracle as O
 from test_lane_emulation import emul, p, script_to_ops, u8p, u32p, u64p  # noqa: F401
 
 
-def wide_encode(L, ops, off, ci, stride, misalign=0):
+# the formulation under test: "wide" (cabac_wide.cuh, throughput kernels) or "spec" (cabac_spec.cuh, latency kernels);
+# every test of the block schedule runs with both
+FORM = ["wide"]
+
+
+@pytest.fixture(params=["wide", "spec"], autouse=True)
+def _formulation(request):
+    FORM[0] = request.param
+    yield
+    FORM[0] = "wide"
+
+
+def wide_encode(L, ops, off, ci, stride, misalign=0, form=None):
     """misalign: byte offset of the op array inside a 64-byte aligned buffer (exercises head/tail)."""
     ops = np.ascontiguousarray(ops, dtype=np.uint8)
     buf = np.zeros(len(ops) + 128, dtype=np.uint8)
@@ -25,13 +37,14 @@ def wide_encode(L, ops, off, ci, stride, misalign=0):
     per = int(ci.ndim == 2)
     slab = np.zeros((n, stride), dtype=np.uint8)
     lens = np.zeros(n, dtype=np.uint32)
-    ovf = L.emul_encode_ops_wide(C.c_uint32(n), p(off, u64p), C.c_void_p(buf.ctypes.data + base), p(ci.reshape(-1), u8p),
+    fn = L.emul_encode_ops_spec if (form or FORM[0]) == "spec" else L.emul_encode_ops_wide
+    ovf = fn(C.c_uint32(n), p(off, u64p), C.c_void_p(buf.ctypes.data + base), p(ci.reshape(-1), u8p),
                                  C.c_uint32(ci.shape[-1]), per, p(slab, u8p), C.c_uint64(stride), p(lens, u32p))
     assert ovf == 0
     return slab, lens
 
 
-def wide_decode(L, payload, boff, ops, off, ci, misalign=0, pay_misalign=0):
+def wide_decode(L, payload, boff, ops, off, ci, misalign=0, pay_misalign=0, form=None):
     ops = np.ascontiguousarray(ops, dtype=np.uint8)
     buf = np.zeros(len(ops) + 128, dtype=np.uint8)
     base = (-buf.ctypes.data) % 64 + misalign
@@ -45,7 +58,8 @@ def wide_decode(L, payload, boff, ops, off, ci, misalign=0, pay_misalign=0):
     per = int(ci.ndim == 2)
     n = len(off) - 1
     ok = np.zeros(n, dtype=np.uint8)
-    L.emul_decode_ops_wide(C.c_uint32(n), p(np.ascontiguousarray(boff, dtype=np.uint64), u64p), C.c_void_p(pb.ctypes.data + pbase),
+    fn = L.emul_decode_ops_spec if (form or FORM[0]) == "spec" else L.emul_decode_ops_wide
+    fn(C.c_uint32(n), p(np.ascontiguousarray(boff, dtype=np.uint64), u64p), C.c_void_p(pb.ctypes.data + pbase),
                            p(np.ascontiguousarray(off, dtype=np.uint64), u64p), C.c_void_p(buf.ctypes.data + base),
                            p(ci.reshape(-1), u8p), C.c_uint32(ci.shape[-1]), per, C.c_void_p(out.ctypes.data + obase), p(ok, u8p))
     return out[obase:obase + len(ops)].copy(), ok
