@@ -885,7 +885,7 @@ int launch_codec(K kernel, const CodecParams& P, size_t smem, cudaStream_t st, c
 
 // picks the context-storage policy; allocates the global scratch when needed
 #ifndef LAT_TILES_PER_SM
-#define LAT_TILES_PER_SM 6
+#define LAT_TILES_PER_SM 4
 #endif
 constexpr uint32_t kLatTilesPerSm = LAT_TILES_PER_SM;
 
@@ -908,11 +908,15 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   const uint32_t split_tiles = (P.n_streams + 31) / 32;
   const bool split_on = split_env && (split_env[0] == '0' || split_env[0] == '1') ? split_env[0] == '1'
                                                                                   : split_tiles <= 11u * (uint32_t)sm_count();
-  // Few tiles per SM: the latency kernels (kernels_lat.cu, cabac_spec.cuh), whose per-bin dependent chain is a third of
-  // the wide kernels' at the price of more instructions per bin.  ISSCABAC_LAT=0 / 1 forces the choice.
+  // Few tiles per SM: the latency decoder (kernels_lat.cu, cabac_spec.cuh) -- context rows in the slots, successor rows
+  // loaded ahead, LPS arm by table: fewer exposed latencies per bin, more instructions.  Measured on B200 over 65,536-bin
+  // streams (profiles/r2_v1_ops_latency.jsonl): decode 4.42 / 5.42 / 5.32 ms against 4.97 / 5.92 / 5.67 ms of the wide
+  // kernel at 32 / 8,192 / 16,384 streams, 6.51 against 5.98 at 32,768 -- so up to kLatTilesPerSm tiles per SM.  The latency
+  // ENCODER (4.63 ms) loses to the two-warp encoder (4.24 ms) and is only used when forced.  ISSCABAC_LAT=0 / 1 forces
+  // the choice for both directions.
   const char* lat_env = getenv("ISSCABAC_LAT");
-  const bool lat_on = lat_env && (lat_env[0] == '0' || lat_env[0] == '1') ? lat_env[0] == '1'
-                                                                           : split_tiles <= kLatTilesPerSm * (uint32_t)sm_count();
+  const bool lat_forced = lat_env && (lat_env[0] == '0' || lat_env[0] == '1');
+  const bool lat_on = lat_forced ? lat_env[0] == '1' : (!ENC && split_tiles <= kLatTilesPerSm * (uint32_t)sm_count());
   if (lat_on && op_width == 1 && P.n_ctx <= 125) {
     bool done = false;
     const int rc_lat = launch_lat_codec(ENC, P, st, done);

@@ -49,11 +49,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ops, off, ci = make_job()
     n = len(off) - 1
-    for balanced in (False, True):
-        a, b = MG.balanced_ranges(off, world)[rank] if balanced else MG.shard_range(n, rank, world)
+    for balanced, fused in ((False, False), (True, False), (False, True), (True, True)):
+        parts = MG.balanced_ranges(off, world) if balanced else [MG.shard_range(n, r, world) for r in range(world)]
+        a, b = parts[rank]
+        first = np.array([p[0] for p in parts] + [n], dtype=np.uint32)     # the partition is known to every rank
         lo, hi = int(off[a]), int(off[b])
         loc_off = off[a:b + 1] - off[a]
-        pay, table, full = MG.encode_ops_sharded(ops[lo:hi], loc_off, ci, assemble=True, slab_stride=1024)
+        # through the C ABI (cabac_multi_gpu_*): NCCL all-gather-v of the lengths + device scan, then either grouped NCCL
+        # broadcasts of the payloads or the compaction kernel storing straight into every rank's buffer (fused)
+        pay, table, full = MG.encode_ops_sharded(ops[lo:hi], loc_off, ci, assemble=True, slab_stride=1024,
+                                                 first=first if balanced else None, fused_p2p=fused)
         bins, ok = MG.decode_ops_sharded(full, table, ops[lo:hi], loc_off, ci)
         torch.cuda.synchronize()
         good = bool(ok.all().item()) and bool((bins.cpu().numpy() == (ops[lo:hi] & 1)).all())
@@ -66,7 +71,7 @@ def main():
             payload, boff = O.compact(slab, lens)
             same = bool((full.cpu().numpy() == payload).all()) and bool(
                 (table.byte_off.cpu().numpy().astype(np.uint64) == boff).all())
-            print(json.dumps({"check": "nccl_sharded_container", "world": world, "balanced": balanced,
+            print(json.dumps({"check": "nccl_sharded_container", "world": world, "balanced": balanced, "assembly": "compaction fused with peer stores (cabac_multi_gpu_compact_p2p)" if fused else "grouped ncclBroadcast (cabac_multi_gpu_assemble)",
                               "streams": n, "payload_bytes": int(len(payload)), "stream_counts": table.stream_counts,
                               "round_trip_all_ranks": bool(flag.item()), "byte_identical_to_oracle": same}))
             assert same and bool(flag.item())

@@ -8,6 +8,9 @@ import os
 import subprocess
 import sys
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import hot_kernel_hash  # noqa: E402  (the stamp bench.py checks before it cites these numbers)
+
 rep, bins = sys.argv[1], int(sys.argv[2])
 out = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -23,6 +26,7 @@ for r in rows[2:]:
         i = hdr.index(k)
         tot += float(r[i]) * scale[units[i]]
     res[short] = {"dram_bytes_per_launch": tot, "bins_per_launch": bins,
-                  "source": f"ncu --set full --clock-control none, {os.path.basename(rep)}"}
+                  "source": f"ncu --set full --clock-control none, {os.path.basename(rep)}",
+                  "csrc_hash": hot_kernel_hash()}
 json.dump(res, open(out, "w"), indent=1)
 print(json.dumps(res, indent=1))
