@@ -38,6 +38,8 @@
  *   op = (code << 1) | bin
  *   u8  ops (op_width 1): code 0..124 = context index, 125 = terminate bin, 126 = bypass bin
  *   u16 ops (op_width 2): code 0..998 = context index, 0x7FFD terminate, 0x7FFE bypass
+ *   A code >= n_ctx of the call that is not the terminate code is coded as a BYPASS bin -- defined behaviour for
+ *   malformed op arrays, identical in every kernel formulation and in both directions.
  * Context state byte: (state << 1) | mps, state 0..63 (CABAC/ContextModel.h:78-80).
  */
 #ifndef ISSCABAC_H
@@ -71,7 +73,11 @@ extern "C" {
 
 /* binarization methods (CABAC/cabacBinarizer.m:12-27) */
 enum { ISSCABAC_BIN_TU = 0, ISSCABAC_BIN_EG0 = 1, ISSCABAC_BIN_EG1 = 2, ISSCABAC_BIN_EG2 = 3,
-       ISSCABAC_BIN_FL32 = 4 };
+       ISSCABAC_BIN_FL32 = 4,
+       /* truncated Rice (cabacBinarizer.m:39-54): binarize / encode only, as upstream -- the reference's decode loops have
+        * no case for it (cabacDecodeSymbolFinished.m:10-32), cabac_decode_symbols returns ISSCABAC_ERR_UNSUPPORTED.
+        * A symbol costs (v >> k) + 1 + k bins: keep values below 2^20. */
+       ISSCABAC_BIN_TR0 = 5, ISSCABAC_BIN_TR1 = 6, ISSCABAC_BIN_TR2 = 7 };
 /* context-selection profiles */
 enum { ISSCABAC_PROFILE_DEMO = 0,       /* CABAC/cabacDemo.m:113-121 (3 contexts)                 */
        ISSCABAC_PROFILE_ISS = 1,        /* ISS/+coder/cabacContextSelection.m:24-67 (7*Nlbp+2)    */

@@ -403,7 +403,7 @@ CB_HD uint32_t dec_finish(DecLane& D) {
 // ---------------------------------------------------------------------------
 // binarization (cabacBinarizer.m:30-75) in closed form
 // ---------------------------------------------------------------------------
-enum { BIN_TU = 0, BIN_EG0 = 1, BIN_EG1 = 2, BIN_EG2 = 3, BIN_FL32 = 4 };
+enum { BIN_TU = 0, BIN_EG0 = 1, BIN_EG1 = 2, BIN_EG2 = 3, BIN_FL32 = 4, BIN_TR0 = 5, BIN_TR1 = 6, BIN_TR2 = 7 };
 enum { PROFILE_DEMO = 0, PROFILE_ISS = 1, PROFILE_FLAT = 2, PROFILE_FLAT_EPSUF = 3 };
 enum { CM_COND0 = 1, CM_COND1 = 2, CM_CONDBINLFT = 4, CM_CONDS0 = 8, CM_CONDS1 = 16 };
 
@@ -426,6 +426,12 @@ CB_HD SymCode sym_code(uint32_t v, uint32_t Nq, int method) {
     c.len = 32;
     c.np = (uint32_t)cb_clz(~v) + 1u;  // 33 when v is all ones
     c.suf = v;
+  } else if (method >= BIN_TR0) {      // truncated Rice, cabacBinarizer.m:39-54: v >> k ones, a zero, k suffix bits
+    const uint32_t k = (uint32_t)(method - BIN_TR0);   // (encode only upstream: the decode loops have no case for it)
+    c.np = (v >> k) + 1u;
+    c.len = c.np + k;
+    // the escape for v >= maxVal is a TODO upstream (:47-50): the suffix bits stay ones there
+    c.suf = v >= Nq - 1u ? (1u << k) - 1u : v - ((c.np - 1u) << k);
   } else {                             // EG-k, cabacBinarizer.m:56-69
     uint32_t k = (uint32_t)(method - BIN_EG0);
     uint64_t t = ((uint64_t)v >> k) + 1u;

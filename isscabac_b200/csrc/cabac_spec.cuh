@@ -55,8 +55,8 @@ struct SpecOp {
   uint32_t ksh;    // scaledRange = rMPS << ksh: 22, bypass 21 (rMPS = range there)
   bool ep;
 };
-CB_HD SpecOp spec_op(uint32_t code) {
-  const bool ep = code > kOpTrmCode;
+CB_HD SpecOp spec_op(uint32_t code, uint32_t n_ctx) {
+  const bool ep = code >= n_ctx;        // bypass, incl. any code that is not a context of this call (see cabac_wide.cuh)
   return SpecOp{ep ? 16u : 6u, ep ? 21u : 22u, ep};
 }
 
@@ -121,13 +121,13 @@ CB_HD SRow spec_sel(bool p, const SRow& a, const SRow& b) {
 // (c_next = that slot; c_next == c: the successor just selected, otherwise the row loaded ahead -- loaded before this
 // op's store, which it can only miss when c_next == c).
 template <bool HAS_NEXT, class Mem>
-CB_HD uint32_t decs_step(DecWide& D, SRow& R, uint32_t code, uint32_t c, uint32_t c_next, const Mem& mem) {
+CB_HD uint32_t decs_step(DecWide& D, SRow& R, uint32_t code, uint32_t c, uint32_t c_next, const Mem& mem, uint32_t n_ctx) {
   SRow rowN = R;
   if (HAS_NEXT) rowN = mem.ldctx(c_next);
   const SRow rowM = mem.ldrow(R.tok_m), rowL = mem.ldrow(R.tok_l);
   bool p;
-  const uint32_t bin = decs_bin(D, spec_op(code), R, p);
-  const bool ctx_lps = code > kOpTrmCode ? false : p;          // a bypass bin leaves its (dummy) slot on the MPS path
+  const uint32_t bin = decs_bin(D, spec_op(code, n_ctx), R, p);
+  const bool ctx_lps = code >= n_ctx ? false : p;          // a bypass bin leaves its (dummy) slot on the MPS path
   const SRow nr = spec_sel(ctx_lps, rowL, rowM);
   mem.stctx(c, nr);
   if (HAS_NEXT) R = spec_sel(c_next == c, nr, rowN);
@@ -136,13 +136,13 @@ CB_HD uint32_t decs_step(DecWide& D, SRow& R, uint32_t code, uint32_t c, uint32_
 
 // One op of a block, encoder: the bin is known, so only the successor that will be taken is loaded.
 template <bool HAS_NEXT, class Mem>
-CB_HD void encs_step(EncWide& E, SRow& R, uint32_t code, uint32_t bin, uint32_t c, uint32_t c_next, const Mem& mem) {
+CB_HD void encs_step(EncWide& E, SRow& R, uint32_t code, uint32_t bin, uint32_t c, uint32_t c_next, const Mem& mem, uint32_t n_ctx) {
   SRow rowN = R;
   if (HAS_NEXT) rowN = mem.ldctx(c_next);
-  const bool ep = code > kOpTrmCode;
+  const bool ep = code >= n_ctx;
   const bool is_lps = (((R.nn4 >> 7) ^ bin) & 1u) != 0u;
   const SRow nr = mem.ldrow((is_lps && !ep) ? R.tok_l : R.tok_m);
-  encs_bin(E, spec_op(code), R, ep ? bin != 0u : is_lps);
+  encs_bin(E, spec_op(code, n_ctx), R, ep ? bin != 0u : is_lps);
   mem.stctx(c, nr);
   if (HAS_NEXT) R = spec_sel(c_next == c, nr, rowN);
 }
@@ -167,8 +167,8 @@ CB_HD void encs_block16(EncWide& E, const uint32_t w[4], const uint32_t cw[4], c
     for (int j = 0; j < 4; ++j) {
       const int k = 4 * g + j;
       const uint32_t bin = (w[g] >> (8 * j)) & 1u;
-      if (k < 15) encs_step<true>(E, R, code[k], bin, c[k], c[k < 15 ? k + 1 : 15], mem);
-      else encs_step<false>(E, R, code[k], bin, c[k], c[k], mem);
+      if (k < 15) encs_step<true>(E, R, code[k], bin, c[k], c[k < 15 ? k + 1 : 15], mem, n_ctx);
+      else encs_step<false>(E, R, code[k], bin, c[k], c[k], mem, n_ctx);
       if (j == 1 && E.n >= kLazy) encw_emit(E);
     }
     if (cb_any<VOTE>(E.n >= kLazy)) encw_emit(E);
@@ -191,8 +191,8 @@ CB_HD void decs_block16(DecWide& D, const uint32_t cw[4], uint32_t r[4], const M
     for (int j = 0; j < 4; ++j) {
       const int k = 4 * g + j;
       uint32_t bin;
-      if (k < 15) bin = decs_step<true>(D, R, code[k], c[k], c[k < 15 ? k + 1 : 15], mem);
-      else bin = decs_step<false>(D, R, code[k], c[k], c[k], mem);
+      if (k < 15) bin = decs_step<true>(D, R, code[k], c[k], c[k < 15 ? k + 1 : 15], mem, n_ctx);
+      else bin = decs_step<false>(D, R, code[k], c[k], c[k], mem, n_ctx);
       acc |= bin << (8 * j);
       if (CABAC_LAZY_DEC == 1 && j == 1 && D.f >= kLazyDec) decw_refill(D);
     }
@@ -210,7 +210,7 @@ CB_HD void encs_general(EncWide& E, uint32_t o, const Mem& mem, uint32_t n_ctx) 
   } else {
     const uint32_t c = spec_slot(code, n_ctx);
     SRow R = mem.ldctx(c);
-    encs_step<false>(E, R, code, o & 1u, c, c, mem);
+    encs_step<false>(E, R, code, o & 1u, c, c, mem, n_ctx);
   }
   encw_emit(E);
 }
@@ -223,7 +223,7 @@ CB_HD uint32_t decs_general(DecWide& D, uint32_t o, const Mem& mem, uint32_t n_c
   } else {
     const uint32_t c = spec_slot(code, n_ctx);
     SRow R = mem.ldctx(c);
-    bin = decs_step<false>(D, R, code, c, c, mem);
+    bin = decs_step<false>(D, R, code, c, c, mem, n_ctx);
   }
   decw_refill(D);
   return bin;

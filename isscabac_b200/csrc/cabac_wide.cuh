@@ -423,7 +423,8 @@ CB_HD uint32_t decw_finish(DecWide& D) {
 // ---------------------------------------------------------------------------
 // op blocks: the schedule both kernels and the host emulation follow
 // ---------------------------------------------------------------------------
-// u8 op format: op = code << 1 | bin, code 0..124 context, 125 terminate, 126 bypass.
+// u8 op format: op = code << 1 | bin, code 0..124 context, 125 terminate, 126 bypass.  A code >= n_ctx that is not the
+// terminate code is coded as a bypass bin (defined behaviour for malformed op arrays, the same in every kernel).
 constexpr uint32_t kOpTrmCode = 125u;
 
 // the four op codes of a word of ops, one per byte
@@ -446,7 +447,7 @@ CB_HD bool block_has_trm(const uint32_t cw[4]) {
 // the bin is bit 8*B of `w`.
 template <int B, bool TP = false, class Ctx, class Tab>
 CB_HD void encw_op(EncWide& E, uint32_t code, uint32_t w, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
-  const bool is_ep = code > kOpTrmCode;
+  const bool is_ep = code >= n_ctx;     // 126, and by definition any code that is not a context of this call (isscabac.h)
   const uint32_t c = code < n_ctx ? code : n_ctx;
   const WRow row = tab.row(ctx.load(c));
   ctx.store_sel(c, encw_bin<B, TP>(E, w, is_ep, row), row.next_lps, row.next_mps);
@@ -480,7 +481,7 @@ CB_HD void encw_general(EncWide& E, uint32_t o, const Ctx& ctx, const Tab& tab, 
 
 template <int B, bool TP = false, class Ctx, class Tab>
 CB_HD uint32_t decw_op(DecWide& D, uint32_t code, const Ctx& ctx, const Tab& tab, uint32_t n_ctx) {
-  const bool is_ep = code > kOpTrmCode;
+  const bool is_ep = code >= n_ctx;
   const uint32_t c = code < n_ctx ? code : n_ctx;
   const WRow row = tab.row(ctx.load(c));
   bool is_lps;

@@ -380,6 +380,11 @@ int cabac_encode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, co
   // bins per symbol: EG-k of a b-bit value has at most 2b+3 bins, TU at most Nq-1
   uint64_t bins_per_sym = cfg->method == ISSCABAC_BIN_TU ? (cfg->Nq > 1 ? cfg->Nq - 1 : 1)
                         : cfg->method == ISSCABAC_BIN_FL32 ? 32 : (uint64_t)(2 * 8 * sym_width + 3);
+  if (cfg->method >= ISSCABAC_BIN_TR0) {   // truncated Rice: (v >> k) + 1 + k bins, v < Nq (or whatever the symbol type holds)
+    const uint32_t k = (uint32_t)(cfg->method - ISSCABAC_BIN_TR0);
+    const uint64_t vmax = cfg->Nq ? cfg->Nq - 1 : (sym_width == 4 ? 0xfffffull : (1ull << (8 * sym_width)) - 1);
+    bins_per_sym = (vmax >> k) + 1 + k;
+  }
   uint64_t stride = cabac_slab_stride_bound(max_sym * bins_per_sym);
   DevBuf d_slab, d_payload;
   Drain drain_inner{g_pipe};

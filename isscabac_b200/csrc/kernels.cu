@@ -108,15 +108,15 @@ __device__ __forceinline__ CtxGmem make_ctx<CtxGmem>(const CodecParams& P, uint8
 // result is blended in with selects, and a single write-out test follows.  Only the
 // terminate bin -- at most a handful per stream -- is a real branch.
 template <int W, class Ctx>
-__device__ __forceinline__ void encode_one(EncLane& L, uint32_t o, const Ctx& ctx, const uint2* mytab, uint32_t ctx_max) {
+__device__ __forceinline__ void encode_one(EncLane& L, uint32_t o, const Ctx& ctx, const uint2* mytab, uint32_t ctx_max, uint32_t n_ctx) {
   typedef OpTraits<W> OT;
   const uint32_t code = o >> 1, bin = o & 1u;
   if (code == OT::TRM) {
     enc_bin_trm<false>(L, bin);
     return;
   }
-  const bool is_ep = code > OT::TRM;
-  const uint32_t c = min(code, ctx_max);  // a context >= n_ctx aliases onto the last one (never out of bounds)
+  const bool is_ep = code >= n_ctx;       // the bypass code, and by definition any code that is not a context of this call
+  const uint32_t c = min(code, ctx_max);  // clamped: the context path is computed unconditionally (never out of bounds)
   uint32_t st = ctx.load(c);
   const uint2 row = mytab[st * 32];
   // encodeBin (Encoder.cpp:113-178), see enc_bin_ctx in cabac_lane.cuh
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NT) k_encode_ops(CodecParams P) {
   uint64_t i = 0;
   // head: up to the first 16-byte boundary
   while (i < n && (reinterpret_cast<uintptr_t>(p + i) & 15u)) {
-    encode_one<W, Ctx>(L, p[i], ctx, mytab, ctx_max);
+    encode_one<W, Ctx>(L, p[i], ctx, mytab, ctx_max, P.n_ctx);
     ++i;
   }
   // body: 16 bytes of ops per load, next block prefetched while this one is coded
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(NT) k_encode_ops(CodecParams P) {
 #pragma unroll
         for (int b = 0; b < 4 / W; ++b) {
           uint32_t o = (W == 1) ? ((w[k] >> (8 * b)) & 0xffu) : ((w[k] >> (16 * b)) & 0xffffu);
-          encode_one<W, Ctx>(L, o, ctx, mytab, ctx_max);
+          encode_one<W, Ctx>(L, o, ctx, mytab, ctx_max, P.n_ctx);
         }
       }
       i += PER;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(NT) k_encode_ops(CodecParams P) {
     }
   }
   // tail
-  for (; i < n; ++i) encode_one<W, Ctx>(L, p[i], ctx, mytab, ctx_max);
+  for (; i < n; ++i) encode_one<W, Ctx>(L, p[i], ctx, mytab, ctx_max, P.n_ctx);
 
   enc_finish<false>(L);
   enc_flush_pending(L);
@@ -201,11 +201,11 @@ __global__ void __launch_bounds__(NT) k_encode_ops(CodecParams P) {
 // decode
 // ---------------------------------------------------------------------------
 template <int W, class Ctx>
-__device__ __forceinline__ uint32_t decode_one(DecLane& D, uint32_t o, const Ctx& ctx, const uint2* mytab, uint32_t ctx_max) {
+__device__ __forceinline__ uint32_t decode_one(DecLane& D, uint32_t o, const Ctx& ctx, const uint2* mytab, uint32_t ctx_max, uint32_t n_ctx) {
   typedef OpTraits<W> OT;
   const uint32_t code = o >> 1;
   if (code == OT::TRM) return dec_bin_trm(D);
-  const bool is_ep = code > OT::TRM;
+  const bool is_ep = code >= n_ctx;
   const uint32_t c = min(code, ctx_max);
   uint32_t st = ctx.load(c);
   const uint2 row = mytab[st * 32];
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NT) k_decode_ops(CodecParams P) {
 
   uint64_t i = 0;
   while (i < n && (reinterpret_cast<uintptr_t>(p + i) & 15u)) {
-    q[i] = (uint8_t)decode_one<W, Ctx>(D, p[i], ctx, mytab, ctx_max);
+    q[i] = (uint8_t)decode_one<W, Ctx>(D, p[i], ctx, mytab, ctx_max, P.n_ctx);
     ++i;
   }
   constexpr int PER = 16 / W;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(NT) k_decode_ops(CodecParams P) {
 #pragma unroll
         for (int b = 0; b < 4 / W; ++b) {
           uint32_t o = (W == 1) ? ((w[k] >> (8 * b)) & 0xffu) : ((w[k] >> (16 * b)) & 0xffffu);
-          uint32_t bin = decode_one<W, Ctx>(D, o, ctx, mytab, ctx_max);
+          uint32_t bin = decode_one<W, Ctx>(D, o, ctx, mytab, ctx_max, P.n_ctx);
           if (W == 1) r[k] |= bin << (8 * b);
           else q[i + k * 2 + b] = (uint8_t)bin;
         }
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NT) k_decode_ops(CodecParams P) {
       cur = nxt;
     }
   }
-  for (; i < n; ++i) q[i] = (uint8_t)decode_one<W, Ctx>(D, p[i], ctx, mytab, ctx_max);
+  for (; i < n; ++i) q[i] = (uint8_t)decode_one<W, Ctx>(D, p[i], ctx, mytab, ctx_max, P.n_ctx);
 
   if (P.finish_ok) P.finish_ok[s] = (uint8_t)dec_finish(D);
 }
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(2 * SPLIT_MAX_PAIRS * 32) k_encode_ops_split(C
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint32_t codes = cw[g];
-          uint32_t fl = ((codes + 0x02020202u) >> 6) & 0x02020202u;      // code >= 126 -> SF_EP in the op's byte
+          uint32_t fl = 0;
           uint32_t l4[4];
 #define SPLIT_OP(K)                                                                                   \
           {                                                                                           \
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(2 * SPLIT_MAX_PAIRS * 32) k_encode_ops_split(C
             const WRow row = tab.row(ctx.load(c));                                                    \
             const uint32_t lb = cb_xor_and<(1u << (8 * K))>(row.mps4, w[g]);                          \
             ctx.store_sel(c, lb, row.next_lps, row.next_mps);                                         \
-            fl |= lb;                                                                                 \
+            fl |= lb | (code >= n_ctx ? (SF_EP << (8 * K)) : 0u);   /* bypass: 126 or any non-context code */ \
             l4[K] = row.lps4;                                                                         \
           }
           SPLIT_OP(0) SPLIT_OP(1) SPLIT_OP(2) SPLIT_OP(3)
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(2 * SPLIT_MAX_PAIRS * 32) k_encode_ops_split(C
               const uint32_t is_lps = (row.mps4 ^ op) & 1u;
               ctx.store(c, is_lps ? row.next_lps : row.next_mps);
               l4[k] = row.lps4;
-              fl |= (is_lps | (code > kOpTrmCode ? SF_EP : 0u)) << (8 * k);
+              fl |= (is_lps | (code >= n_ctx ? SF_EP : 0u)) << (8 * k);
             }
           }
           asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(ring_s + st_off + g * SPLIT_GROUP), "r"(l4[0]), "r"(l4[1]), "r"(l4[2]), "r"(l4[3]) : "memory");
@@ -895,7 +895,7 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   if (P.n_ctx > ISSCABAC_MAX_CTX) { set_error("n_ctx > %u", ISSCABAC_MAX_CTX); return ISSCABAC_ERR_INVALID; }
   if (P.n_streams == 0) return ISSCABAC_OK;
   const size_t tab_bytes = TAB_WORDS * sizeof(uint2);
-  const size_t smem_ctx = tab_bytes + (size_t)P.n_ctx * NT * 4;
+  const size_t smem_ctx = tab_bytes + (size_t)(P.n_ctx ? P.n_ctx : 1) * NT * 4;   // n_ctx == 0: slot 0 is still loaded (value unused)
   const size_t lim = smem_limit();
   if (!lim) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
   // hot path: u8 ops, context block of one warp fits shared memory next to the table

@@ -818,13 +818,14 @@ int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, name);
 }
 
-int check_cfg(const isscabac_symcfg* cfg, uint32_t n_ctx, int sym_width, bool need_ctx) {
+int check_cfg(const isscabac_symcfg* cfg, uint32_t n_ctx, int sym_width, bool need_ctx, bool decode = false) {
   if (!cfg) { set_error("symcfg is NULL"); return ISSCABAC_ERR_INVALID; }
   if (cfg->profile < 0 || cfg->profile > ISSCABAC_PROFILE_FLAT_EPSUF) { set_error("unknown profile %d", cfg->profile); return ISSCABAC_ERR_INVALID; }
-  if (cfg->method < 0 || cfg->method > ISSCABAC_BIN_FL32) {
-    // the truncated-Rice codes of cabacBinarizer.m:39-54 are incomplete upstream (escape is a TODO)
-    // and cannot be decoded by the reference loops (cabacDecodeSymbolFinished.m has no case)
-    set_error("binarization method %d not supported", cfg->method);
+  if (cfg->method < 0 || cfg->method > ISSCABAC_BIN_TR2) { set_error("unknown binarization method %d", cfg->method); return ISSCABAC_ERR_INVALID; }
+  if (decode && cfg->method >= ISSCABAC_BIN_TR0) {
+    // truncated Rice is encode-only upstream: the escape code is a TODO (cabacBinarizer.m:47-50) and the decode loops
+    // have no case for it (cabacDecodeSymbolFinished.m:10-32)
+    set_error("truncated-Rice streams cannot be decoded (as in the reference)");
     return ISSCABAC_ERR_UNSUPPORTED;
   }
   if (cfg->Nlbp < 1 || cfg->Nlbp > 32) { set_error("Nlbp out of range"); return ISSCABAC_ERR_INVALID; }
@@ -951,7 +952,7 @@ int cabac_decode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const u
                          const uint8_t* d_bytes, const uint64_t* d_sym_off,
                          const uint8_t* d_ctx_init, uint32_t n_ctx, int per_stream_init,
                          void* d_symbols, int sym_width, uint8_t* d_finish_ok, void* stream) {
-  int rc = check_cfg(cfg, n_ctx, sym_width, true);
+  int rc = check_cfg(cfg, n_ctx, sym_width, true, true);
   if (rc) return rc;
   if (n_streams == 0) return ISSCABAC_OK;
   if (!d_sym_off || !d_byte_off || !d_bytes || !d_symbols || !d_ctx_init) { set_error("cabac_decode_symbols: null pointer"); return ISSCABAC_ERR_INVALID; }

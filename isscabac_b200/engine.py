@@ -14,11 +14,12 @@ import torch
 
 from ._lib import CabacError, SymCfg, check, lib, vp
 
-BIN_TU, BIN_EG0, BIN_EG1, BIN_EG2, BIN_FL32 = range(5)
+BIN_TU, BIN_EG0, BIN_EG1, BIN_EG2, BIN_FL32, BIN_TR0, BIN_TR1, BIN_TR2 = range(8)
 PROFILE_DEMO, PROFILE_ISS, PROFILE_FLAT, PROFILE_FLAT_EPSUF = range(4)
 CM_COND0, CM_COND1, CM_CONDBINLFT, CM_CONDS0, CM_CONDS1 = 1, 2, 4, 8, 16
 OP8_TRM, OP8_EP, OP16_TRM, OP16_EP = 125, 126, 0x7FFD, 0x7FFE
-METHODS = {"DEC2TU": BIN_TU, "DEC2EG0": BIN_EG0, "DEC2EG1": BIN_EG1, "DEC2EG2": BIN_EG2, "DEC2FL32": BIN_FL32}
+METHODS = {"DEC2TU": BIN_TU, "DEC2EG0": BIN_EG0, "DEC2EG1": BIN_EG1, "DEC2EG2": BIN_EG2, "DEC2FL32": BIN_FL32,
+           "DEC2TR0": BIN_TR0, "DEC2TR1": BIN_TR1, "DEC2TR2": BIN_TR2}   # truncated Rice: binarize / encode only (as upstream)
 CM_TYPES = {"cond0": CM_COND0, "cond1": CM_COND1, "condbinlft": CM_CONDBINLFT, "conds0": CM_CONDS0, "conds1": CM_CONDS1}
 
 
@@ -328,7 +329,11 @@ def encode_symbols_host(cfg: SymCfg, symbols, sym_off, ctx_init, want_bits: bool
     off = np.ascontiguousarray(sym_off, dtype=np.uint64)
     n = off.size - 1
     c, n_ctx, per = _np_ctx(ctx_init, n)
-    per_sym = 67 if cfg.method != BIN_TU else max(int(cfg.Nq), 2)
+    if cfg.method >= BIN_TR0:
+        k = cfg.method - BIN_TR0
+        per_sym = ((max(int(cfg.Nq), 2) - 1) >> k) + 1 + k if cfg.Nq else (1 << (8 * s.dtype.itemsize)) + k
+    else:
+        per_sym = 67 if cfg.method != BIN_TU else max(int(cfg.Nq), 2)
     payload = np.empty(int(s.size) * per_sym // 8 + 16 * max(n, 1) + 64, dtype=np.uint8)
     boff = np.empty(n + 1, dtype=np.uint64)
     bits = np.empty(max(s.size, 1), dtype=np.uint32) if want_bits else None

@@ -569,7 +569,8 @@ static void encode_ops_stream(void* arg, uint32_t s) {
   orc_enc_start(&e);
   for (uint64_t i = j->op_off[s]; i < j->op_off[s + 1]; ++i) {
     uint32_t o = job_op(j, i), code = o >> 1, bin = o & 1u;
-    if (code == j->ep) orc_enc_ep(&e, bin);
+    /* op format (include/isscabac.h): a code >= n_ctx that is not the terminate code is a bypass bin */
+    if (code == j->ep || (code != j->trm && code >= j->n_ctx)) orc_enc_ep(&e, bin);
     else if (code == j->trm) orc_enc_trm(&e, bin);
     else orc_enc_bin(&e, bin, &ctx[code]);
   }
@@ -597,7 +598,7 @@ static void decode_ops_stream(void* arg, uint32_t s) {
   for (uint64_t i = j->op_off[s]; i < j->op_off[s + 1]; ++i) {
     uint32_t code = job_op(j, i) >> 1;
     unsigned bin;
-    if (code == j->ep) bin = orc_dec_ep(&d);
+    if (code == j->ep || (code != j->trm && code >= j->n_ctx)) bin = orc_dec_ep(&d);
     else if (code == j->trm) bin = orc_dec_trm(&d);
     else bin = orc_dec_bin(&d, &ctx[code]);
     j->out_bins[i] = (uint8_t)bin;

@@ -25,7 +25,7 @@ int emul_encode_ops(uint32_t n_streams, const uint64_t* op_off, const void* ops,
     for (uint64_t i = op_off[s]; i < op_off[s + 1]; ++i) {
       uint32_t o = width == 1 ? ((const uint8_t*)ops)[i] : ((const uint16_t*)ops)[i];
       uint32_t code = o >> 1, bin = o & 1u;
-      if (code == ep) enc_bin_ep<true>(L, bin);
+      if (code == ep || (code != trm && code >= n_ctx)) enc_bin_ep<true>(L, bin);   // op format: non-context codes are bypass bins
       else if (code == trm) enc_bin_trm<true>(L, bin);
       else enc_bin_ctx<true>(L, bin, ctx[code], fused_row(ctx[code]));
       if (bits_trace) bits_trace[i] = enc_bits_written(L);
@@ -51,7 +51,7 @@ int emul_decode_ops(uint32_t n_streams, const uint64_t* byte_off, const uint8_t*
     for (uint64_t i = op_off[s]; i < op_off[s + 1]; ++i) {
       uint32_t o = width == 1 ? ((const uint8_t*)ops)[i] : ((const uint16_t*)ops)[i];
       uint32_t code = o >> 1;
-      if (code == ep) bins[i] = (uint8_t)dec_bin_ep(D);
+      if (code == ep || (code != trm && code >= n_ctx)) bins[i] = (uint8_t)dec_bin_ep(D);
       else if (code == trm) bins[i] = (uint8_t)dec_bin_trm(D);
       else bins[i] = (uint8_t)dec_bin_ctx(D, ctx[code], fused_row(ctx[code]));
     }

@@ -213,3 +213,23 @@ def test_full_length_streams_roundtrip(I, enc_kernel):
     assert ok.all() and (bins == (ops & 1)).all()
     s_ref, l_ref = O.encode_ops(ops[:64 * 65536], off[:65], ci, out_stride=16448, n_threads=8)
     assert (lens[:64] == l_ref).all() and same_rows(slab[:64], s_ref, l_ref)
+
+
+def test_out_of_range_codes_are_bypass_bins(I, enc_kernel):
+    """Codes >= n_ctx (other than terminate) are bypass bins in every kernel formulation: wide / two-warp / latency kernels
+    (u8, shared-memory contexts), the general kernels (u16 ops, many contexts), n_ctx == 0 included."""
+    rng = np.random.default_rng(43)
+    for n_ctx, wide16 in ((5, False), (0, False), (23, True), (300, True)):
+        n_streams, n_ops = 100, 500
+        off = (np.arange(n_streams + 1) * n_ops).astype(np.int64)
+        hi = 0x7FFD if wide16 else 125
+        code = rng.integers(0, max(n_ctx, 1), size=n_streams * n_ops).astype(np.uint32)
+        bad = rng.random(len(code)) < (0.1 if n_ctx else 1.0)
+        code[bad] = rng.integers(n_ctx, hi, size=int(bad.sum()))
+        bins = (rng.random(len(code)) < 0.4).astype(np.uint32)
+        ops = ((code << 1) | bins).astype(np.uint16 if wide16 else np.uint8)
+        ci = rng.integers(0, 126, size=max(n_ctx, 0)).astype(np.uint8)
+        slab, lens, payload, boff, dbins, ok = gpu_roundtrip(I, ops, off, ci, stride=512)
+        s_ref, l_ref = O.encode_ops(ops, off.astype(np.uint64), ci, out_stride=512, n_threads=4)
+        assert (lens == l_ref).all() and same_rows(slab, s_ref, l_ref), (n_ctx, wide16)
+        assert ok.all() and (dbins == bins).all(), (n_ctx, wide16)

@@ -53,6 +53,9 @@ def test_golden_symbol_cases(I, golden_dir):
     (O.PROFILE_FLAT, O.BIN_EG0, 16, 0, np.uint8),       # config C4 segments
     (O.PROFILE_FLAT_EPSUF, O.BIN_EG2, 256, 0, np.uint8),  # config C5 streams
     (O.PROFILE_FLAT, O.BIN_FL32, 0, 0, np.uint32),
+    (O.PROFILE_FLAT, O.BIN_TR0, 16, 0, np.uint8),       # truncated Rice: binarize / encode only, as upstream
+    (O.PROFILE_ISS, O.BIN_TR1, 16, 40, np.uint8),
+    (O.PROFILE_DEMO, O.BIN_TR2, 32, 0, np.uint8),
 ])
 def test_many_streams_vs_oracle(I, prof, meth, Nq, rows, dtype):
     rng = np.random.default_rng(21)
@@ -86,9 +89,13 @@ def test_many_streams_vs_oracle(I, prof, meth, Nq, rows, dtype):
     assert (bits.cpu().numpy().astype(np.uint32) == bits_ref).all()        # getNumBits() after every symbol
     pay = I.compact(enc)
     tdt = {np.uint8: torch.uint8, np.uint16: torch.int16, np.uint32: torch.int32}[dtype]
-    dec, ok = I.decode_symbols(cfg, pay, off.astype(np.int64), ci, sym_dtype=tdt)
-    assert bool(ok.all().item())
-    assert (dec.cpu().numpy().view(dtype) == sym).all()
+    if meth >= O.BIN_TR0:   # the reference's decode loops have no case for truncated Rice: refused, not guessed
+        with pytest.raises(I.CabacError):
+            I.decode_symbols(cfg, pay, off.astype(np.int64), ci, sym_dtype=tdt)
+    else:
+        dec, ok = I.decode_symbols(cfg, pay, off.astype(np.int64), ci, sym_dtype=tdt)
+        assert bool(ok.all().item())
+        assert (dec.cpu().numpy().view(dtype) == sym).all()
     # symbol-parallel binarizer against the oracle's op stream
     ops, op_off = I.binarize_symbols(cfg, sym, off.astype(np.int64))
     want = np.concatenate([O.symbols_to_ops(ocfg, sym[int(off[s]):int(off[s + 1])]) for s in range(n_streams)])
@@ -152,6 +159,27 @@ def test_baseline_symbol_configs_properties(I, name, scale):
     assert bool(ok.all().item()) and bool((dec == sym).all().item())
     bins, ok2 = I.decode_ops(p1, ops, op_off, ctx)
     assert bool(ok2.all().item()) and bool((bins == (ops & 1)).all().item())
+    # the CUDA path against the ORACLE on a stratified sample of the streams (runs of 8 spread over the whole range, first
+    # and last streams included): bytes and lengths of the fused encoder, decoded symbols
+    ocfg = O.make_cfg(cfg.profile, cfg.method, cfg.Nq, cfg.Nlbp, cfg.types, cfg.rows)
+    offn_all = off.cpu().numpy()
+    starts = np.unique(np.round(np.linspace(0, n - 8, 48)).astype(np.int64))
+    ids = np.unique(np.concatenate([np.arange(st, st + 8) for st in starts] + [np.arange(0, 3)]))
+    lens_s = offn_all[ids + 1] - offn_all[ids]
+    off_s = np.zeros(len(ids) + 1, dtype=np.uint64)
+    np.cumsum(lens_s, out=off_s[1:])
+    gather = np.concatenate([np.arange(offn_all[i], offn_all[i + 1]) for i in ids])
+    sym_s = sym[torch.as_tensor(gather, device=dev)].cpu().numpy().astype(np.uint32)
+    s_ref, l_ref = O.encode_symbols(ocfg, sym_s, off_s, np.full(nctx, 1, np.uint8), stride, n_threads=8)
+    idt = torch.as_tensor(ids, device=dev)
+    assert (e2.lengths[idt].cpu().numpy().astype(np.uint32) == l_ref).all(), "stream lengths differ from the oracle"
+    w = int(l_ref.max())
+    live = np.arange(w)[None, :] < l_ref[:, None]
+    assert (e2.slab[idt][:, :w].cpu().numpy()[live] == s_ref[:, :w][live]).all(), "fused encoder bytes differ from the oracle"
+    assert (e1.slab[idt][:, :w].cpu().numpy()[live] == s_ref[:, :w][live]).all(), "two-pass encoder bytes differ from the oracle"
+    pay_ref, boff_ref = O.compact(s_ref, l_ref)
+    d_ref, ok_ref = O.decode_symbols(ocfg, pay_ref, boff_ref, off_s, np.full(nctx, 1, np.uint8), n_threads=8)
+    assert ok_ref.all() and (d_ref == sym_s).all() and (dec[torch.as_tensor(gather, device=dev)].cpu().numpy() == d_ref).all()
     if name == "c5":   # the empty stream is the two bytes of start(); finish() (KAT K0)
         b = p1.payload[int(p1.byte_off[0].item()):int(p1.byte_off[1].item())].cpu().numpy()
         assert bytes(b) == bytes.fromhex("fe80")

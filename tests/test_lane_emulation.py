@@ -178,3 +178,24 @@ def test_lane_symbol_wide_values(emul):
         k = emul.emul_symbols_to_ops(cfgv.ctypes.data_as(C.POINTER(C.c_int32)), p(np.ascontiguousarray(v), u32p), C.c_uint64(len(v)), p(ops, u8p))
         want = O.symbols_to_ops(O.make_cfg(O.PROFILE_FLAT, meth, Nq, 3, 0, 0), v)
         assert k == len(want) and (ops[:k] == want).all(), meth
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_lane_truncated_rice(emul, k):
+    """DEC2TR0 / TR1 / TR2 (cabacBinarizer.m:39-54, encode-only upstream): the closed-form code of cabac_lane.cuh against
+    the oracle's bin-by-bin TRCode -- values below, at and above maxVal (the unfinished escape: suffix bits stay ones) --
+    and, for k = 0, against the arithmetic of TRCode worked by hand: n_p = v + 1, n_s = 0 -> v ones and a zero."""
+    Nq = 16
+    v = np.array(list(range(0, 40)) + [100, 255], dtype=np.uint32)
+    for prof in (O.PROFILE_FLAT, O.PROFILE_DEMO, O.PROFILE_ISS):
+        cfgv = np.array([prof, O.BIN_TR0 + k, Nq, 3, 0x1b, 0], dtype=np.int32)
+        ops = np.zeros(int(v.sum()) + 8 * len(v) + 64, dtype=np.uint8)
+        n = emul.emul_symbols_to_ops(cfgv.ctypes.data_as(C.POINTER(C.c_int32)), p(v, u32p), C.c_uint64(len(v)), p(ops, u8p))
+        want = O.symbols_to_ops(O.make_cfg(prof, O.BIN_TR0 + k, Nq, 3, 0x1b, 0), v)
+        assert n == len(want) and (ops[:n] == want).all(), (k, prof)
+    if k == 0:
+        for x in (0, 1, 5, 15, 16):
+            assert list(O.binarize(x, Nq, O.BIN_TR0)) == [1] * x + [0]
+    else:
+        assert list(O.binarize(5, Nq, O.BIN_TR0 + k)) == [1] * (5 >> k) + [0] + [(5 >> (k - 1 - i)) & 1 for i in range(k)]
+        assert list(O.binarize(15, Nq, O.BIN_TR0 + k)) == [1] * (15 >> k) + [0] + [1] * k        # v >= maxVal: escape TODO upstream

@@ -245,3 +245,31 @@ def test_wide_bypass_runs(emul, max_run):
                                    p(off, u64p), p(ops, u8p), p(ci.reshape(-1), u8p), C.c_uint32(n_ctx), 1,
                                    p(out, u8p), p(ok, u8p), C.c_uint32(max_run))
     assert ok.all() and (out[:n] == bins).all()
+
+
+def test_out_of_range_codes_are_bypass_bins(emul):
+    """Op format: a code >= n_ctx that is not the terminate code is coded as a BYPASS bin (include/isscabac.h) -- the same
+    in every formulation and in both directions, so a malformed op array cannot make encoder and decoder disagree."""
+    from test_lane_emulation import emul_decode, emul_encode
+    rng = np.random.default_rng(41)
+    n_ctx, n_streams, n_ops = 5, 40, 700
+    off = (np.arange(n_streams + 1) * n_ops).astype(np.uint64)
+    code = rng.integers(0, n_ctx, size=n_streams * n_ops).astype(np.uint8)
+    bad = rng.random(len(code)) < 0.1
+    code[bad] = rng.integers(n_ctx, 125, size=int(bad.sum()))        # not contexts of this call, not TRM, not EP
+    ops = ((code << 1) | (rng.random(len(code)) < 0.4)).astype(np.uint8)
+    as_ep = ops.copy()
+    as_ep[bad] = (O.OP8_EP << 1) | (ops[bad] & 1)
+    ci = rng.integers(0, 126, size=n_ctx).astype(np.uint8)
+    s_ref, l_ref = O.encode_ops(as_ep, off, ci, out_stride=512)      # the same ops with the bad codes written as bypass ops
+    s_o, l_o = O.encode_ops(ops, off, ci, out_stride=512)
+    assert (l_o == l_ref).all() and (s_o == s_ref).all()
+    s1, l1 = wide_encode(emul, ops, off, ci, 512, misalign=3)
+    s2, l2 = emul_encode(emul, ops, off, ci, 512)
+    live = np.arange(512)[None, :] < l_ref[:, None]
+    assert (l1 == l_ref).all() and (s1[live] == s_ref[live]).all()
+    assert (l2 == l_ref).all() and (s2[live] == s_ref[live]).all()
+    payload, boff = O.compact(s_ref, l_ref)
+    for bins, ok in (wide_decode(emul, payload, boff, ops, off, ci, misalign=3), emul_decode(emul, payload, boff, ops, off, ci),
+                     O.decode_ops(payload, boff, ops, off, ci)):
+        assert ok.all() and (bins == (ops & 1)).all()
