@@ -5,6 +5,9 @@ Tolerance (floating point, stated here as the task asks): the device sums the SO
 the restatement sums in storage order like the reference, so centroids are compared at 1e-10 relative
 (observed: ~1e-15) and group indices must be identical except for elements closer than 1e-9 to a decision
 threshold (observed: none)."""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -94,3 +97,23 @@ def test_quantize_wrapper_mirror_and_coder_round_trip(QZ, tmp_path):
     assert nbits > 0
     back = coder.cabacDecode(8, param, ctx_init, G.shape)
     assert (np.asarray(back) == G).all()
+
+
+def test_handworked_deadzone_cases_on_device(QZ, golden_dir):
+    """The fixture worked by hand from quantizeWrapper.m (tests/golden/quantize_handworked.json, arithmetic shown there):
+    integer data make every sum exact, so the device result must equal it BIT FOR BIT -- centroids, groups and the
+    Lloyd iteration count -- in all three modes with a dead zone.  No tolerance."""
+    with open(os.path.join(golden_dir, "quantize_handworked.json")) as f:
+        fx = json.load(f)
+    x = np.array(fx["x_rows"], dtype=np.float64)
+    for c in fx["cases"]:
+        fixed = c.get("fixedCentroids")
+        cfg = QZ.make_quant_cfg(N=c["N"], GMM=int(c["mode"] == "lloyd"), deadzoneQuant=fx["deadzoneQuant"],
+                                quantileprob=tuple(c.get("quantileprob", (0.0, 1.0))), fixedCentroids=fixed)
+        g, cent, it = QZ.quantize_matrices([x, x], cfg, fixed, want_iters=True)     # twice: batch entries are independent
+        torch.cuda.synchronize()
+        for k in range(2):
+            assert cent[k].cpu().numpy().tolist() == c["centroids"], c["name"]
+            assert g.cpu().numpy()[12 * k: 12 * k + 12].tolist() == c["group_minus_1_flattened"], c["name"]
+            if "iterations" in c:
+                assert int(it[k].item()) == c["iterations"], c["name"]

@@ -2,6 +2,9 @@
 quantize.m) against hand-computed cases and the properties Lloyd's iteration must have.  The reference
 holds no vectors for this step and MATLAB is absent: parity with MATLAB output is unpinned (see the
 oracle's header); these tests pin the restatement to the cited lines."""
+import json
+import os
+
 import numpy as np
 
 from oracle import quantize_oracle as Q
@@ -71,3 +74,22 @@ def test_wrapper_dead_zone():
     sym4, cent4, _ = Q.quantize_wrapper(x, N=8, mode=Q.MODE_UNIFORM, deadzone_quant=None, quantileprob=(0.1, 0.9))
     lo, hi = Q.matlab_quantile(x, [0.1, 0.9])
     assert cent4[0] == lo and cent4[-1] == hi and np.allclose(np.diff(cent4), (hi - lo) / 7)
+
+
+def test_handworked_deadzone_cases(golden_dir):
+    """tests/golden/quantize_handworked.json: a 12-element matrix taken through quantizeWrapper.m BY HAND (the file shows the
+    arithmetic line by line; integer data, so every operation is exact or a single correctly rounded division) in all
+    three modes with a dead zone.  The restatement must reproduce it to the bit."""
+    with open(os.path.join(golden_dir, "quantize_handworked.json")) as f:
+        fx = json.load(f)
+    x = np.array(fx["x_rows"], dtype=np.float64)
+    assert x.ravel(order="F").tolist() == fx["x_flattened_column_major"]
+    assert Q.matlab_quantile(x, fx["deadzoneQuant"])[0] == -1.5
+    for c in fx["cases"]:
+        mode = {"lloyd": Q.MODE_LLOYD, "uniform": Q.MODE_UNIFORM, "fixed": Q.MODE_FIXED}[c["mode"]]
+        sym, cent, it = Q.quantize_wrapper(x, N=c["N"], mode=mode, deadzone_quant=fx["deadzoneQuant"],
+                                           quantileprob=tuple(c.get("quantileprob", (0.0, 1.0))), fixed_centroids=c.get("fixedCentroids"))
+        assert cent.tolist() == c["centroids"], c["name"]
+        assert sym.ravel(order="F").tolist() == c["group_minus_1_flattened"], c["name"]
+        if "iterations" in c:
+            assert it == c["iterations"], c["name"]
