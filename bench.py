@@ -780,7 +780,7 @@ def run_b200(a):
     value = 2.0 * total_bins * world * a.steps / (ms * 1e-3) / 1e9
 
     # ---- end to end through the host-buffer C ABI (pinned host arrays) ------------------
-    e2e = None
+    e2e = e2e_u8 = None
     if not a.no_e2e:
         h_ops = torch.empty(total_bins, dtype=torch.uint8, pin_memory=True)
         h_ops.copy_(ops)
@@ -792,31 +792,45 @@ def run_b200(a):
         h_ok = np.empty(S, dtype=np.uint8)
         np_ops, np_pay, np_bins = h_ops.numpy(), h_pay.numpy(), h_bins.numpy()
 
-        def e2e_step():
+        h_bits = torch.empty((total_bins + 7) // 8, dtype=torch.uint8, pin_memory=True)
+        np_bits = h_bits.numpy()
+
+        def e2e_step(packed):
             p, bo = I.encode_ops_host(np_ops, h_off, h_ctx, payload_out=np_pay, byte_off_out=h_boff)
-            I.decode_ops_host(p, bo, np_ops, h_off, h_ctx, bins_out=np_bins)
+            I.decode_ops_host(p, bo, np_ops, h_off, h_ctx, bins_out=np_bits if packed else np_bins, packed=packed)
             return p
 
-        e2e_step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.e2e_steps):
-            p = e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        def e2e_run(packed):
+            e2e_step(packed)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(a.e2e_steps):
+                p = e2e_step(packed)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            h2d = total_bins + (S + 1) * 8 + N_CTX            # encode: ops, offsets, ctx
+            h2d += total_bins + len(p) + 2 * (S + 1) * 8 + N_CTX   # decode: op kinds, payload, both offset tables, ctx
+            d2h = len(p) + (S + 1) * 8 + (len(np_bits) if packed else total_bins) + S        # payload, offsets, bins, finish flags
+            return {"value": 2.0 * total_bins * world * a.e2e_steps / dt / 1e9, "unit": "Gbins/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": a.e2e_steps,
+                    "ms_per_step": dt / a.e2e_steps * 1e3,
+                    "gbytes_per_s_over_pcie": (h2d + d2h) / (dt / a.e2e_steps) / 1e9,
+                    "api": "cabac_encode_ops_host + " + ("cabac_decode_ops_host_packed (decoded bins bit-packed, 8 per byte)" if packed
+                                                         else "cabac_decode_ops_host (decoded bins one per byte)")}
+
+        e2e_u8 = e2e_run(False)
         assert (np_bins[:1 << 20] == (np_ops[:1 << 20] & 1)).all()
-        h2d = total_bins + (S + 1) * 8 + N_CTX            # encode: ops, offsets, ctx
-        h2d += total_bins + len(p) + 2 * (S + 1) * 8 + N_CTX   # decode: op kinds, payload, both offset tables, ctx
-        d2h = len(p) + (S + 1) * 8 + total_bins + S        # payload, offsets, bins, finish flags
-        e2e = {"value": 2.0 * total_bins * world * a.e2e_steps / dt / 1e9, "unit": "Gbins/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": a.e2e_steps,
-               "ms_per_step": dt / a.e2e_steps * 1e3}
+        e2e = e2e_run(True)
+        assert (np.unpackbits(np_bits[:1 << 17], bitorder="little") == (np_ops[:1 << 20] & 1)).all()
+        e2e["note"] = ("host buffers in, host buffers out, every copy inside the timed calls; PCIe-bound (see gbytes_per_s_over_pcie; "
+                       "the box moves ~55 GB/s one way, ~47 GB/s each way when both directions run)")
+        del h_bits
         del h_ops, h_bins, h_pay
 
     # ---- CPU baseline beside it (rank 0 only, N=1 only): bounded sample + byte parity -------
@@ -941,6 +955,7 @@ def run_b200(a):
         "gpu_launches": (5 + (2 if world > 1 else 0)) * a.steps,   # encode, scan_init, scan, compact_copy, decode (+ the global scan at N > 1)
         "clocks": clocks,
         "e2e": e2e,
+        "e2e_u8_bins": e2e_u8,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                      "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes": dom_bytes, "peak_source": peak_src,

@@ -275,6 +275,15 @@ int cabac_decode_ops_host(uint32_t n_streams, const uint64_t* h_byte_off, const 
                           const uint64_t* h_op_off, const void* h_ops, int op_width,
                           const uint8_t* h_ctx_init, uint32_t n_ctx, int per_stream_init,
                           uint8_t* h_bins, uint8_t* h_finish_ok);
+/* The same decode with the bins returned BIT-PACKED: bit (i & 7) of h_bins_packed[i >> 3] = bin of op i (ops counted over
+ * the whole op array, (n_ops + 7) / 8 bytes).  A decoded bin is one bit of information; one byte per bin is what the
+ * op-level contract above carries, and on a PCIe-bound call the device-to-host leg shrinks eightfold. */
+int cabac_decode_ops_host_packed(uint32_t n_streams, const uint64_t* h_byte_off, const uint8_t* h_bytes,
+                                 const uint64_t* h_op_off, const void* h_ops, int op_width,
+                                 const uint8_t* h_ctx_init, uint32_t n_ctx, int per_stream_init,
+                                 uint8_t* h_bins_packed, uint8_t* h_finish_ok);
+/* device: d_packed[(bit_begin >> 3) ...] = bins [bit_begin, bit_end) packed as above; bit_begin must be a multiple of 8 */
+int cabac_pack_bins(const uint8_t* d_bins, uint64_t bit_begin, uint64_t bit_end, uint8_t* d_packed, void* stream);
 int cabac_encode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* h_sym_off,
                               const void* h_symbols, int sym_width,
                               const uint8_t* h_ctx_init, uint32_t n_ctx, int per_stream_init,

@@ -67,6 +67,9 @@ CB_HD uint32_t cb_bswap(uint32_t x) { return cb_perm(x, 0, 0x0123); }
 #ifndef CABAC_LAZY
 #define CABAC_LAZY 1
 #endif
+#ifndef CABAC_DEC_TMA
+#define CABAC_DEC_TMA 0      // decoder input staged by bulk copies: compile-time experiment, see below
+#endif
 // VOTE = all 32 lanes of the warp execute this call together (the caller guarantees it: the kernels
 // walk the blocks every lane of a full warp has in lockstep); otherwise this lane decides alone
 template <bool VOTE>
@@ -296,12 +299,66 @@ struct DecWide {
   uint32_t widx, wcnt;   // next aligned word to load / number of aligned words that hold stream bytes
   const uint32_t* wbase; // aligned word that holds stream byte 3
   const uint8_t* in;     // first byte of the stream
+#if CABAC_DEC_TMA && defined(__CUDACC__)
+  // experiment (see the CABAC_DEC_TMA block below): the stream's bytes staged in shared memory by 1-D bulk copies
+  uint32_t ring = 0;     // shared-window address of this lane's two 64-byte stages (0: plain global loads)
+  uint32_t mbar;         // shared-window address of this lane's two mbarriers
+  uint32_t cwait;        // chunk (relative to g0) this lane has already waited for
+  uint64_t g0;           // global address of chunk 0 (64-byte aligned)
+  uint64_t gend;         // no chunk is copied past this address (end of the payload, rounded up to 16)
+#endif
 };
 
+// ---------------------------------------------------------------------------
+// CABAC_DEC_TMA (compile-time experiment, north_star (4): "pulls each stream's bytes into shared memory with TMA bulk
+// copies").  Every lane owns a ring of two 64-byte stages and two mbarriers; chunk c of its stream (the 64-byte aligned
+// piece of the payload that holds it) is brought in with ONE cp.async.bulk.shared.global (UBLKCP in SASS) that
+// completes on the stage's mbarrier; the aligned words the window refill needs are then LDS.32 from the ring instead
+// of per-lane 32-bit global loads.  Chunk c + 2 is requested when the last word of chunk c has been taken.
+// Built only into tuning variants (tools/tune.py build tma:CABAC_DEC_TMA=1); result in profiles/r2_tma_decode_experiment.txt.
+// ---------------------------------------------------------------------------
+#if CABAC_DEC_TMA && defined(__CUDACC__)
+constexpr uint32_t kTmaLaneStride = 144;     // 2 x 64 B + 16 B pad (keeps the stages 16-byte aligned, spreads the banks)
+__device__ __forceinline__ void decw_tma_issue(DecWide& D, uint32_t c) {
+  const uint64_t src = D.g0 + 64ull * c;
+  if (src >= D.gend || src >= reinterpret_cast<uint64_t>(D.in) + D.len) return;   // nothing of this stream in the chunk
+  const uint64_t left = D.gend - src;
+  const uint32_t bytes = left < 64 ? (uint32_t)left : 64u;
+  const uint32_t st = c & 1u, bar = D.mbar + 8u * st, dst = D.ring + 64u * st;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was read through the generic proxy
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void decw_tma_wait(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+               :: "r"(bar), "r"(parity) : "memory");
+}
+#endif
+
+
 CB_HD uint32_t decw_load(DecWide& D) {
+#if CABAC_DEC_TMA && defined(__CUDA_ARCH__)
+  uint32_t v = 0u;
+  if (!D.ring) {
+    if (D.widx < D.wcnt) v = D.wbase[D.widx];
+  } else if (D.widx < D.wcnt) {
+    const uint64_t a = reinterpret_cast<uint64_t>(D.wbase) + 4ull * D.widx;
+    const uint32_t c = (uint32_t)((a - D.g0) >> 6), st = c & 1u, o = (uint32_t)a & 63u;
+    if (c != D.cwait) {                     // first word taken from this chunk
+      decw_tma_wait(D.mbar + 8u * st, (c >> 1) & 1u);
+      D.cwait = c;
+    }
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(D.ring + 64u * st + o) : "memory");
+    if (o == 60u) decw_tma_issue(D, c + 2u);
+  }
+  D.widx++;
+  return v;
+#else
   const uint32_t v = D.widx < D.wcnt ? D.wbase[D.widx] : 0u;
   D.widx++;
   return v;
+#endif
 }
 
 // big-endian word of stream bytes p..p+3, 0xFF past the end (BitstreamFile.cpp:153-158)
@@ -341,6 +398,11 @@ CB_HD void decw_start(DecWide& D, const uint8_t* in, uint32_t len) {
   // aligned words from the one holding byte 3 to the one holding byte len-1
   D.wcnt = len > 3 ? (uint32_t)(((a + (len - 4u)) >> 2) - (a >> 2)) + 1u : 0u;
   D.widx = 0;
+#if CABAC_DEC_TMA && defined(__CUDA_ARCH__)
+  D.g0 = reinterpret_cast<uint64_t>(D.wbase) & ~63ull;
+  D.cwait = 0xffffffffu;
+  if (D.wcnt && D.ring) { decw_tma_issue(D, 0u); decw_tma_issue(D, 1u); }
+#endif
   D.cur = decw_load(D);
   D.nxt = decw_load(D);
   decw_refill(D);   // bytes 3..6

@@ -275,10 +275,10 @@ int cabac_encode_ops_host(uint32_t n_streams, const uint64_t* h_op_off, const vo
   return ISSCABAC_ERR_OVERFLOW;
 }
 
-int cabac_decode_ops_host(uint32_t n_streams, const uint64_t* h_byte_off, const uint8_t* h_bytes,
+static int decode_ops_host_impl(uint32_t n_streams, const uint64_t* h_byte_off, const uint8_t* h_bytes,
                           const uint64_t* h_op_off, const void* h_ops, int op_width,
                           const uint8_t* h_ctx_init, uint32_t n_ctx, int per_stream_init,
-                          uint8_t* h_bins, uint8_t* h_finish_ok) {
+                          uint8_t* h_bins, uint8_t* h_finish_ok, bool packed) {
   if (!h_op_off || !h_byte_off) { set_error("cabac_decode_ops_host: null pointer"); return ISSCABAC_ERR_INVALID; }
   if (op_width != 1 && op_width != 2) { set_error("op_width must be 1 or 2"); return ISSCABAC_ERR_INVALID; }
   if (n_streams == 0) return ISSCABAC_OK;
@@ -291,11 +291,12 @@ int cabac_decode_ops_host(uint32_t n_streams, const uint64_t* h_byte_off, const 
   const uint64_t obase = h_op_off[0], total = h_op_off[n_streams] - obase;
   const uint64_t bbase = h_byte_off[0], nbytes = h_byte_off[n_streams] - bbase;
   const size_t ctx_bytes = (size_t)n_ctx * (per_stream_init ? n_streams : 1);
-  DevBuf d_ops, d_off, d_boff, d_bytes, d_ctx, d_bins, d_ok;
+  DevBuf d_ops, d_off, d_boff, d_bytes, d_ctx, d_bins, d_ok, d_packed;
   Drain drain{g_pipe};
   if ((rc = d_ops.alloc(total * op_width, s0)) || (rc = d_off.alloc((n_streams + 1ull) * 8, s0)) ||
       (rc = d_boff.alloc((n_streams + 1ull) * 8, s0)) || (rc = d_bytes.alloc(nbytes + 16, s0)) ||
-      (rc = d_ctx.alloc(ctx_bytes, s0)) || (rc = d_bins.alloc(total, s0)) || (rc = d_ok.alloc(n_streams, s0)))
+      (rc = d_ctx.alloc(ctx_bytes, s0)) || (rc = d_bins.alloc(total, s0)) || (rc = d_ok.alloc(n_streams, s0)) ||
+      (rc = d_packed.alloc(packed ? (total + 7) / 8 + 16 : 16, s0)))
     return rc;
   std::vector<uint64_t> off_rel, boff_rel;
   const uint64_t *off_src = h_op_off, *boff_src = h_byte_off;
@@ -317,6 +318,8 @@ int cabac_decode_ops_host(uint32_t n_streams, const uint64_t* h_byte_off, const 
   for (int l = 1; l < kLanes; ++l) CK(cudaStreamWaitEvent(g_pipe.s[l], g_pipe.done[0], 0));
   std::vector<uint32_t> cb;
   make_chunks(n_streams, off_src, kChunks, cb);
+  bool chunks_byte_aligned = true;
+  for (size_t k = 1; k + 1 < cb.size(); ++k) chunks_byte_aligned = chunks_byte_aligned && (off_src[cb[k]] & 7u) == 0;
   for (size_t k = 0; k + 1 < cb.size(); ++k) {
     cudaStream_t st = g_pipe.s[k % kLanes];
     const uint32_t a = cb[k], b = cb[k + 1];
@@ -328,17 +331,44 @@ int cabac_decode_ops_host(uint32_t n_streams, const uint64_t* h_byte_off, const 
                           op_width, d_ctx.as<uint8_t>() + (per_stream_init ? (size_t)a * n_ctx : 0), n_ctx,
                           per_stream_init, d_bins.as<uint8_t>(), d_ok.as<uint8_t>() + a, st);
     if (rc) return rc;
-    if (h_bins && ob > oa)
+    if (h_bins && ob > oa && !packed)
       CK(cudaMemcpyAsync(h_bins + oa, d_bins.as<uint8_t>() + oa, ob - oa, cudaMemcpyDeviceToHost, st));
+    // packed: a chunk whose op range starts and ends on byte boundaries of the packed array is packed and sent home
+    // on its own lane while later chunks are still coded; otherwise everything is packed after the last chunk
+    if (h_bins && ob > oa && packed && chunks_byte_aligned) {
+      if ((rc = cabac_pack_bins(d_bins.as<uint8_t>(), oa, ob, d_packed.as<uint8_t>(), st))) return rc;
+      CK(cudaMemcpyAsync(h_bins + (oa >> 3), d_packed.as<uint8_t>() + (oa >> 3), (ob - oa + 7) >> 3, cudaMemcpyDeviceToHost, st));
+    }
   }
   for (int l = 1; l < kLanes; ++l) {
     CK(cudaEventRecord(g_pipe.done[l], g_pipe.s[l]));
     CK(cudaStreamWaitEvent(s0, g_pipe.done[l], 0));
   }
+  if (h_bins && packed && !chunks_byte_aligned && total) {
+    if ((rc = cabac_pack_bins(d_bins.as<uint8_t>(), 0, total, d_packed.as<uint8_t>(), s0))) return rc;
+    CK(cudaMemcpyAsync(h_bins, d_packed.p, (total + 7) >> 3, cudaMemcpyDeviceToHost, s0));
+  }
   if (h_finish_ok) CK(cudaMemcpyAsync(h_finish_ok, d_ok.p, n_streams, cudaMemcpyDeviceToHost, s0));
   CK(cudaStreamSynchronize(s0));
   return ISSCABAC_OK;
 }
+
+int cabac_decode_ops_host(uint32_t n_streams, const uint64_t* h_byte_off, const uint8_t* h_bytes,
+                          const uint64_t* h_op_off, const void* h_ops, int op_width,
+                          const uint8_t* h_ctx_init, uint32_t n_ctx, int per_stream_init,
+                          uint8_t* h_bins, uint8_t* h_finish_ok) {
+  return decode_ops_host_impl(n_streams, h_byte_off, h_bytes, h_op_off, h_ops, op_width, h_ctx_init, n_ctx, per_stream_init,
+                              h_bins, h_finish_ok, false);
+}
+
+int cabac_decode_ops_host_packed(uint32_t n_streams, const uint64_t* h_byte_off, const uint8_t* h_bytes,
+                                 const uint64_t* h_op_off, const void* h_ops, int op_width,
+                                 const uint8_t* h_ctx_init, uint32_t n_ctx, int per_stream_init,
+                                 uint8_t* h_bins_packed, uint8_t* h_finish_ok) {
+  return decode_ops_host_impl(n_streams, h_byte_off, h_bytes, h_op_off, h_ops, op_width, h_ctx_init, n_ctx, per_stream_init,
+                              h_bins_packed, h_finish_ok, true);
+}
+
 
 }  // extern "C"
 

@@ -591,6 +591,18 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, WIDE_DEC_MINBLOCKS) k_dec
   const uint64_t b0 = P.byte_off[s], b1 = P.byte_off[s + 1];
 
   DecWide D;
+#if CABAC_DEC_TMA
+  {   // this lane's ring + mbarriers behind the context blocks (see run_codec for the size)
+    const uint32_t nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)WIDE_TAB_BYTES + nwarps * (n_ctx + 1) * 128u;
+    D.ring = base + (warp * 32u + lane) * kTmaLaneStride;
+    D.mbar = base + nwarps * 32u * kTmaLaneStride + (warp * 32u + lane) * 16u;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(D.mbar) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(D.mbar + 8u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    D.gend = (reinterpret_cast<uint64_t>(P.bytes) + P.byte_off[P.n_streams] + 15ull) & ~15ull;
+  }
+#endif
   decw_start(D, P.bytes + b0, (uint32_t)(b1 - b0));
 
   uint64_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u;
@@ -771,6 +783,26 @@ __global__ void __launch_bounds__(256) k_compact_copy(const uint8_t* slab, uint6
   if (lane < len - done) dst[done + lane] = src[done + lane];
 }
 
+// bins one per byte -> one per bit: thread t packs bytes [16t, 16t + 16) of the range into two bytes
+__global__ void __launch_bounds__(256) k_pack_bins(const uint8_t* bins, uint64_t n, uint8_t* out) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t i0 = t * 16;
+  if (i0 >= n) return;
+  uint32_t w[4] = {0, 0, 0, 0};
+  if (i0 + 16 <= n && (reinterpret_cast<uintptr_t>(bins + i0) & 15u) == 0) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(bins + i0));
+    w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+  } else {
+    for (uint32_t k = 0; k < 16 && i0 + k < n; ++k) w[k >> 2] |= (uint32_t)bins[i0 + k] << (8 * (k & 3));
+  }
+  uint32_t bits = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) bits |= ((((w[k] & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * k);   // byte j bit 0 -> bit j
+  const uint64_t left = n - i0;
+  out[2 * t] = (uint8_t)bits;
+  if (left > 8) out[2 * t + 1] = (uint8_t)(bits >> 8);
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -944,6 +976,9 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   }
   if (op_width == 1 && wide_geometry(P.n_streams, P.n_ctx, nw, grid, wsmem)) {
     auto kernel = ENC ? k_encode_ops_wide : k_decode_ops_wide;
+#if CABAC_DEC_TMA
+    if (!ENC) wsmem += (size_t)nw * 32 * (kTmaLaneStride + 16);     // rings + mbarriers of the bulk-copy experiment
+#endif
     if (wsmem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
@@ -1024,6 +1059,16 @@ int cabac_decode_ops(uint32_t n_streams, const uint64_t* d_byte_off, const uint8
   P.op_off = d_op_off; P.ops = d_ops; P.ctx_init = d_ctx_init;
   P.byte_off = d_byte_off; P.bytes = d_bytes; P.bins = d_bins; P.finish_ok = d_finish_ok;
   return run_codec<false>(P, op_width, static_cast<cudaStream_t>(stream));
+}
+
+int cabac_pack_bins(const uint8_t* d_bins, uint64_t bit_begin, uint64_t bit_end, uint8_t* d_packed, void* stream) {
+  if (bit_begin & 7u) { set_error("cabac_pack_bins: bit_begin must be a multiple of 8"); return ISSCABAC_ERR_INVALID; }
+  if (bit_end <= bit_begin) return ISSCABAC_OK;
+  if (!d_bins || !d_packed) { set_error("cabac_pack_bins: null pointer"); return ISSCABAC_ERR_INVALID; }
+  const uint64_t n = bit_end - bit_begin, threads = (n + 15) / 16;
+  k_pack_bins<<<(uint32_t)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_bins + bit_begin, n, d_packed + (bit_begin >> 3));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_pack_bins");
 }
 
 size_t cabac_compact_scratch_bytes(uint32_t n_streams) {

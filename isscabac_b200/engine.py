@@ -303,7 +303,9 @@ def encode_ops_host(ops, op_off, ctx_init, payload_out: np.ndarray | None = None
     return payload_out[:int(byte_off_out[-1])], byte_off_out
 
 
-def decode_ops_host(payload, byte_off, ops, op_off, ctx_init, bins_out: np.ndarray | None = None):
+def decode_ops_host(payload, byte_off, ops, op_off, ctx_init, bins_out: np.ndarray | None = None, packed: bool = False):
+    """-> (bins, finish_ok).  packed=True: bins come back bit-packed (bit i & 7 of byte i >> 3 = bin of op i,
+    np.unpackbits(..., bitorder="little") restores one per byte) -- cabac_decode_ops_host_packed."""
     _require_cuda()
     a, w = _np_ops(ops)
     off = np.ascontiguousarray(op_off, dtype=np.uint64)
@@ -311,14 +313,15 @@ def decode_ops_host(payload, byte_off, ops, op_off, ctx_init, bins_out: np.ndarr
     pay = np.ascontiguousarray(payload, dtype=np.uint8)
     n = off.size - 1
     c, n_ctx, per = _np_ctx(ctx_init, n)
+    n_out = (a.size + 7) // 8 if packed else a.size
     if bins_out is None:
-        bins_out = np.empty(max(a.size, 1), dtype=np.uint8)
+        bins_out = np.empty(max(n_out, 1), dtype=np.uint8)
     ok = np.zeros(max(n, 1), dtype=np.uint8)
     if pay.size == 0:
         pay = np.zeros(1, dtype=np.uint8)
-    check(lib().cabac_decode_ops_host(C.c_uint32(n), vp(boff), vp(pay), vp(off), vp(a), w, vp(c), C.c_uint32(n_ctx),
-                                      per, vp(bins_out), vp(ok)))
-    return bins_out[:a.size], ok[:n]
+    fn = lib().cabac_decode_ops_host_packed if packed else lib().cabac_decode_ops_host
+    check(fn(C.c_uint32(n), vp(boff), vp(pay), vp(off), vp(a), w, vp(c), C.c_uint32(n_ctx), per, vp(bins_out), vp(ok)))
+    return bins_out[:n_out], ok[:n]
 
 
 def encode_symbols_host(cfg: SymCfg, symbols, sym_off, ctx_init, want_bits: bool = False):

@@ -233,3 +233,31 @@ def test_out_of_range_codes_are_bypass_bins(I, enc_kernel):
         s_ref, l_ref = O.encode_ops(ops, off.astype(np.uint64), ci, out_stride=512, n_threads=4)
         assert (lens == l_ref).all() and same_rows(slab, s_ref, l_ref), (n_ctx, wide16)
         assert ok.all() and (dbins == bins).all(), (n_ctx, wide16)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_host_buffer_api_packed_bins(I, ragged):
+    """cabac_decode_ops_host_packed: the decoded bins one per BIT (little-endian within a byte) equal the one-per-byte
+    result; ragged streams put the chunk boundaries of the pipeline off the byte grid (packed after the last chunk then)."""
+    rng = np.random.default_rng(47)
+    n_streams = 3000
+    lens = rng.integers(0, 900, size=n_streams) if ragged else np.full(n_streams, 512)
+    off = np.zeros(n_streams + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    n = int(off[-1])
+    code = rng.integers(0, 7, size=n).astype(np.uint8)
+    code[rng.random(n) < 0.2] = O.OP8_EP
+    bins = (rng.random(n) < 0.35).astype(np.uint8)
+    ops = ((code << 1) | bins).astype(np.uint8)
+    ci = rng.integers(0, 126, size=7).astype(np.uint8)
+    payload, boff = I.encode_ops_host(ops, off, ci)
+    s_ref, l_ref = O.encode_ops(ops, off, ci, out_stride=512, n_threads=4)
+    p_ref, b_ref = O.compact(s_ref, l_ref)
+    assert (boff == b_ref).all() and (payload == p_ref).all()
+    b8, ok8 = I.decode_ops_host(payload, boff, ops, off, ci)
+    bp, okp = I.decode_ops_host(payload, boff, ops, off, ci, packed=True)
+    assert ok8.all() and okp.all() and (b8 == bins).all()
+    assert bp.size == (n + 7) // 8
+    assert (np.unpackbits(bp, bitorder="little")[:n] == bins).all()
+    if n % 8:    # padding bits of the last byte are zero
+        assert (np.unpackbits(bp, bitorder="little")[n:] == 0).all()

@@ -32,7 +32,7 @@ def main():
         env = dict(os.environ)
         if lib:
             env["ISSCABAC_LIB"] = lib
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-e2e", "--no-cpu", "--steps", "10"] + extra,
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-e2e", "--no-cpu", "--no-configs", "--steps", "10"] + extra,
                            capture_output=True, text=True, env=env)
         name = os.path.basename(lib) if lib else "default"
         try:
