@@ -422,9 +422,9 @@ __global__ void __launch_bounds__(2 * SPLIT_MAX_PAIRS * 32) k_encode_ops_split(C
   // table + context blocks (producers) as in wide_setup
   WRow* t = reinterpret_cast<WRow*>(smem);
   const uint32_t tab0 = (uint32_t)__cvta_generic_to_shared(smem);
-  for (uint32_t i = threadIdx.x; i < kNumRows * 32; i += blockDim.x) {
-    WRow r = c_wide_rows.r[i >> 5];
-    const uint32_t col = tab0 + (i & 31u) * (uint32_t)sizeof(WRow);
+  for (uint32_t i = threadIdx.x; i < kNumRows * WIDE_COLS; i += blockDim.x) {
+    WRow r = c_wide_rows.r[i / WIDE_COLS];
+    const uint32_t col = tab0 + (i % WIDE_COLS) * (uint32_t)sizeof(WRow);
     r.next_mps = col + r.next_mps * WIDE_ROW_STRIDE;
     r.next_lps = col + r.next_lps * WIDE_ROW_STRIDE;
     t[i] = r;
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(2 * SPLIT_MAX_PAIRS * 32) k_encode_ops_split(C
   const uint32_t s = (blockIdx.x * np + pair) * 32 + lane;
   const bool valid = s < P.n_streams;
   WTab tab;
-  tab.base = cb_keep32(tab0 + lane * (uint32_t)sizeof(WRow));
+  tab.base = cb_keep32(tab0 + (lane % WIDE_COLS) * (uint32_t)sizeof(WRow));
   WCtx ctx;
   ctx.p = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + cb_keep32(pair * (n_ctx + 1) * 32 + lane);
   if (producer) {

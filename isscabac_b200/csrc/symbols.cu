@@ -13,6 +13,7 @@
 //                            the debinarized symbol is stored.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/isscabac.h"
@@ -694,6 +695,155 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fused encoder, second formulation: the binarizer runs AHEAD of the coder through a per-lane ring of op bytes in
+// shared memory, so the coder's step is the 16-op block of the op-array kernels (encw_block16, ~35 instructions per
+// warp-bin) instead of a per-bin state machine whose divergent symbol fetch runs in nearly every step for some lane
+// (112 instructions per warp-step, profiles/r1_v10_fused_c4.txt).
+//   refill (warp-uniform loop, lanes vote): every lane short of 16 buffered ops expands ONE symbol per trip -- its op
+//     string comes out of the per-call table of k_bin_lut as 7 op bytes + length in 8 bytes (one LDS.64), is shifted to
+//     the ring's byte position in registers and stored with up to three aligned word stores; strings longer than 7 ops
+//     and symbols outside the table are produced 7 ops per trip by the closed form (sym_code / select_ctx / sym_bin);
+//   code: a lane with 16 buffered ops loads them with one LDS.128 and runs encw_block16 (voted emission when all 32
+//     lanes have a full block); a lane whose stream has run out of symbols codes its last ops one by one, finishes the
+//     stream and claims the next one from the work queue.
+// Used for u8 symbols when the profile has a table (every profile but FL32 alphabets); results are byte-identical to
+// k_encode_symbols_wide (tests/test_gpu_symbols.py runs both against the oracle).
+// ---------------------------------------------------------------------------
+constexpr uint32_t RING_BYTES = 64;                 // per lane: four 16-op blocks
+constexpr uint32_t RING_LANE_STRIDE = 80;           // + 16 B pad: the 8 lanes of a quarter-warp start in 8 different bank quads
+constexpr uint32_t RING_WARP_BYTES = 32 * RING_LANE_STRIDE;
+
+template <int PROF, int METH>
+__global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_ring(SymParams P, uint32_t* next_stream, const uint32_t* order) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint32_t s, n_ctx;
+  WCtx ctx;
+  WTab tab;
+  wide_setup(P.n_streams, P.n_ctx, P.ctx_init, 0, smem, s, ctx, tab, n_ctx);
+  const LaneCtx lc{ctx, tab, n_ctx, P.ctx_init, P.per_stream_init};
+  const SymCfg cfg = fixed_cfg<PROF, METH>(P.cfg);
+  const uint32_t cap = (uint32_t)(P.slab_stride > 0xfffffffcull ? 0xfffffffcull : P.slab_stride);
+  const uint32_t nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shared memory behind the context blocks: [entries] 8-byte op strings, then the rings
+  uint8_t* lp = smem + WIDE_TAB_BYTES + (size_t)nwarps * (P.n_ctx + 1) * 32 * 4;
+  uint2* lut8 = reinterpret_cast<uint2*>(lp);
+  for (uint32_t e = threadIdx.x; e < P.lut_entries; e += blockDim.x) {
+    const uint4 q = __ldg(P.lut + e);
+    const uint32_t len = q.w >> 24;                 // 0: more than 15 ops
+    lut8[e] = (len >= 1 && len <= 7) ? make_uint2(q.x, (q.y & 0x00ffffffu) | (len << 24)) : make_uint2(0u, 0u);
+  }
+  __syncthreads();
+  const uint32_t lut0 = (uint32_t)__cvta_generic_to_shared(lp);
+  const uint32_t ring0 = lut0 + ((P.lut_entries * 8u + 15u) & ~15u) + warp * RING_WARP_BYTES + lane * RING_LANE_STRIDE;
+
+  EncWide E;
+  encw_start(E, nullptr, 0);
+  const uint8_t* src = nullptr;
+  uint32_t cnt = 0, si = 0, row = 0;      // symbols in the stream, symbols expanded, row of the next symbol in its column
+  uint32_t curv = 0, nextv = 0;           // value of the symbol expanded last / of symbol si (loaded one symbol ahead)
+  uint32_t wr = 0, buffered = 0, pw = 0;  // ring: bytes appended (mod 64 = write position), ops not yet coded, the partial word at wr
+  uint32_t rd = 0;                        // ring read position (multiple of 16 until the tail)
+  // a symbol whose string does not come out of the table in one piece: produced 7 ops per trip by the closed form
+  SymCode cur = {0, 0, 0}, prevc = {0, 0, 0};
+  uint32_t mb = 1, mlen = 0;              // next bin (1-based) and length of that symbol's string; mb > mlen: none in progress
+  bool up = false, active = false, have = s < P.n_streams;
+  if (have && order) s = order[s];
+
+  // append `len` (1..7) op bytes held in (lo, hi) -- little-endian, zero above len -- to the ring
+  auto append = [&](uint32_t lo, uint32_t hi, uint32_t len) {
+    const uint32_t b8 = (wr & 3u) * 8u;
+    const uint32_t t0 = pw | (lo << b8);
+    const uint32_t t1 = cb_funnel_l(lo, hi, b8);
+    const uint32_t t2 = cb_funnel_l(hi, 0u, b8);
+    const uint32_t k0 = wr & 60u, end = (wr & 3u) + len;           // bytes of the touched words that are valid afterwards
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(ring0 + k0), "r"(t0) : "memory");
+    if (end > 4u) asm volatile("st.shared.u32 [%0], %1;" :: "r"(ring0 + ((k0 + 4u) & 60u)), "r"(t1) : "memory");
+    if (end > 8u) asm volatile("st.shared.u32 [%0], %1;" :: "r"(ring0 + ((k0 + 8u) & 60u)), "r"(t2) : "memory");
+    pw = (end & 3u) == 0u ? 0u : (end < 4u ? t0 : (end < 8u ? t1 : t2));
+    wr += len;
+    buffered += len;
+  };
+
+  for (;;) {
+    if (!active && have) {               // claim the stream
+      lc.reset(s);
+      const uint64_t s0 = P.sym_off[s];
+      cnt = (uint32_t)(P.sym_off[s + 1] - s0);
+      src = static_cast<const uint8_t*>(P.symbols) + s0;
+      encw_start(E, P.slab + (uint64_t)s * P.slab_stride, cap);
+      si = 0; row = 0; curv = 0; wr = 0; rd = 0; buffered = 0; pw = 0; mb = 1; mlen = 0; up = false;
+      cur = SymCode{0, 0, 0}; prevc = cur;
+      nextv = cnt ? src[0] : 0u;
+      active = true;
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+    // ---- refill: one symbol (or one piece of a long symbol) per lane and trip
+    for (;;) {
+      const bool need = active && buffered < 16u && (mb <= mlen || si < cnt);
+      if (!__any_sync(0xffffffffu, need)) break;
+      if (need) {
+        if (mb > mlen) {                 // next symbol
+          const uint32_t prevv = curv;
+          curv = nextv;
+          if (si + 1 < cnt) nextv = src[si + 1];
+          up = has_up_row(cfg, si, row);
+          ++si;
+          if (++row == cfg.rows) row = 0;
+          const uint32_t key = lut_index(cfg, P.lut_dom, curv, prevv, up);
+          uint2 e = make_uint2(0u, 0u);
+          if (key != LUT_ESC) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(lut0 + key * 8u));
+          const uint32_t len = e.y >> 24;
+          if (len) {
+            append(e.x, e.y & 0x00ffffffu, len);
+          } else {                       // not in the table in one piece: closed form, 7 ops per trip
+            prevc = sym_code(prevv, cfg.Nq, cfg.method);
+            cur = sym_code(curv, cfg.Nq, cfg.method);
+            mb = 1;
+            mlen = cur.len;
+          }
+        }
+        if (mb <= mlen) {
+          uint32_t lo = 0, hi = 0, k = 0;
+          for (; k < 7u && mb <= mlen; ++k, ++mb) {
+            const int cx = select_ctx(cfg, mb, cur.np, prevc, up);
+            const uint32_t op = ((cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx) << 1) | sym_bin(cur, mb);
+            if (k < 4u) lo |= op << (8u * k); else hi |= op << (8u * (k - 4u));
+          }
+          append(lo, hi, k);
+        }
+      }
+    }
+    // ---- code: a full block of 16 ops, or the tail of the stream
+    const bool full = active && buffered >= 16u;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (full) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(ring0 + (rd & 48u)) : "memory");
+    const uint32_t cw[4] = {op_codes4(w[0]), op_codes4(w[1]), op_codes4(w[2]), op_codes4(w[3])};
+    if (__all_sync(0xffffffffu, full)) {
+      encw_block16<true>(E, w, cw, ctx, tab, n_ctx);
+    } else if (full) {
+      encw_block16<false>(E, w, cw, ctx, tab, n_ctx);
+    }
+    if (full) { rd += 16u; buffered -= 16u; }
+    if (active && !full) {               // fewer than 16 ops left and no symbol to expand: the stream's tail
+      for (uint32_t k = 0; k < buffered; ++k) {
+        uint32_t op;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(op) : "r"(ring0 + ((rd + k) & 63u)) : "memory");
+        encw_general(E, op, ctx, tab, n_ctx);
+      }
+      const uint32_t len = encw_finish(E);
+      P.lengths[s] = len;
+      if (len > cap && P.overflow) atomicOr(P.overflow, 1u);
+      encw_start(E, nullptr, 0);
+      active = false;
+      buffered = 0;
+      s = gridDim.x * blockDim.x + atomicAdd(next_stream, 1u);
+      have = s < P.n_streams;
+      if (have && order) s = order[s];
+    }
+  }
+}
+
 template <int PROF, int METH>
 __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_symbols_wide(SymParams P, uint32_t* next_stream, const uint32_t* order) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -773,12 +923,53 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_symbols_wide(Sym
 
 // persistent launch: as many warps as the streams need, at most what is resident on the device
 template <class K>
-int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char* name, bool& done, bool want_lut = false) {
+int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char* name, bool& done, bool want_lut = false,
+                    bool ring = false) {
   SymParams P = P_in;
   uint32_t nw, grid;
   size_t smem;
   done = false;
   if (!wide_geometry(P.n_streams, P.n_ctx, nw, grid, smem)) return ISSCABAC_OK;
+  if (ring) {
+    // the ring encoder: 8-byte op strings + one ring per lane behind the context blocks; fewer warps per CTA if needed
+    const LutGeom rg = lut_geom(P.cfg.profile, P.cfg.method, P.cfg.Nq);
+    if (!rg.entries) return ISSCABAC_OK;
+    const size_t lut_b = ((size_t)rg.entries * 8 + 15) & ~(size_t)15;
+    const size_t per_warp = ((size_t)P.n_ctx + 1) * 128 + RING_WARP_BYTES;
+    const size_t lim = smem_limit();
+    if (WIDE_TAB_BYTES + lut_b + per_warp > lim) return ISSCABAC_OK;
+    const uint32_t nw_fit = (uint32_t)((lim - WIDE_TAB_BYTES - lut_b) / per_warp);
+    if (nw > nw_fit) { nw = nw_fit; grid = ((P.n_streams + 31) / 32 + nw - 1) / nw; }
+    smem = WIDE_TAB_BYTES + lut_b + per_warp * nw;
+    int rc = keep_pool_cached();
+    if (rc) return rc;
+    uint4* lut = nullptr;
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&lut), rg.entries * sizeof(uint4), st));
+    k_bin_lut<<<(rg.entries + 127) / 128, 128, 0, st>>>(P.cfg, lut);
+    P.lut = lut; P.lut_entries = rg.entries; P.lut_dom = rg.dom;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(nw * 32), smem));
+    const uint32_t resident = (uint32_t)(per_sm > 0 ? per_sm : 1) * (uint32_t)sm_count();
+    if (grid > resident) grid = resident;
+    uint32_t* counter = nullptr;
+    if ((rc = work_counter(st, &counter))) return rc;
+    uint32_t* order = nullptr;
+    if (P.n_streams > grid * nw * 32) {
+      CK(cudaMallocAsync(reinterpret_cast<void**>(&order), ((size_t)P.n_streams + 2 * ORDER_BUCKETS) * sizeof(uint32_t), st));
+      uint32_t* hist = order + P.n_streams;
+      CK(cudaMemsetAsync(hist, 0, 2 * ORDER_BUCKETS * sizeof(uint32_t), st));
+      const uint32_t blocks = (P.n_streams + 255) / 256;
+      k_order_hist<<<blocks, 256, 0, st>>>(P.sym_off, P.n_streams, hist);
+      k_order_scatter<<<blocks, 256, 0, st>>>(P.sym_off, P.n_streams, hist, hist + ORDER_BUCKETS, order);
+    }
+    kernel<<<grid, nw * 32, smem, st>>>(P, counter, order);
+    cudaError_t e = cudaGetLastError();
+    if (order) cudaFreeAsync(order, st);
+    cudaFreeAsync(lut, st);
+    done = true;
+    return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, name);
+  }
   // op strings by table for the encoder when they fit shared memory behind the context blocks
   const LutGeom geom = lut_geom(P.cfg.profile, P.cfg.method, P.cfg.Nq);
   uint4* lut = nullptr;
@@ -934,8 +1125,23 @@ int cabac_encode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const u
   P.slab = d_slab; P.slab_stride = slab_stride; P.lengths = d_lengths; P.bits_after = d_bits_after_symbol; P.overflow = d_overflow;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d_bits_after_symbol) return launch_sym(k_encode_symbols<true>, P, st, "k_encode_symbols");   // getNumBits() trace
-  bool done;
+  bool done = false;
   constexpr bool kWantLut = true;
+  // the ring encoder (binarizer ahead of the coder) for u8 symbols of profiles with an op-string table;
+  // ISSCABAC_SYM_RING=0 keeps the per-bin state machine (both are tested against the oracle)
+  const char* ring_env = getenv("ISSCABAC_SYM_RING");
+  if (sym_width == 1 && !(ring_env && ring_env[0] == '0')) {
+#define SYM_RING_CASE(PR, ME) \
+  if (cfg->profile == PR && cfg->method == ME) rc = launch_sym_wide(k_encode_symbols_ring<PR, ME>, P, st, "k_encode_symbols_ring", done, false, true); else
+    SYM_RING_CASE(ISSCABAC_PROFILE_ISS, ISSCABAC_BIN_EG0)
+    SYM_RING_CASE(ISSCABAC_PROFILE_FLAT, ISSCABAC_BIN_EG0)
+    SYM_RING_CASE(ISSCABAC_PROFILE_FLAT_EPSUF, ISSCABAC_BIN_EG2)
+    SYM_RING_CASE(ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_TU)
+    SYM_RING_CASE(ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_EG0)
+    rc = launch_sym_wide(k_encode_symbols_ring<-1, -1>, P, st, "k_encode_symbols_ring", done, false, true);
+#undef SYM_RING_CASE
+    if (rc || done) return rc;
+  }
 #define SYM_WIDE_CASE(K, PR, ME) \
   if (cfg->profile == PR && cfg->method == ME) rc = launch_sym_wide(K<PR, ME>, P, st, #K, done, kWantLut); else
   SYM_WIDE_CASE(k_encode_symbols_wide, ISSCABAC_PROFILE_ISS, ISSCABAC_BIN_EG0)

@@ -11,7 +11,14 @@
 namespace cabac {
 
 constexpr int WIDE_MAX_WARPS = 16;
-constexpr uint32_t WIDE_ROW_STRIDE = 32 * sizeof(WRow);   // bytes between consecutive states of one lane
+// Columns of the table: an LDS.128 is served one QUARTER-warp (8 lanes x 16 B = all 32 banks) at a time, so 8 copies of a row
+// already keep 32 lanes with 32 unrelated states conflict-free (ncu: exactly 4 wavefronts per LDS.128 and 0 bank conflicts,
+// profiles/r2_v1_lone_tile_lat_decode_stalls.txt): 16.5 KB instead of the 66 KB of a copy per lane (round 1) -- which is what
+// lets two CTAs of the symbol kernels share an SM, and a quarter of the table fill for small jobs.
+#ifndef WIDE_COLS
+#define WIDE_COLS 8
+#endif
+constexpr uint32_t WIDE_ROW_STRIDE = WIDE_COLS * sizeof(WRow);   // bytes between consecutive states of one column
 constexpr size_t WIDE_TAB_BYTES = (size_t)kNumRows * WIDE_ROW_STRIDE;
 
 struct WideRowTable {
@@ -30,7 +37,7 @@ struct WCtx {
   // it measured slower on B200: encode 590 -> 559, decode 556 -> 541 Gbins/s at C3.)
   __device__ __forceinline__ void store_sel(uint32_t c, uint32_t sel, uint32_t a, uint32_t b) const { p[c * 32] = sel ? a : b; }
 };
-// Table [state][lane] of 16-byte rows in shared memory: lane l always reads its own column, so 32
+// Table [state][column] of 16-byte rows in shared memory: lane l always reads column l % WIDE_COLS, so 32
 // lanes with 32 unrelated states never conflict (each quarter-warp of an LDS.128 covers all 32
 // banks once).  A token is the shared-window address of a row of this lane's column; the next_*
 // fields of the rows hold tokens of the same column.
@@ -53,9 +60,9 @@ __device__ __forceinline__ bool wide_setup(uint32_t n_streams, uint32_t n_ctx_in
                                            uint32_t& n_ctx, uint32_t* vmask = nullptr) {
   WRow* t = reinterpret_cast<WRow*>(smem);
   const uint32_t tab0 = (uint32_t)__cvta_generic_to_shared(smem);
-  for (uint32_t i = threadIdx.x; i < kNumRows * 32; i += blockDim.x) {
-    WRow r = c_wide_rows.r[i >> 5];
-    const uint32_t col = tab0 + (i & 31u) * (uint32_t)sizeof(WRow);
+  for (uint32_t i = threadIdx.x; i < kNumRows * WIDE_COLS; i += blockDim.x) {
+    WRow r = c_wide_rows.r[i / WIDE_COLS];
+    const uint32_t col = tab0 + (i % WIDE_COLS) * (uint32_t)sizeof(WRow);
     r.next_mps = col + r.next_mps * WIDE_ROW_STRIDE;
     r.next_lps = col + r.next_lps * WIDE_ROW_STRIDE;
     t[i] = r;
@@ -68,7 +75,7 @@ __device__ __forceinline__ bool wide_setup(uint32_t n_streams, uint32_t n_ctx_in
   const uint32_t coff = cb_keep32(warp * (n_ctx + 1) * 32 + lane);
   uint32_t* c0 = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + coff;
   const uint8_t* init = ctx_init + (per_stream_init && valid ? (uint64_t)s * n_ctx : 0);
-  tab.base = cb_keep32(tab0 + lane * (uint32_t)sizeof(WRow));
+  tab.base = cb_keep32(tab0 + (lane % WIDE_COLS) * (uint32_t)sizeof(WRow));
   for (uint32_t c = 0; c < n_ctx; ++c) c0[c * 32] = tab.token(init[c] & 127u);
   c0[n_ctx * 32] = tab.token(kEpState);
   ctx.p = c0;

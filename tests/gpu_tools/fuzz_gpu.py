@@ -89,13 +89,16 @@ def fuzz_symbols(rng):
     cfg, ocfg = I.make_cfg(prof, meth, Nq, 3, T, rows), O.make_cfg(prof, meth, Nq, 3, T, rows)
     stride = 16 * 1024
     s_ref, l_ref = O.encode_symbols(ocfg, sym, off, ci, stride, n_threads=8)
-    enc = I.encode_symbols(cfg, sym, off.astype(np.int64), ci, slab_stride=stride)
-    torch.cuda.synchronize()
-    enc.check_overflow()
-    assert (enc.lengths.cpu().numpy().astype(np.uint32) == l_ref).all(), "symbol lengths"
     w = int(l_ref.max()) if n_streams else 0
     live = np.arange(w)[None, :] < l_ref[:, None]
-    assert (enc.slab[:, :w].cpu().numpy()[live] == s_ref[:, :w][live]).all(), "symbol bytes"
+    for ring in ("0", "1"):              # both fused encoders: per-bin state machine / binarizer ahead of the coder through a ring
+        os.environ["ISSCABAC_SYM_RING"] = ring
+        enc = I.encode_symbols(cfg, sym, off.astype(np.int64), ci, slab_stride=stride)
+        torch.cuda.synchronize()
+        os.environ.pop("ISSCABAC_SYM_RING")
+        enc.check_overflow()
+        assert (enc.lengths.cpu().numpy().astype(np.uint32) == l_ref).all(), ("symbol lengths", ring)
+        assert (enc.slab[:, :w].cpu().numpy()[live] == s_ref[:, :w][live]).all(), ("symbol bytes", ring)
     pay = I.compact(enc)
     tdt = {np.uint8: torch.uint8, np.uint16: torch.int16, np.uint32: torch.int32}[dt]
     dec, ok = I.decode_symbols(cfg, pay, off.astype(np.int64), ci, sym_dtype=tdt)

@@ -87,6 +87,18 @@ def test_many_streams_vs_oracle(I, prof, meth, Nq, rows, dtype):
     live = np.arange(w)[None, :] < l_ref[:, None]   # bytes past a stream's length are unspecified
     assert (enc.slab[:, :w].cpu().numpy()[live] == s_ref[:, :w][live]).all()
     assert (bits.cpu().numpy().astype(np.uint32) == bits_ref).all()        # getNumBits() after every symbol
+    # the fused encoders proper (no per-symbol bit trace): the ring formulation (binarizer ahead of the coder through a
+    # per-lane ring of op bytes) and the per-bin state machine, each against the oracle
+    for ring in ("1", "0"):
+        os.environ["ISSCABAC_SYM_RING"] = ring
+        try:
+            encf = I.encode_symbols(cfg, sym, off.astype(np.int64), ci, slab_stride=stride)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("ISSCABAC_SYM_RING")
+        encf.check_overflow()
+        assert (encf.lengths.cpu().numpy().astype(np.uint32) == l_ref).all(), ("fused encoder lengths", ring)
+        assert (encf.slab[:, :w].cpu().numpy()[live] == s_ref[:, :w][live]).all(), ("fused encoder bytes", ring)
     pay = I.compact(enc)
     tdt = {np.uint8: torch.uint8, np.uint16: torch.int16, np.uint32: torch.int32}[dtype]
     if meth >= O.BIN_TR0:   # the reference's decode loops have no case for truncated Rice: refused, not guessed
