@@ -16,6 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/isscabac.h"
 #include "cabac_lane.cuh"
 #include "internal.h"
@@ -921,6 +923,197 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_decode_symbols_wide(Sym
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fused decoder, second formulation: the binarization is a prefix code, so "finish detector + context selection +
+// debinarizer" (cabacDecodeSymbolFinished.m:10-32, cabacContextSelection.m:24-67, cabacDebinarizer.m:28-57) is a walk down
+// the CODE TREE: every internal node names the context of its bin (or bypass) and its two children, a leaf is a symbol value.
+// The tree is built per call on the host from the same closed-form helpers as everything else (sym_code / select_ctx /
+// sym_bin), once per neighbour variant (ISS: the up neighbour's value; DEMO: the first bin of the previous symbol), and sits
+// in shared memory.  A decode step is then: node (LDS.64) -> decw_op -> child by the bin -> leaf? store the symbol and
+// restart at the root of the next symbol's variant.  No per-profile code in the kernel, ~50 instead of 112 instructions
+// per warp-step.  A bin string that is no codeword of the alphabet (possible only in a corrupt stream) ends in an escape
+// leaf: the stream is flagged (finish_ok = 0) and decoding goes on at the root.
+// ---------------------------------------------------------------------------
+struct TreeNode {            // 8 bytes
+  uint16_t child[2];         // by bin: node index, or kLeaf | next variant << 8 | value, or kEscape
+  uint16_t code;             // op code of the node's bin: context index, ISSCABAC_OP8_EP for a bypass bin
+  uint16_t pad;
+};
+constexpr uint16_t kLeaf = 0x8000, kEscape = 0xffff;     // bit 14 is set in kEscape only: leaves carry at most 6 variant bits
+constexpr uint32_t TREE_MAX_NODES = 4096;
+#ifndef TREE_MIN_BLOCKS
+#define TREE_MIN_BLOCKS 2
+#endif
+constexpr uint32_t TREE_STAGE_STRIDE = 48;     // 32-byte output stage per lane + 16 B (bank spread, keeps 16-byte alignment)
+
+struct TreeInfo { uint32_t n_nodes, var_stride; };   // var_stride: nodes per variant (variant v's root = node v * var_stride)
+
+// host: the code trees of a configuration; false when the configuration is not covered (large alphabets, FL32, TR)
+static bool build_code_tree(const isscabac_symcfg& c, std::vector<TreeNode>& nodes, TreeInfo& info) {
+  const SymCfg cfg = SymCfg{c.profile, c.method, c.Nq, c.Nlbp, c.types, c.rows};
+  if (!(cfg.method == BIN_TU || (cfg.method >= BIN_EG0 && cfg.method <= BIN_EG2))) return false;
+  const uint32_t nq = cfg.Nq;
+  if (nq < 2 || nq > 256 || (cfg.profile == PROFILE_ISS && nq > 31)) return false;
+  const uint32_t n_var = cfg.profile == PROFILE_ISS ? nq + 1 : (cfg.profile == PROFILE_DEMO ? 3u : 1u);
+  std::vector<std::vector<TreeNode>> trees(n_var);
+  uint32_t stride = 0;
+  for (uint32_t var = 0; var < n_var; ++var) {
+    bool has_up = false;
+    SymCode uc = {0, 0, 0};
+    if (cfg.profile == PROFILE_ISS) { has_up = var != 0; if (has_up) uc = sym_code(var - 1, nq, cfg.method); }
+    else if (cfg.profile == PROFILE_DEMO) { has_up = var != 0; uc = SymCode{1u, var == 1 ? 2u : 1u, 0u}; }   // first bin 1 / 0, as k_bin_lut
+    std::vector<TreeNode>& t = trees[var];
+    t.push_back(TreeNode{{kEscape, kEscape}, 0, 0});
+    std::vector<bool> set(1, false);
+    for (uint32_t v = 0; v < nq; ++v) {
+      const SymCode code = sym_code(v, nq, cfg.method);
+      if (code.len == 0 || code.len > 64) return false;
+      uint32_t at = 0;
+      for (uint32_t b = 1; b <= code.len; ++b) {
+        const int cx = select_ctx(cfg, b, code.np, uc, has_up);
+        const uint16_t opc = (uint16_t)(cx < 0 ? ISSCABAC_OP8_EP : cx);
+        if (set[at] && t[at].code != opc) return false;      // a prefix shared by two symbols must name one context
+        t[at].code = opc;
+        set[at] = true;
+        const uint32_t bin = sym_bin(code, b);
+        if (b == code.len) {
+          // the variant of the NEXT symbol when this one is its neighbour
+          const uint32_t nv = cfg.profile == PROFILE_ISS ? v + 1u : (cfg.profile == PROFILE_DEMO ? (code.np > 1u ? 1u : 2u) : 0u);
+          t[at].child[bin] = (uint16_t)(kLeaf | (nv << 8) | v);
+        } else {
+          if (t[at].child[bin] == kEscape) {
+            t[at].child[bin] = (uint16_t)t.size();
+            t.push_back(TreeNode{{kEscape, kEscape}, 0, 0});
+            set.push_back(false);
+          } else if (t[at].child[bin] & kLeaf) {
+            return false;                                     // not a prefix code
+          }
+          at = t[at].child[bin];
+        }
+      }
+    }
+    if (t.size() > stride) stride = (uint32_t)t.size();
+  }
+  if ((uint64_t)stride * n_var > TREE_MAX_NODES) return false;
+  nodes.assign((size_t)stride * n_var, TreeNode{{kEscape, kEscape}, 0, 0});
+  for (uint32_t var = 0; var < n_var; ++var)
+    for (size_t k = 0; k < trees[var].size(); ++k) {
+      TreeNode nd = trees[var][k];
+      for (int b = 0; b < 2; ++b)
+        if (!(nd.child[b] & kLeaf)) nd.child[b] = (uint16_t)(nd.child[b] + var * stride);   // variant-local -> global node index
+      nodes[(size_t)var * stride + k] = nd;
+    }
+  info.n_nodes = stride * n_var;
+  info.var_stride = stride;
+  return true;
+}
+
+// MODE: how the next symbol's variant follows from the one just decoded -- 0: one variant (FLAT profiles), 1: always the
+// decoded symbol's (DEMO), 2: the decoded symbol's unless the next symbol starts a column (ISS)
+template <int MODE>
+__global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode_symbols_tree(SymParams P, uint32_t* next_stream, const uint32_t* order,
+                                                                                               const uint2* tree, TreeInfo ti) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint32_t s, n_ctx;
+  WCtx ctx;
+  WTab tab;
+  wide_setup(P.n_streams, P.n_ctx, P.ctx_init, 0, smem, s, ctx, tab, n_ctx);
+  const LaneCtx lc{ctx, tab, n_ctx, P.ctx_init, P.per_stream_init};
+  uint8_t* tp = smem + WIDE_TAB_BYTES + (size_t)(blockDim.x >> 5) * (P.n_ctx + 1) * 32 * 4;
+  for (uint32_t e = threadIdx.x; e < ti.n_nodes; e += blockDim.x) reinterpret_cast<uint2*>(tp)[e] = __ldg(tree + e);
+  __syncthreads();
+  const uint32_t tree0 = (uint32_t)__cvta_generic_to_shared(tp);
+  const uint32_t var_bytes = ti.var_stride * 8u, rows = P.cfg.rows;
+  // Decoded symbols leave through a 32-byte stage per lane: one byte store to shared memory per symbol, one 16-byte store
+  // to global memory per 16 symbols (a byte store per symbol and lane is a 32-byte sector write each: at C4 that was
+  // the bound of the launch, not the instruction count).  Stage position = low address bits of the symbol's place in
+  // the output, so the 16-byte pieces are the aligned pieces of the output array.
+  const uint32_t stage0 = tree0 + ((ti.n_nodes * 8u + 15u) & ~15u) + ((threadIdx.x >> 5) * 32u + (threadIdx.x & 31u)) * TREE_STAGE_STRIDE;
+  DecWide D;
+  decw_start(D, P.bytes, 0);
+  uint8_t* dst = nullptr;       // output position of symbol 0 of the stream
+  uint32_t a0 = 0;              // low address bits of dst
+  uint32_t fl = 0;              // symbols [0, fl) of the stream have been written to global memory
+  uint32_t i = 0, cnt = 0, row = 0, node = tree0, seen = 0;   // seen: OR of every child taken; bit 14 = an escape leaf was hit
+  bool active = false, have = s < P.n_streams;
+  if (have && order) s = order[s];
+  // write symbols [fl, upto) out of the stage: the aligned 16-byte piece in one store, anything else byte by byte
+  auto flush = [&](uint32_t upto) {
+    while (fl < upto) {
+      const uint32_t a = a0 + fl;
+      if ((a & 15u) == 0u && fl + 16u <= upto) {
+        uint4 q;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(stage0 + (a & 16u)) : "memory");
+        *reinterpret_cast<uint4*>(dst + fl) = q;
+        fl += 16u;
+      } else {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stage0 + (a & 31u)) : "memory");
+        dst[fl] = (uint8_t)v;
+        fl += 1u;
+      }
+    }
+  };
+  for (;;) {
+    if (!active && have) {
+      lc.reset(s);
+      const uint64_t s0 = P.sym_off[s];
+      cnt = (uint32_t)(P.sym_off[s + 1] - s0);
+      dst = static_cast<uint8_t*>(P.out_symbols) + s0;
+      a0 = (uint32_t)reinterpret_cast<uintptr_t>(dst);
+      const uint64_t b0 = P.byte_off[s], b1 = P.byte_off[s + 1];
+      decw_start(D, P.bytes + b0, (uint32_t)(b1 - b0));
+      i = 0; fl = 0; row = 0; node = tree0; seen = 0;
+      active = true;
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (active && i < cnt) {
+        uint2 nd;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nd.x), "=r"(nd.y) : "r"(node));
+        const uint32_t bin = decw_op<0>(D, nd.y & 0xffffu, ctx, tab, n_ctx);
+        const uint32_t child = bin ? nd.x >> 16 : nd.x & 0xffffu;
+        seen |= child;
+        node = tree0 + child * 8u;
+        if (child & kLeaf) {                       // the symbol is complete
+          asm volatile("st.shared.u8 [%0], %1;" :: "r"(stage0 + ((a0 + i) & 31u)), "r"(child) : "memory");
+          ++i;
+          if (MODE == 0) {
+            node = tree0;
+          } else {
+            // the next symbol's variant: its neighbour is this symbol, unless it starts a column (ISS, cabacEncode.m:52);
+            // an escape leaf (corrupt stream) carries variant bits 0x3f: clamp to the root
+            uint32_t nv = (child >> 8) & 0x3fu;
+            if (MODE == 2) {
+              if (++row == rows) row = 0;
+              if (rows && row == 0u) nv = 0u;
+            }
+            node = tree0 + (child == kEscape ? 0u : nv * var_bytes);
+          }
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, D.f >= kLazyDec)) decw_refill(D);
+    // at most 4 symbols per group: the stage (two 16-byte pieces) never holds more than one complete aligned piece + 4
+    {
+      const bool crossed = active && (((a0 + i) ^ (a0 + fl)) & ~15u) != 0u;
+      if (__any_sync(0xffffffffu, crossed)) {
+        if (crossed) flush(i - ((a0 + i) & 15u));      // up to the last 16-byte boundary reached
+      }
+    }
+    if (active && i >= cnt) {
+      flush(cnt);
+      if (P.finish_ok) P.finish_ok[s] = (uint8_t)(decw_finish(D) & (((seen >> 14) & 1u) ^ 1u));
+      decw_start(D, P.bytes, 0);
+      active = false;
+      s = gridDim.x * blockDim.x + atomicAdd(next_stream, 1u);
+      have = s < P.n_streams;
+      if (have && order) s = order[s];
+    }
+  }
+}
+
 // persistent launch: as many warps as the streams need, at most what is resident on the device
 template <class K>
 int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char* name, bool& done, bool want_lut = false,
@@ -1007,6 +1200,52 @@ int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char
   if (lut) cudaFreeAsync(lut, st);
   done = true;
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, name);
+}
+
+int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
+  done = false;
+  std::vector<TreeNode> nodes;
+  TreeInfo ti;
+  if (!build_code_tree(P.cfg, nodes, ti)) return ISSCABAC_OK;
+  uint32_t nw, grid;
+  size_t smem;
+  if (!wide_geometry(P.n_streams, P.n_ctx, nw, grid, smem)) return ISSCABAC_OK;
+  const size_t tree_b = ((size_t)ti.n_nodes * sizeof(TreeNode) + 15) & ~(size_t)15;
+  const size_t lim = smem_limit();
+  const size_t per_warp = ((size_t)P.n_ctx + 1) * 128 + 32 * TREE_STAGE_STRIDE;
+  if (WIDE_TAB_BYTES + tree_b + per_warp > lim) return ISSCABAC_OK;
+  const uint32_t nw_fit = (uint32_t)((lim - WIDE_TAB_BYTES - tree_b) / per_warp);
+  if (nw > nw_fit) { nw = nw_fit; grid = ((P.n_streams + 31) / 32 + nw - 1) / nw; }
+  smem = WIDE_TAB_BYTES + tree_b + per_warp * nw;
+  int rc = keep_pool_cached();
+  if (rc) return rc;
+  uint2* d_tree = nullptr;
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&d_tree), tree_b, st));
+  CK(cudaMemcpyAsync(d_tree, nodes.data(), (size_t)ti.n_nodes * sizeof(TreeNode), cudaMemcpyHostToDevice, st));
+  auto kernel = P.cfg.profile == ISSCABAC_PROFILE_ISS ? k_decode_symbols_tree<2>
+              : P.cfg.profile == ISSCABAC_PROFILE_DEMO ? k_decode_symbols_tree<1> : k_decode_symbols_tree<0>;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(nw * 32), smem));
+  const uint32_t resident = (uint32_t)(per_sm > 0 ? per_sm : 1) * (uint32_t)sm_count();
+  if (grid > resident) grid = resident;
+  uint32_t* counter = nullptr;
+  if ((rc = work_counter(st, &counter))) return rc;
+  uint32_t* order = nullptr;
+  if (P.n_streams > grid * nw * 32) {
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&order), ((size_t)P.n_streams + 2 * ORDER_BUCKETS) * sizeof(uint32_t), st));
+    uint32_t* hist = order + P.n_streams;
+    CK(cudaMemsetAsync(hist, 0, 2 * ORDER_BUCKETS * sizeof(uint32_t), st));
+    const uint32_t blocks = (P.n_streams + 255) / 256;
+    k_order_hist<<<blocks, 256, 0, st>>>(P.sym_off, P.n_streams, hist);
+    k_order_scatter<<<blocks, 256, 0, st>>>(P.sym_off, P.n_streams, hist, hist + ORDER_BUCKETS, order);
+  }
+  kernel<<<grid, nw * 32, smem, st>>>(P, counter, order, d_tree, ti);
+  cudaError_t e = cudaGetLastError();
+  if (order) cudaFreeAsync(order, st);
+  cudaFreeAsync(d_tree, st);
+  done = true;
+  return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_decode_symbols_tree");
 }
 
 int check_cfg(const isscabac_symcfg* cfg, uint32_t n_ctx, int sym_width, bool need_ctx, bool decode = false) {
@@ -1167,9 +1406,16 @@ int cabac_decode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const u
   P.cfg = *cfg; P.n_streams = n_streams; P.n_ctx = n_ctx; P.per_stream_init = per_stream_init; P.sym_width = sym_width;
   P.sym_off = d_sym_off; P.ctx_init = d_ctx_init; P.byte_off = d_byte_off; P.bytes = d_bytes;
   P.out_symbols = d_symbols; P.finish_ok = d_finish_ok;
-  bool done;
+  bool done = false;
   constexpr bool kWantLut = false;   // the decoder's contexts depend on the bins it decodes
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the tree decoder (code tree in shared memory, no per-profile code) for u8 symbols of small alphabets;
+  // ISSCABAC_SYM_TREE=0 keeps the closed-form state machine (both are tested against the oracle)
+  const char* tree_env = getenv("ISSCABAC_SYM_TREE");
+  if (sym_width == 1 && !(tree_env && tree_env[0] == '0')) {
+    rc = launch_sym_tree(P, st, done);
+    if (rc || done) return rc;
+  }
   SYM_WIDE_CASE(k_decode_symbols_wide, ISSCABAC_PROFILE_ISS, ISSCABAC_BIN_EG0)
   SYM_WIDE_CASE(k_decode_symbols_wide, ISSCABAC_PROFILE_FLAT, ISSCABAC_BIN_EG0)
   SYM_WIDE_CASE(k_decode_symbols_wide, ISSCABAC_PROFILE_FLAT_EPSUF, ISSCABAC_BIN_EG2)

@@ -101,8 +101,12 @@ def fuzz_symbols(rng):
         assert (enc.slab[:, :w].cpu().numpy()[live] == s_ref[:, :w][live]).all(), ("symbol bytes", ring)
     pay = I.compact(enc)
     tdt = {np.uint8: torch.uint8, np.uint16: torch.int16, np.uint32: torch.int32}[dt]
-    dec, ok = I.decode_symbols(cfg, pay, off.astype(np.int64), ci, sym_dtype=tdt)
-    assert bool(ok.all().item()) and (dec.cpu().numpy().view(dt)[:n] == sym).all(), "symbol decode"
+    for tree in ("0", "1"):              # both fused decoders: closed-form state machine / code-tree walk
+        os.environ["ISSCABAC_SYM_TREE"] = tree
+        dec, ok = I.decode_symbols(cfg, pay, off.astype(np.int64), ci, sym_dtype=tdt)
+        torch.cuda.synchronize()
+        os.environ.pop("ISSCABAC_SYM_TREE")
+        assert bool(ok.all().item()) and (dec.cpu().numpy().view(dt)[:n] == sym).all(), ("symbol decode", tree)
     if n:
         ops, op_off = I.binarize_symbols(cfg, sym, off.astype(np.int64))
         want = np.concatenate([O.symbols_to_ops(ocfg, sym[int(off[s]):int(off[s + 1])]) for s in range(n_streams)])

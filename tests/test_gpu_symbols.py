@@ -105,9 +105,16 @@ def test_many_streams_vs_oracle(I, prof, meth, Nq, rows, dtype):
         with pytest.raises(I.CabacError):
             I.decode_symbols(cfg, pay, off.astype(np.int64), ci, sym_dtype=tdt)
     else:
-        dec, ok = I.decode_symbols(cfg, pay, off.astype(np.int64), ci, sym_dtype=tdt)
-        assert bool(ok.all().item())
-        assert (dec.cpu().numpy().view(dtype) == sym).all()
+        # both fused decoders: the code-tree walk (u8 symbols of small alphabets) and the closed-form state machine
+        for tree in ("1", "0"):
+            os.environ["ISSCABAC_SYM_TREE"] = tree
+            try:
+                dec, ok = I.decode_symbols(cfg, pay, off.astype(np.int64), ci, sym_dtype=tdt)
+                torch.cuda.synchronize()
+            finally:
+                os.environ.pop("ISSCABAC_SYM_TREE")
+            assert bool(ok.all().item()), ("finish flags", tree)
+            assert (dec.cpu().numpy().view(dtype) == sym).all(), ("decoded symbols", tree)
     # symbol-parallel binarizer against the oracle's op stream
     ops, op_off = I.binarize_symbols(cfg, sym, off.astype(np.int64))
     want = np.concatenate([O.symbols_to_ops(ocfg, sym[int(off[s]):int(off[s + 1])]) for s in range(n_streams)])
