@@ -781,9 +781,13 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_ring(Sym
     }
     if (!__any_sync(0xffffffffu, active)) break;
     // ---- refill: one symbol (or one piece of a long symbol) per lane and trip
+    // A trip is forced by the lanes that are short of a block (must); every lane with room works ahead in it (need), so the
+    // number of trips per block follows the average symbols per block, not the maximum over the 32 lanes.
     for (;;) {
-      const bool need = active && buffered < 16u && (mb <= mlen || si < cnt);
-      if (!__any_sync(0xffffffffu, need)) break;
+      const bool more = active && (mb <= mlen || si < cnt);
+      const bool must = more && buffered < 16u;
+      const bool need = more && buffered < 32u;
+      if (!__any_sync(0xffffffffu, must)) break;
       if (need) {
         if (mb > mlen) {                 // next symbol
           const uint32_t prevv = curv;
