@@ -255,6 +255,51 @@ def int_peak_lanes():
         return 64.0, 128.0, "FALLBACK (profiles/int_peak.json missing): 64 ALU lanes, 128 issue lanes per clock and SM"
 
 
+def bind_to_gpu_numa(local_index):
+    """Run this process (and so its first-touch / pinned allocations) on the CPUs of the NUMA node the GPU hangs off
+    (sysfs: the PCI device's numa_node -> that node's cpulist).  -> a description for the result line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        if node < 0 or len(nodes) < 2:
+            return f"single NUMA node ({len(nodes)} node(s), GPU reports node {node}): nothing to bind"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return f"GPU on NUMA node {node}, none of its CPUs is available to this process"
+        os.sched_setaffinity(0, allowed)
+        return f"bound to NUMA node {node} of GPU {bdf} ({len(allowed)} CPUs) before the pinned buffers were allocated"
+    except Exception as e:   # best effort: a missing sysfs entry must not fail the bench
+        return f"not bound ({type(e).__name__})"
+
+
+def pcie_bandwidth(torch, dev, nbytes=1 << 30):
+    """Host <-> device copy bandwidth of this rank, pinned memory, measured in the run (the e2e numbers are read against it)."""
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    res = {}
+    for name, (dst, src) in (("h2d", (d, h)), ("d2h", (h, d))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = 3 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    del h, d
+    return res
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -782,6 +827,8 @@ def run_b200(a):
     # ---- end to end through the host-buffer C ABI (pinned host arrays) ------------------
     e2e = e2e_u8 = None
     if not a.no_e2e:
+        numa = bind_to_gpu_numa(local)
+        pcie = pcie_bandwidth(torch, dev)
         h_ops = torch.empty(total_bins, dtype=torch.uint8, pin_memory=True)
         h_ops.copy_(ops)
         h_off = np.arange(S + 1, dtype=np.uint64) * np.uint64(B)
@@ -828,8 +875,13 @@ def run_b200(a):
         assert (np_bins[:1 << 20] == (np_ops[:1 << 20] & 1)).all()
         e2e = e2e_run(True)
         assert (np.unpackbits(np_bits[:1 << 17], bitorder="little") == (np_ops[:1 << 20] & 1)).all()
-        e2e["note"] = ("host buffers in, host buffers out, every copy inside the timed calls; PCIe-bound (see gbytes_per_s_over_pcie; "
-                       "the box moves ~55 GB/s one way, ~47 GB/s each way when both directions run)")
+        for e in (e2e, e2e_u8):
+            # the roof of the call pair: its host-to-device bytes at the measured H2D bandwidth (the larger direction)
+            e["pcie_gbs_measured"] = pcie
+            e["frac_of_pcie"] = (e["h2d_bytes_per_step"] / (e["ms_per_step"] * 1e-3) / 1e9) / pcie["h2d"]
+        e2e["numa"] = numa
+        e2e["note"] = ("host buffers in, host buffers out, every copy inside the timed calls; PCIe-bound: frac_of_pcie = achieved "
+                       "host-to-device GB/s over the H2D bandwidth measured in this run (at N > 1 the ranks share the host's PCIe / DRAM)")
         del h_bits
         del h_ops, h_bins, h_pay
 

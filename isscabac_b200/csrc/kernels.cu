@@ -435,14 +435,19 @@ __global__ void __launch_bounds__(2 * SPLIT_MAX_PAIRS * 32) k_encode_ops_split(C
   WTab tab;
   tab.base = cb_keep32(tab0 + (lane % WIDE_COLS) * (uint32_t)sizeof(WRow));
   WCtx ctx;
+#if WIDE_CTX_ROWS
+  ctx.base = cb_keep32(tab0 + (uint32_t)WIDE_TAB_BYTES + (pair * (n_ctx + 1) * 32 + lane) * WIDE_SLOT_BYTES);
+  __syncthreads();
+#else
   ctx.p = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + cb_keep32(pair * (n_ctx + 1) * 32 + lane);
+#endif
   if (producer) {
     const uint8_t* init = P.ctx_init + (P.per_stream_init && valid ? (uint64_t)s * n_ctx : 0);
-    for (uint32_t c = 0; c < n_ctx; ++c) ctx.p[c * 32] = tab.token(init[c] & 127u);
-    ctx.p[n_ctx * 32] = tab.token(kEpState);
+    for (uint32_t c = 0; c < n_ctx; ++c) ctx.store(c, tab.token(init[c] & 127u));
+    ctx.store(n_ctx, tab.token(kEpState));
   }
   __syncthreads();
-  uint8_t* ring = smem + WIDE_TAB_BYTES + (size_t)np * (n_ctx + 1) * 128 + (size_t)pair * SPLIT_RING;
+  uint8_t* ring = smem + WIDE_TAB_BYTES + (size_t)np * (n_ctx + 1) * WIDE_CTX_STRIDE + (size_t)pair * SPLIT_RING;
   const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16u;   // this lane's lps4 quad of group 0, stage 0
   const uint32_t flag_s = (uint32_t)__cvta_generic_to_shared(ring) + 512u + lane * 4u;
   const uint32_t bar_id = pair + 1;
@@ -594,7 +599,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, WIDE_DEC_MINBLOCKS) k_dec
 #if CABAC_DEC_TMA
   {   // this lane's ring + mbarriers behind the context blocks (see run_codec for the size)
     const uint32_t nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)WIDE_TAB_BYTES + nwarps * (n_ctx + 1) * 128u;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)WIDE_TAB_BYTES + nwarps * (n_ctx + 1) * WIDE_CTX_STRIDE;
     D.ring = base + (warp * 32u + lane) * kTmaLaneStride;
     D.mbar = base + nwarps * 32u * kTmaLaneStride + (warp * 32u + lane) * 16u;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(D.mbar) : "memory");
@@ -957,7 +962,7 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   if (ENC && split_on && op_width == 1 && P.n_ctx <= 125) {
     const uint32_t sms = (uint32_t)sm_count();
     const uint32_t tiles = split_tiles;
-    const size_t per_pair = ((size_t)P.n_ctx + 1) * 128 + SPLIT_RING;
+    const size_t per_pair = ((size_t)P.n_ctx + 1) * WIDE_CTX_STRIDE + SPLIT_RING;
     uint32_t np_max = (uint32_t)((lim - WIDE_TAB_BYTES) / per_pair);
     if (np_max > SPLIT_MAX_PAIRS) np_max = SPLIT_MAX_PAIRS;
     if (np_max >= 1) {

@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_wide(Sym
   const bool lut_on = kLutProfile && (cfg.profile == PROFILE_ISS || cfg.profile == PROFILE_DEMO) && P.lut != nullptr;
   uint32_t lut0 = 0;
   if (lut_on) {
-    uint8_t* lp = smem + WIDE_TAB_BYTES + (size_t)(blockDim.x >> 5) * (P.n_ctx + 1) * 32 * 4;
+    uint8_t* lp = smem + WIDE_TAB_BYTES + (size_t)(blockDim.x >> 5) * (P.n_ctx + 1) * WIDE_CTX_STRIDE;
     for (uint32_t e = threadIdx.x; e < P.lut_entries; e += blockDim.x) reinterpret_cast<uint4*>(lp)[e] = __ldg(P.lut + e);
     lut0 = (uint32_t)__cvta_generic_to_shared(lp);
     __syncthreads();
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_ring(Sym
   const uint32_t cap = (uint32_t)(P.slab_stride > 0xfffffffcull ? 0xfffffffcull : P.slab_stride);
   const uint32_t nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // shared memory behind the context blocks: [entries] 8-byte op strings, then the rings
-  uint8_t* lp = smem + WIDE_TAB_BYTES + (size_t)nwarps * (P.n_ctx + 1) * 32 * 4;
+  uint8_t* lp = smem + WIDE_TAB_BYTES + (size_t)nwarps * (P.n_ctx + 1) * WIDE_CTX_STRIDE;
   uint2* lut8 = reinterpret_cast<uint2*>(lp);
   for (uint32_t e = threadIdx.x; e < P.lut_entries; e += blockDim.x) {
     const uint4 q = __ldg(P.lut + e);
@@ -1023,7 +1023,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
   WTab tab;
   wide_setup(P.n_streams, P.n_ctx, P.ctx_init, 0, smem, s, ctx, tab, n_ctx);
   const LaneCtx lc{ctx, tab, n_ctx, P.ctx_init, P.per_stream_init};
-  uint8_t* tp = smem + WIDE_TAB_BYTES + (size_t)(blockDim.x >> 5) * (P.n_ctx + 1) * 32 * 4;
+  uint8_t* tp = smem + WIDE_TAB_BYTES + (size_t)(blockDim.x >> 5) * (P.n_ctx + 1) * WIDE_CTX_STRIDE;
   for (uint32_t e = threadIdx.x; e < ti.n_nodes; e += blockDim.x) reinterpret_cast<uint2*>(tp)[e] = __ldg(tree + e);
   __syncthreads();
   const uint32_t tree0 = (uint32_t)__cvta_generic_to_shared(tp);
@@ -1132,7 +1132,7 @@ int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char
     const LutGeom rg = lut_geom(P.cfg.profile, P.cfg.method, P.cfg.Nq);
     if (!rg.entries) return ISSCABAC_OK;
     const size_t lut_b = ((size_t)rg.entries * 8 + 15) & ~(size_t)15;
-    const size_t per_warp = ((size_t)P.n_ctx + 1) * 128 + RING_WARP_BYTES;
+    const size_t per_warp = ((size_t)P.n_ctx + 1) * WIDE_CTX_STRIDE + RING_WARP_BYTES;
     const size_t lim = smem_limit();
     if (WIDE_TAB_BYTES + lut_b + per_warp > lim) return ISSCABAC_OK;
     const uint32_t nw_fit = (uint32_t)((lim - WIDE_TAB_BYTES - lut_b) / per_warp);
@@ -1216,7 +1216,7 @@ int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
   if (!wide_geometry(P.n_streams, P.n_ctx, nw, grid, smem)) return ISSCABAC_OK;
   const size_t tree_b = ((size_t)ti.n_nodes * sizeof(TreeNode) + 15) & ~(size_t)15;
   const size_t lim = smem_limit();
-  const size_t per_warp = ((size_t)P.n_ctx + 1) * 128 + 32 * TREE_STAGE_STRIDE;
+  const size_t per_warp = ((size_t)P.n_ctx + 1) * WIDE_CTX_STRIDE + 32 * TREE_STAGE_STRIDE;
   if (WIDE_TAB_BYTES + tree_b + per_warp > lim) return ISSCABAC_OK;
   const uint32_t nw_fit = (uint32_t)((lim - WIDE_TAB_BYTES - tree_b) / per_warp);
   if (nw > nw_fit) { nw = nw_fit; grid = ((P.n_streams + 31) / 32 + nw - 1) / nw; }

@@ -29,6 +29,38 @@ struct WideRowTable {
 };
 static __constant__ WideRowTable c_wide_rows = WideRowTable();
 
+// What a context slot holds.  WIDE_CTX_ROWS = 0: a TOKEN (4 bytes) for its state's row -- per bin LDS token -> LDS.128 row,
+// update = one word store.  WIDE_CTX_ROWS = 1 (compile-time experiment, profiles/r2_ctx_rows_experiment.txt): the ROW itself
+// (16 bytes) -- per bin ONE LDS.128 on the dependent chain, update = LDS.128 of the successor row + STS.128 (off the chain).
+#ifndef WIDE_CTX_ROWS
+#define WIDE_CTX_ROWS 0
+#endif
+constexpr uint32_t WIDE_SLOT_BYTES = WIDE_CTX_ROWS ? 16 : 4;                 // per (context, lane)
+constexpr uint32_t WIDE_CTX_STRIDE = 32 * WIDE_SLOT_BYTES;                   // bytes between consecutive contexts of one lane
+
+#if WIDE_CTX_ROWS
+struct WCtx {
+  uint32_t base;  // shared-window address of this lane's slot 0
+  // "loading" a slot yields what WTab::row() turns into the row: here the slot's address
+  __device__ __forceinline__ uint32_t load(uint32_t c) const { return base + c * WIDE_CTX_STRIDE; }
+  __device__ __forceinline__ void store(uint32_t c, uint32_t tok) const {
+    uint32_t a, b, d, e;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(d), "=r"(e) : "r"(tok) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(base + c * WIDE_CTX_STRIDE), "r"(a), "r"(b), "r"(d), "r"(e) : "memory");
+  }
+  __device__ __forceinline__ void store_sel(uint32_t c, uint32_t sel, uint32_t a, uint32_t b) const { store(c, sel ? a : b); }
+};
+struct WTab {
+  uint32_t base;  // shared-window address of row 0 of this lane's column
+  __device__ __forceinline__ uint32_t token(uint32_t st) const { return base + st * WIDE_ROW_STRIDE; }
+  __device__ __forceinline__ WRow row(uint32_t addr) const {     // addr: a slot (mutable) -- ordered against the slot stores
+    WRow r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.lps4), "=r"(r.next_mps), "=r"(r.next_lps), "=r"(r.mps4) : "r"(addr) : "memory");
+    return r;
+  }
+};
+#else
 struct WCtx {
   uint32_t* p;  // this lane's column of this warp's context block
   __device__ __forceinline__ uint32_t load(uint32_t c) const { return p[c * 32]; }
@@ -51,6 +83,7 @@ struct WTab {
     return r;
   }
 };
+#endif
 
 // Fills the table, initialises this warp's context block (slot n_ctx = bypass slot); returns
 // false for lanes without a stream.  The per-lane offsets are made opaque so that they stay in
@@ -72,13 +105,17 @@ __device__ __forceinline__ bool wide_setup(uint32_t n_streams, uint32_t n_ctx_in
   n_ctx = cb_keep32(n_ctx_in);
   s = (blockIdx.x * nw + warp) * 32 + lane;
   const bool valid = s < n_streams;
-  const uint32_t coff = cb_keep32(warp * (n_ctx + 1) * 32 + lane);
-  uint32_t* c0 = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + coff;
   const uint8_t* init = ctx_init + (per_stream_init && valid ? (uint64_t)s * n_ctx : 0);
   tab.base = cb_keep32(tab0 + (lane % WIDE_COLS) * (uint32_t)sizeof(WRow));
-  for (uint32_t c = 0; c < n_ctx; ++c) c0[c * 32] = tab.token(init[c] & 127u);
-  c0[n_ctx * 32] = tab.token(kEpState);
-  ctx.p = c0;
+#if WIDE_CTX_ROWS
+  ctx.base = cb_keep32(tab0 + (uint32_t)WIDE_TAB_BYTES + (warp * (n_ctx + 1) * 32 + lane) * WIDE_SLOT_BYTES);
+  __syncthreads();                       // the slots are filled with rows read from the table
+#else
+  const uint32_t coff = cb_keep32(warp * (n_ctx + 1) * 32 + lane);
+  ctx.p = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + coff;
+#endif
+  for (uint32_t c = 0; c < n_ctx; ++c) ctx.store(c, tab.token(init[c] & 127u));
+  ctx.store(n_ctx, tab.token(kEpState));
   __syncthreads();
   if (vmask) *vmask = __ballot_sync(0xffffffffu, valid);   // the lanes of this warp that hold a stream
   return valid;
@@ -89,7 +126,7 @@ __device__ __forceinline__ bool wide_setup(uint32_t n_streams, uint32_t n_ctx_in
 // each of 147 SMs).  Returns false when one warp's context block does not fit shared memory.
 inline bool wide_geometry(uint32_t n_streams, uint32_t n_ctx, uint32_t& nw, uint32_t& grid, size_t& smem) {
   const size_t lim = isscabac_internal::smem_limit();
-  const size_t warp_ctx = ((size_t)n_ctx + 1) * 32 * 4;
+  const size_t warp_ctx = ((size_t)n_ctx + 1) * WIDE_CTX_STRIDE;
   if (!lim || n_ctx > 125 || WIDE_TAB_BYTES + warp_ctx > lim) return false;
   const uint32_t sms = (uint32_t)isscabac_internal::sm_count();
   const uint32_t tiles = (n_streams + 31) / 32;
