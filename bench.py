@@ -650,6 +650,41 @@ def cfg_c4(env):
     if env.rank == 0 and env.world == 1 and not a.no_cpu:
         out["cpu_baseline"] = _cpu_symbols(env, cfg_args, sym, off.cpu().numpy(), _sample_ids(n, 2048), np.full(8, 1, np.uint8), enc, "c4")
     mg.close_symmetric()
+    if not a.no_e2e:
+        # end to end through the host-buffer C ABI at symbol level: pinned symbols in -> payload + offset table out ->
+        # symbols back (cabac_encode_symbols_host / cabac_decode_symbols_host, stream groups pipelined over 4 CUDA streams)
+        h_sym = torch.empty(n * per, dtype=torch.uint8, pin_memory=True)
+        h_sym.copy_(sym)
+        h_pay = torch.empty(pb + (1 << 20), dtype=torch.uint8, pin_memory=True)
+        h_back = torch.empty(n * per, dtype=torch.uint8, pin_memory=True)
+        h_off = off.cpu().numpy().astype(np.uint64)
+        h_boff = np.empty(n + 1, dtype=np.uint64)
+        h_ctx = np.full(8, 1, dtype=np.uint8)
+        np_sym, np_pay, np_back = h_sym.numpy(), h_pay.numpy(), h_back.numpy()
+
+        def e2e_step():
+            p, bo = I.encode_symbols_host(cfg, np_sym, h_off, h_ctx, payload_out=np_pay, byte_off_out=h_boff)
+            I.decode_symbols_host(cfg, p, bo, h_off, h_ctx, dtype=np.uint8, out=np_back)
+            return p
+
+        p = e2e_step()
+        torch.cuda.synchronize()
+        if env.world > 1:
+            env.dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            p = e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 2
+        if env.world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=env.dev)
+            env.dist.all_reduce(t, op=env.dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert len(p) == pb and (np_back[:1 << 20] == np_sym[:1 << 20]).all(), "c4 host round trip failed"
+        out["e2e"] = {"value": 2.0 * tot_bins / dt / 1e9, "unit": "Gbins/s", "ms_per_step": dt * 1e3,
+                      "h2d_bytes_per_step": int(n * per + pb + 3 * (n + 1) * 8 + 16), "d2h_bytes_per_step": int(pb + (n + 1) * 8 + n * per + n),
+                      "api": "cabac_encode_symbols_host + cabac_decode_symbols_host (u8 symbols in, payload + offsets out, symbols back)"}
+        del h_sym, h_pay, h_back
     return out
 
 

@@ -404,7 +404,6 @@ int cabac_encode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, co
       (rc = d_scr.alloc(cabac_compact_scratch_bytes(n_streams), s0)) || (rc = d_flag.alloc(16, s0)) ||
       (rc = d_bits.alloc(h_bits_after_symbol ? n_sym * 4 : 16, s0)))
     return rc;
-  if (n_sym) CK(cudaMemcpyAsync(d_sym.p, h_symbols, n_sym * sym_width, cudaMemcpyHostToDevice, s0));
   CK(cudaMemcpyAsync(d_off.p, h_sym_off, (n_streams + 1ull) * 8, cudaMemcpyHostToDevice, s0));
   if (ctx_bytes) CK(cudaMemcpyAsync(d_ctx.p, h_ctx_init, ctx_bytes, cudaMemcpyHostToDevice, s0));
   // bins per symbol: EG-k of a b-bit value has at most 2b+3 bins, TU at most Nq-1
@@ -415,35 +414,64 @@ int cabac_encode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, co
     const uint64_t vmax = cfg->Nq ? cfg->Nq - 1 : (sym_width == 4 ? 0xfffffull : (1ull << (8 * sym_width)) - 1);
     bins_per_sym = (vmax >> k) + 1 + k;
   }
-  uint64_t stride = cabac_slab_stride_bound(max_sym * bins_per_sym);
-  DevBuf d_slab, d_payload;
-  Drain drain_inner{g_pipe};
-  if ((rc = d_slab.alloc((size_t)n_streams * stride, s0))) return rc;
-  CK(cudaMemsetAsync(d_flag.p, 0, 16, s0));
-  rc = cabac_encode_symbols(cfg, n_streams, d_off.as<uint64_t>(), d_sym.p, sym_width, d_ctx.as<uint8_t>(), n_ctx,
-                            per_stream_init, d_slab.as<uint8_t>(), stride, d_len.as<uint32_t>(),
-                            h_bits_after_symbol ? d_bits.as<uint32_t>() : nullptr, d_flag.as<uint32_t>(), s0);
-  if (rc) return rc;
-  if ((rc = exclusive_scan_u32_u64(d_len.as<uint32_t>(), d_boff.as<uint64_t>(), n_streams, d_scr.p, s0))) return rc;
-  uint32_t flag = 0;
-  uint64_t total_bytes = 0;
-  CK(cudaMemcpyAsync(&flag, d_flag.p, 4, cudaMemcpyDeviceToHost, s0));
-  CK(cudaMemcpyAsync(&total_bytes, d_boff.as<uint64_t>() + n_streams, 8, cudaMemcpyDeviceToHost, s0));
-  CK(cudaStreamSynchronize(s0));
-  if (flag & 1u) { set_error("slab overflow"); return ISSCABAC_ERR_OVERFLOW; }
-  if (total_bytes > payload_cap) {
-    set_error("payload needs %llu bytes, capacity %llu", (unsigned long long)total_bytes, (unsigned long long)payload_cap);
-    return ISSCABAC_ERR_OVERFLOW;
+  // practical stride first (one byte per symbol: adaptive CABAC of quantised data stays far below), proof-level bound on retry
+  const uint64_t stride_bound = cabac_slab_stride_bound(max_sym * bins_per_sym);
+  uint64_t stride = std::min<uint64_t>(stride_bound, ((max_sym + 64) + 15) & ~15ull);
+  std::vector<uint32_t> cb;
+  // (the per-symbol bit trace runs on the one-kernel path: its output is indexed by the global symbol position)
+  make_chunks(n_streams, h_sym_off, h_bits_after_symbol ? 1 : kChunks, cb);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    DevBuf d_slab, d_payload;
+    Drain drain_inner{g_pipe};
+    if ((rc = d_slab.alloc((size_t)n_streams * stride, s0))) return rc;
+    CK(cudaMemsetAsync(d_flag.p, 0, 16, s0));
+    CK(cudaEventRecord(g_pipe.done[0], s0));
+    for (int l = 1; l < kLanes; ++l) CK(cudaStreamWaitEvent(g_pipe.s[l], g_pipe.done[0], 0));
+    // stream groups over the lanes: the symbols of group k+1 travel while group k is coded
+    for (size_t k = 0; k + 1 < cb.size(); ++k) {
+      cudaStream_t st = g_pipe.s[k % kLanes];
+      const uint32_t a = cb[k], b = cb[k + 1];
+      const uint64_t sa = h_sym_off[a], sb = h_sym_off[b];
+      if (attempt == 0 && sb > sa)
+        CK(cudaMemcpyAsync(d_sym.as<uint8_t>() + sa * sym_width, (const uint8_t*)h_symbols + sa * sym_width, (sb - sa) * sym_width,
+                           cudaMemcpyHostToDevice, st));
+      // the chunk's offsets index the whole symbol buffer: the kernels get the buffer base and this chunk's slice of the table
+      rc = cabac_encode_symbols(cfg, b - a, d_off.as<uint64_t>() + a, d_sym.p, sym_width,
+                                d_ctx.as<uint8_t>() + (per_stream_init ? (size_t)a * n_ctx : 0), n_ctx, per_stream_init,
+                                d_slab.as<uint8_t>() + (size_t)a * stride, stride, d_len.as<uint32_t>() + a,
+                                h_bits_after_symbol ? d_bits.as<uint32_t>() : nullptr, d_flag.as<uint32_t>(), st);
+      if (rc) return rc;
+    }
+    for (int l = 1; l < kLanes; ++l) {
+      CK(cudaEventRecord(g_pipe.done[l], g_pipe.s[l]));
+      CK(cudaStreamWaitEvent(s0, g_pipe.done[l], 0));
+    }
+    if ((rc = exclusive_scan_u32_u64(d_len.as<uint32_t>(), d_boff.as<uint64_t>(), n_streams, d_scr.p, s0))) return rc;
+    uint32_t flag = 0;
+    uint64_t total_bytes = 0;
+    CK(cudaMemcpyAsync(&flag, d_flag.p, 4, cudaMemcpyDeviceToHost, s0));
+    CK(cudaMemcpyAsync(&total_bytes, d_boff.as<uint64_t>() + n_streams, 8, cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+    if (flag & 1u) {
+      if (attempt == 1 || stride >= stride_bound) { set_error("slab overflow with the proof-level stride"); return ISSCABAC_ERR_OVERFLOW; }
+      stride = stride_bound;
+      continue;
+    }
+    if (total_bytes > payload_cap) {
+      set_error("payload needs %llu bytes, capacity %llu", (unsigned long long)total_bytes, (unsigned long long)payload_cap);
+      return ISSCABAC_ERR_OVERFLOW;
+    }
+    if ((rc = d_payload.alloc(total_bytes, s0))) return rc;
+    rc = cabac_compact(n_streams, d_slab.as<uint8_t>(), stride, d_len.as<uint32_t>(), d_payload.as<uint8_t>(), total_bytes,
+                       d_boff.as<uint64_t>(), d_scr.p, d_flag.as<uint32_t>(), s0);
+    if (rc) return rc;
+    if (total_bytes) CK(cudaMemcpyAsync(h_payload, d_payload.p, total_bytes, cudaMemcpyDeviceToHost, s0));
+    CK(cudaMemcpyAsync(h_byte_off, d_boff.p, (n_streams + 1ull) * 8, cudaMemcpyDeviceToHost, s0));
+    if (h_bits_after_symbol && n_sym) CK(cudaMemcpyAsync(h_bits_after_symbol, d_bits.p, n_sym * 4, cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+    return ISSCABAC_OK;
   }
-  if ((rc = d_payload.alloc(total_bytes, s0))) return rc;
-  rc = cabac_compact(n_streams, d_slab.as<uint8_t>(), stride, d_len.as<uint32_t>(), d_payload.as<uint8_t>(), total_bytes,
-                     d_boff.as<uint64_t>(), d_scr.p, d_flag.as<uint32_t>(), s0);
-  if (rc) return rc;
-  if (total_bytes) CK(cudaMemcpyAsync(h_payload, d_payload.p, total_bytes, cudaMemcpyDeviceToHost, s0));
-  CK(cudaMemcpyAsync(h_byte_off, d_boff.p, (n_streams + 1ull) * 8, cudaMemcpyDeviceToHost, s0));
-  if (h_bits_after_symbol && n_sym) CK(cudaMemcpyAsync(h_bits_after_symbol, d_bits.p, n_sym * 4, cudaMemcpyDeviceToHost, s0));
-  CK(cudaStreamSynchronize(s0));
-  return ISSCABAC_OK;
+  return ISSCABAC_ERR_OVERFLOW;
 }
 
 int cabac_decode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* h_byte_off,
@@ -470,12 +498,29 @@ int cabac_decode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, co
     return rc;
   CK(cudaMemcpyAsync(d_off.p, h_sym_off, (n_streams + 1ull) * 8, cudaMemcpyHostToDevice, s0));
   CK(cudaMemcpyAsync(d_boff.p, h_byte_off, (n_streams + 1ull) * 8, cudaMemcpyHostToDevice, s0));
-  if (nbytes) CK(cudaMemcpyAsync(d_bytes.p, h_bytes, nbytes, cudaMemcpyHostToDevice, s0));
   if (ctx_bytes) CK(cudaMemcpyAsync(d_ctx.p, h_ctx_init, ctx_bytes, cudaMemcpyHostToDevice, s0));
-  rc = cabac_decode_symbols(cfg, n_streams, d_boff.as<uint64_t>(), d_bytes.as<uint8_t>(), d_off.as<uint64_t>(),
-                            d_ctx.as<uint8_t>(), n_ctx, per_stream_init, d_sym.p, sym_width, d_ok.as<uint8_t>(), s0);
-  if (rc) return rc;
-  if (n_sym && h_symbols) CK(cudaMemcpyAsync(h_symbols, d_sym.p, n_sym * sym_width, cudaMemcpyDeviceToHost, s0));
+  CK(cudaEventRecord(g_pipe.done[0], s0));
+  for (int l = 1; l < kLanes; ++l) CK(cudaStreamWaitEvent(g_pipe.s[l], g_pipe.done[0], 0));
+  // stream groups over the lanes: the bytes of group k+1 arrive and the symbols of group k-1 leave while group k is decoded
+  std::vector<uint32_t> cb;
+  make_chunks(n_streams, h_sym_off, kChunks, cb);
+  for (size_t k = 0; k + 1 < cb.size(); ++k) {
+    cudaStream_t st = g_pipe.s[k % kLanes];
+    const uint32_t a = cb[k], b = cb[k + 1];
+    const uint64_t ba = h_byte_off[a], bb = h_byte_off[b], sa = h_sym_off[a], sb = h_sym_off[b];
+    if (bb > ba) CK(cudaMemcpyAsync(d_bytes.as<uint8_t>() + ba, h_bytes + ba, bb - ba, cudaMemcpyHostToDevice, st));
+    rc = cabac_decode_symbols(cfg, b - a, d_boff.as<uint64_t>() + a, d_bytes.as<uint8_t>(), d_off.as<uint64_t>() + a,
+                              d_ctx.as<uint8_t>() + (per_stream_init ? (size_t)a * n_ctx : 0), n_ctx, per_stream_init, d_sym.p,
+                              sym_width, d_ok.as<uint8_t>() + a, st);
+    if (rc) return rc;
+    if (h_symbols && sb > sa)
+      CK(cudaMemcpyAsync((uint8_t*)h_symbols + sa * sym_width, d_sym.as<uint8_t>() + sa * sym_width, (sb - sa) * sym_width,
+                         cudaMemcpyDeviceToHost, st));
+  }
+  for (int l = 1; l < kLanes; ++l) {
+    CK(cudaEventRecord(g_pipe.done[l], g_pipe.s[l]));
+    CK(cudaStreamWaitEvent(s0, g_pipe.done[l], 0));
+  }
   if (h_finish_ok) CK(cudaMemcpyAsync(h_finish_ok, d_ok.p, n_streams, cudaMemcpyDeviceToHost, s0));
   CK(cudaStreamSynchronize(s0));
   return ISSCABAC_OK;

@@ -324,7 +324,10 @@ def decode_ops_host(payload, byte_off, ops, op_off, ctx_init, bins_out: np.ndarr
     return bins_out[:n_out], ok[:n]
 
 
-def encode_symbols_host(cfg: SymCfg, symbols, sym_off, ctx_init, want_bits: bool = False):
+def encode_symbols_host(cfg: SymCfg, symbols, sym_off, ctx_init, want_bits: bool = False, payload_out: np.ndarray | None = None,
+                        byte_off_out: np.ndarray | None = None):
+    """-> (payload u8, byte_off u64[n+1] (, bits_after_symbol)) with host buffers; see cabac_encode_symbols_host.
+    payload_out / byte_off_out: caller-owned (e.g. pinned) result buffers."""
     _require_cuda()
     s = np.ascontiguousarray(symbols)
     if s.dtype not in (np.uint8, np.uint16, np.uint32):
@@ -337,8 +340,8 @@ def encode_symbols_host(cfg: SymCfg, symbols, sym_off, ctx_init, want_bits: bool
         per_sym = ((max(int(cfg.Nq), 2) - 1) >> k) + 1 + k if cfg.Nq else (1 << (8 * s.dtype.itemsize)) + k
     else:
         per_sym = 67 if cfg.method != BIN_TU else max(int(cfg.Nq), 2)
-    payload = np.empty(int(s.size) * per_sym // 8 + 16 * max(n, 1) + 64, dtype=np.uint8)
-    boff = np.empty(n + 1, dtype=np.uint64)
+    payload = payload_out if payload_out is not None else np.empty(int(s.size) * per_sym // 8 + 16 * max(n, 1) + 64, dtype=np.uint8)
+    boff = byte_off_out if byte_off_out is not None else np.empty(n + 1, dtype=np.uint64)
     bits = np.empty(max(s.size, 1), dtype=np.uint32) if want_bits else None
     check(lib().cabac_encode_symbols_host(C.byref(cfg), C.c_uint32(n), vp(off), vp(s), s.dtype.itemsize, vp(c),
                                           C.c_uint32(n_ctx), per, vp(payload), C.c_uint64(payload.size), vp(boff),
@@ -347,7 +350,7 @@ def encode_symbols_host(cfg: SymCfg, symbols, sym_off, ctx_init, want_bits: bool
     return res + (bits[:s.size],) if want_bits else res
 
 
-def decode_symbols_host(cfg: SymCfg, payload, byte_off, sym_off, ctx_init, dtype=np.uint32):
+def decode_symbols_host(cfg: SymCfg, payload, byte_off, sym_off, ctx_init, dtype=np.uint32, out: np.ndarray | None = None):
     _require_cuda()
     off = np.ascontiguousarray(sym_off, dtype=np.uint64)
     boff = np.ascontiguousarray(byte_off, dtype=np.uint64)
@@ -356,7 +359,8 @@ def decode_symbols_host(cfg: SymCfg, payload, byte_off, sym_off, ctx_init, dtype
         pay = np.zeros(1, dtype=np.uint8)
     n = off.size - 1
     c, n_ctx, per = _np_ctx(ctx_init, n)
-    out = np.empty(max(int(off[-1]), 1), dtype=dtype)
+    if out is None:
+        out = np.empty(max(int(off[-1]), 1), dtype=dtype)
     ok = np.zeros(max(n, 1), dtype=np.uint8)
     check(lib().cabac_decode_symbols_host(C.byref(cfg), C.c_uint32(n), vp(boff), vp(pay), vp(off), vp(c),
                                           C.c_uint32(n_ctx), per, vp(out), out.dtype.itemsize, vp(ok)))
