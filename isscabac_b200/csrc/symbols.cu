@@ -220,15 +220,10 @@ __global__ void k_bin_lut(isscabac_symcfg c, uint4* lut) {
   lut[e] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Pass 2, op-parallel.  Phase A (symbol-parallel, 8 symbols per thread): codes, block scan, the
-// op_off entries of the streams that start in this tile, and per symbol in shared memory its first
-// op position, its table key (index | length << 10) and its value.  Phase B (op-parallel): the
-// tile's ops are cut into the 16-byte pieces of their place in HBM; every piece is produced by one
-// thread -- it starts at the symbol that owns the piece's first op (each symbol writes its index
-// into the owner slot of the pieces that begin inside it: disjoint, no atomics) and walks on from
-// there, one table byte per op -- and leaves as ONE aligned 16-byte store.  A warp therefore does
-// not pay for the longest of 32 threads' 8-symbol runs, and no op is staged in shared memory.
-constexpr uint32_t BIN_ROUND = 1024;     // 16-byte pieces per round (a tile of EG0 symbols has ~300)
+// Pass 2.  Phase A (symbol-parallel, 8 symbols per thread): codes, block scan, the op_off entries of the streams that
+// start in this tile.  Phase B: the threads write the op bytes of their symbols into a stage in shared memory at their
+// tile positions -- one table byte per op -- and the stage leaves for HBM as the aligned 16-byte pieces of the op array.
+constexpr uint32_t BIN_STAGE = 16 * 1024; // bytes of ops staged per round (a tile of 2,048 EG0 symbols has ~4,800)
 
 template <int W, int PROF, int METH>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, const void* sym, uint64_t n,
@@ -237,11 +232,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, con
                                                            const uint64_t* tile_prefix, uint64_t* op_off, uint8_t* ops,
                                                            uint64_t cap, const uint4* lut) {
   __shared__ uint32_t s_warp[BIN_THREADS / 32];
-  __shared__ uint32_t s_pos[BIN_TILE + 1];
-  __shared__ uint32_t s_sym[BIN_TILE + 2];        // [0] = the symbol in front of the tile, [i + 1] = symbol i of the tile
-  __shared__ uint16_t s_key[BIN_TILE + 2];
-  __shared__ uint8_t s_up[BIN_THREADS];           // bit k of byte t: symbol 8t + k has an up / previous neighbour
-  __shared__ uint16_t s_owner[BIN_ROUND];
+  __shared__ __align__(16) uint8_t s_stage[BIN_STAGE];
   __shared__ __align__(16) uint4 s_lut[LUT_MAX];
   const SymCfg cfg = fixed_cfg<PROF, METH>(c);
   const LutGeom geom = lut_geom(cfg.profile, cfg.method, cfg.Nq);
@@ -309,100 +300,66 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, con
     }
   }
   if (!ops) return;      // offsets only (first of the two calls)
-  {
-    // the symbol in front of this thread's run (the neighbour of its first symbol)
-    uint32_t before = 0;
-    if ((up_mask & 1u) || threadIdx.x == 0) before = i0 > 0 && i0 <= n ? load_sym(sym, W, i0 - 1) : 0u;
-    uint32_t pos = lo;
-#pragma unroll
-    for (int k = 0; k < BIN_ITEMS; ++k) {
-      const uint32_t li = threadIdx.x * BIN_ITEMS + k;
-      const uint32_t idx = lut_index(cfg, geom.dom, v[k], k ? v[k - 1] : before, (up_mask >> k) & 1u);
-      s_pos[li] = pos;
-      s_sym[li + 1] = v[k];
-      s_key[li] = (uint16_t)((idx == LUT_ESC || code[k].len > 15u) ? LUT_ESC : (idx | (code[k].len << 10)));
-      pos += code[k].len;
-    }
-    s_up[threadIdx.x] = (uint8_t)up_mask;
-    if (threadIdx.x == 0) {
-      s_sym[0] = before;
-      s_sym[BIN_TILE + 1] = 0;
-      s_key[BIN_TILE] = 0;
-      s_pos[BIN_TILE] = block_total;
-    }
-  }
-  const uint32_t skew = (uint32_t)((reinterpret_cast<uintptr_t>(ops) + tile_base) & 15u);
-  const uint32_t npieces = (block_total + skew + 15u) >> 4;   // piece j = tile positions [16j - skew, 16j - skew + 16)
+  // Phase B.  Every thread writes the op bytes of its 8 symbols into a STAGE in shared memory at their tile positions
+  // (one table byte load + one byte store per op; symbols outside the table take the closed form op by op), then the
+  // stage leaves for HBM in the aligned 16-byte pieces of the op array, one LDS.128 + STG.128 per piece.  (Round 1
+  // produced each piece by one thread walking the symbols that overlap it: 43 thread-instructions per op, 63 % of
+  // the shared-memory wavefronts bank conflicts.)  A tile whose ops exceed the stage is done in rounds.
+  const uint32_t skew = (uint32_t)((reinterpret_cast<uintptr_t>(ops) + tile_base) & 15u);   // stage byte = tile position + skew
   // ops the caller's buffer has room for (a too small buffer is filled up to its capacity)
   const uint32_t room = tile_base >= cap ? 0u : (cap - tile_base < block_total ? (uint32_t)(cap - tile_base) : block_total);
   const uint32_t lut0 = (uint32_t)__cvta_generic_to_shared(s_lut);
-  for (uint32_t r0 = 0; r0 < npieces; r0 += BIN_ROUND) {
-    __syncthreads();     // records complete (first round) / owner slots free again (later rounds)
-    {
-      uint32_t pos = lo;
+  const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(s_stage);
+  // the neighbour of this thread's first symbol
+  uint32_t before = 0;
+  if (up_mask & 1u) before = i0 > 0 && i0 <= n ? load_sym(sym, W, i0 - 1) : 0u;
+  for (uint32_t w0 = 0; w0 < block_total + skew; w0 += BIN_STAGE) {     // stage window = stage bytes [w0, w0 + BIN_STAGE)
+    if (w0) __syncthreads();                                            // the previous round has left the stage
+    const uint32_t w1 = w0 + BIN_STAGE;
+    uint32_t pos = lo + skew;
 #pragma unroll
-      for (int k = 0; k < BIN_ITEMS; ++k) {
-        const uint32_t len = code[k].len;
-        if (len) {
-          // pieces whose first op lies inside this symbol; piece 0 starts with the tile's op 0
-          uint32_t j_lo = pos == 0 ? 0u : (pos + skew + 15u) >> 4;
-          const uint32_t j_hi = (pos + len - 1u + skew) >> 4;
-          if (j_lo < r0) j_lo = r0;
-          for (uint32_t j = j_lo; j <= j_hi && j < r0 + BIN_ROUND; ++j) s_owner[j - r0] = (uint16_t)(threadIdx.x * BIN_ITEMS + k);
+    for (int k = 0; k < BIN_ITEMS; ++k) {
+      const uint32_t len = code[k].len;
+      if (len && pos < w1 && pos + len > w0) {
+        const uint32_t u = k ? v[k - 1] : before;
+        const bool up = (up_mask >> k) & 1u;
+        const uint32_t idx = len > 15u ? LUT_ESC : lut_index(cfg, geom.dom, v[k], u, up);
+        const uint32_t j0 = pos < w0 ? w0 - pos : 0u, j1 = pos + len > w1 ? w1 - pos : len;   // ops of this symbol inside the window
+        if (idx != LUT_ESC) {
+          const uint32_t src = lut0 + (idx << 4), dst = stage0 + pos - w0;
+          for (uint32_t j = j0; j < j1; ++j) {
+            uint32_t byte;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(byte) : "r"(src + j));
+            asm volatile("st.shared.u8 [%0], %1;" :: "r"(dst + j), "r"(byte) : "memory");
+          }
+        } else {
+          const SymCode prev = sym_code(u, cfg.Nq, cfg.method);
+          for (uint32_t j = j0; j < j1; ++j) {
+            const int cx = select_ctx(cfg, j + 1u, code[k].np, prev, up);
+            const uint32_t byte = ((cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx) << 1) | sym_bin(code[k], j + 1u);
+            asm volatile("st.shared.u8 [%0], %1;" :: "r"(stage0 + pos - w0 + j), "r"(byte) : "memory");
+          }
         }
-        pos += len;
       }
+      pos += len;
     }
     __syncthreads();
-    const uint32_t r1 = r0 + BIN_ROUND < npieces ? r0 + BIN_ROUND : npieces;
-    for (uint32_t j = r0 + threadIdx.x; j < r1; j += BIN_THREADS) {
-      const int32_t pbeg = (int32_t)(16u * j) - (int32_t)skew;           // tile position of byte 0 of the piece
-      const uint32_t e0 = pbeg < 0 ? (uint32_t)(-pbeg) : 0u;             // valid bytes: [e0, e1)
+    // pieces of this window: stage bytes [16 p, 16 p + 16) <-> tile positions [w0 + 16 p - skew, ...)
+    const uint32_t wend = w1 < block_total + skew ? w1 : block_total + skew;
+    const uint32_t npieces = (wend - w0 + 15u) >> 4;
+    for (uint32_t pc = threadIdx.x; pc < npieces; pc += BIN_THREADS) {
+      const int32_t pbeg = (int32_t)(w0 + 16u * pc) - (int32_t)skew;           // tile position of byte 0 of the piece
+      const uint32_t e0 = pbeg < 0 ? (uint32_t)(-pbeg) : 0u;                   // valid bytes: [e0, e1)
       const int32_t left = (int32_t)room - pbeg;
       const uint32_t e1 = left <= 0 ? 0u : (left < 16 ? (uint32_t)left : 16u);
       if (e0 >= e1) continue;
-      uint32_t i = s_owner[j - r0];
-      uint32_t b = (uint32_t)(pbeg + (int32_t)e0) - s_pos[i];            // ops of symbol i already out (0-based position)
-      uint32_t a = 0, len = 0;      // table route: shared-window address of the symbol's string, its length
-      bool esc = false;             // closed-form route
-      SymCode cur = {0, 0, 0}, prev = {0, 0, 0};
-      bool up = false;
-      auto enter = [&]() {
-        const uint32_t key = s_key[i];
-        esc = key == LUT_ESC;
-        a = lut0 + ((key & 1023u) << 4);
-        len = key >> 10;
-        if (esc) {
-          cur = sym_code(s_sym[i + 1], cfg.Nq, cfg.method);
-          prev = sym_code(s_sym[i], cfg.Nq, cfg.method);
-          up = (s_up[i >> 3] >> (i & 7u)) & 1u;
-          len = cur.len;
-        }
-      };
-      enter();
-      uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-      for (uint32_t e = 0; e < 16; ++e) {
-        if (e >= e0 && e < e1) {
-          uint32_t byte;
-          if (!esc) {
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(byte) : "r"(a + b));
-          } else {
-            const int cx = select_ctx(cfg, b + 1u, cur.np, prev, up);
-            byte = ((cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx) << 1) | sym_bin(cur, b + 1u);
-          }
-          w[e >> 2] |= byte << (8u * (e & 3u));
-          if (++b == len) {
-            ++i;
-            b = 0;
-            enter();
-          }
-        }
-      }
+      uint4 q;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(stage0 + 16u * pc) : "memory");
       uint8_t* dst = ops + tile_base + pbeg;       // 16-byte aligned by the choice of skew
       if (e0 == 0 && e1 == 16) {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dst) = q;
       } else {
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (uint32_t e = 0; e < 16; ++e)
           if (e >= e0 && e < e1) dst[e] = (uint8_t)(w[e >> 2] >> (8u * (e & 3u)));
