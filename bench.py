@@ -1014,11 +1014,11 @@ def run_b200(a):
     ctx_bins, ep_bins = total_bins * (1 - P_EP), total_bins * P_EP
     enc_ops = ctx_bins * 16 + ep_bins * 6 + payload_bytes * 12
     dec_ops = ctx_bins * 16 + ep_bins * 6 + payload_bytes * 4
-    lanes_alu, lanes_both, peak_src = int_peak_lanes()
+    lanes_alu, lanes_both, int_src = int_peak_lanes()
     int_peak = sm * lanes_both * f_sm * 1e6
     roof_int = {"bound": "int32-issue", "unit": "Tops/s", "peak": int_peak / 1e12, "peak_note":
                 f"{sm} SMs x {lanes_both:.1f} int32 lanes/clk/SM (ALU + FMA pipes, dependent-free IADD3:IMAD 1:1) x {f_sm:.0f} MHz "
-                f"(median SM clock in the timed region); {peak_src}",
+                f"(median SM clock in the timed region); {int_src}",
                 "peak_alu_pipe": sm * lanes_alu * f_sm * 1e6 / 1e12,
                 "peak_alu_pipe_note": f"ALU pipe alone: {lanes_alu:.1f} lanes/clk/SM (IADD3 / LOP3 / SHF / PRMT / ISETP+SEL all measure the same)",
                 "encode": {"achieved": enc_ops / (ms_enc * 1e-3) / 1e12, "frac": enc_ops / (ms_enc * 1e-3) / int_peak,
