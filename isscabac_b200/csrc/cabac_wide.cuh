@@ -457,6 +457,26 @@ CB_HD uint32_t decw_ep_run(DecWide& D, uint32_t n) {
   return q;
 }
 
+// The same n bypass decisions (n <= kEpRunMax, f <= 54 - n on entry) as a restoring division on the upper word alone:
+// the shifted window of step k compares >= range << 21 exactly when the UNSHIFTED remainder compares >= (range << 21) >> k
+// (both sides of the shifted comparison are multiples of 2^k up to the k look-ahead bits shifted in below them), so the
+// window is shifted once, by n, at the end.  Two dependent operations per bin and no divide: for the 2 - 4 suffix bits of
+// a small exp-Golomb value this is both shorter and far lower in latency than decw_ep_run's quotient.
+CB_HD uint32_t decw_ep_bits(DecWide& D, uint32_t n) {
+  uint32_t S = D.range << 21, H = D.hi, q = 0;
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint32_t t = H - S;
+    const bool p = H >= S;
+    H = p ? t : H;
+    q = 2u * q + (p ? 1u : 0u);
+    S >>= 1;
+  }
+  D.hi = cb_funnel_l(D.lo, H, n);   // (H:lo) << n, n in 1..16
+  D.lo <<= n;
+  D.f += (int32_t)n;
+  return q;
+}
+
 // decodeBinTrm, Decoder.cpp:423-472
 CB_HD uint32_t decw_trm(DecWide& D) {
   D.range -= 2;

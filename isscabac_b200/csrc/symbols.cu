@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cstdio>
 #include <vector>
 
 #include "../../include/isscabac.h"
@@ -901,6 +902,14 @@ struct TreeNode {            // 8 bytes
   uint16_t pad;
 };
 constexpr uint16_t kLeaf = 0x8000, kEscape = 0xffff;     // bit 14 is set in kEscape only: leaves carry at most 6 variant bits
+// A subtree of bypass nodes that is a COMPLETE binary tree of depth n whose leaves are base, base + 1, ... in bin order is
+// n bypass bins read as one number (the suffix of an exp-Golomb code under FLAT_EPSUF): it collapses into one node with
+// code = kTreeEpRun, child[0] = n, child[1] = the leaf entry of value 0 (kLeaf | next variant << 8), pad = base, and the
+// decoder takes it in one step with decw_ep_bits (decodeBinsEP, Decoder.cpp:333-421 == n single decodeBinEP calls).
+constexpr uint16_t kTreeEpRun = 0xfffe;
+#ifndef TREE_EP_RUNS
+#define TREE_EP_RUNS 1
+#endif
 constexpr uint32_t TREE_MAX_NODES = 4096;
 #ifndef TREE_MIN_BLOCKS
 #define TREE_MIN_BLOCKS 2
@@ -908,6 +917,31 @@ constexpr uint32_t TREE_MAX_NODES = 4096;
 constexpr uint32_t TREE_STAGE_STRIDE = 48;     // 32-byte output stage per lane + 16 B (bank spread, keeps 16-byte alignment)
 
 struct TreeInfo { uint32_t n_nodes, var_stride; };   // var_stride: nodes per variant (variant v's root = node v * var_stride)
+
+// host: is the subtree below node `at` a complete tree of bypass nodes over consecutive values with one next variant?
+static bool tree_ep_complete(const std::vector<TreeNode>& t, uint32_t at, uint32_t& depth, uint32_t& base, uint32_t& nv) {
+  if (t[at].code != ISSCABAC_OP8_EP) return false;
+  uint32_t d[2], b[2], v[2];
+  for (int k = 0; k < 2; ++k) {
+    const uint16_t c = t[at].child[k];
+    if (c == kEscape) return false;
+    if (c & kLeaf) { d[k] = 0; b[k] = c & 0xffu; v[k] = (c >> 8) & 0x3fu; }
+    else if (!tree_ep_complete(t, c, d[k], b[k], v[k])) return false;
+  }
+  if (d[0] != d[1] || v[0] != v[1] || b[1] != b[0] + (1u << d[0])) return false;
+  depth = d[0] + 1; base = b[0]; nv = v[0];
+  return true;
+}
+static void tree_collapse_ep(std::vector<TreeNode>& t, uint32_t at, bool is_root) {
+  uint32_t depth, base, nv;
+  // the root stays a plain node: the kernel looks for a run only behind a decoded bin
+  if (!is_root && tree_ep_complete(t, at, depth, base, nv) && depth <= kEpRunMax) {
+    t[at] = TreeNode{{(uint16_t)depth, (uint16_t)(kLeaf | (nv << 8))}, kTreeEpRun, (uint16_t)base};
+    return;
+  }
+  for (int k = 0; k < 2; ++k)
+    if (!(t[at].child[k] & kLeaf)) tree_collapse_ep(t, t[at].child[k], false);
+}
 
 // host: the code trees of a configuration; false when the configuration is not covered (large alphabets, FL32, TR)
 static bool build_code_tree(const isscabac_symcfg& c, std::vector<TreeNode>& nodes, TreeInfo& info) {
@@ -953,6 +987,7 @@ static bool build_code_tree(const isscabac_symcfg& c, std::vector<TreeNode>& nod
         }
       }
     }
+    if (TREE_EP_RUNS) tree_collapse_ep(t, 0, true);
     if (t.size() > stride) stride = (uint32_t)t.size();
   }
   if ((uint64_t)stride * n_var > TREE_MAX_NODES) return false;
@@ -961,7 +996,7 @@ static bool build_code_tree(const isscabac_symcfg& c, std::vector<TreeNode>& nod
     for (size_t k = 0; k < trees[var].size(); ++k) {
       TreeNode nd = trees[var][k];
       for (int b = 0; b < 2; ++b)
-        if (!(nd.child[b] & kLeaf)) nd.child[b] = (uint16_t)(nd.child[b] + var * stride);   // variant-local -> global node index
+        if (nd.code != kTreeEpRun && !(nd.child[b] & kLeaf)) nd.child[b] = (uint16_t)(nd.child[b] + var * stride);   // variant-local -> global node index
       nodes[(size_t)var * stride + k] = nd;
     }
   info.n_nodes = stride * n_var;
@@ -998,6 +1033,8 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
   uint32_t i = 0, cnt = 0, row = 0, node = tree0, seen = 0;   // seen: OR of every child taken; bit 14 = an escape leaf was hit
   bool active = false, have = s < P.n_streams;
   if (have && order) s = order[s];
+  uint2 nd = make_uint2(0u, 0u);                 // the node at `node`, loaded as soon as `node` is known
+  auto ld_node = [](uint2& v, uint32_t a) { asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); };
   // write symbols [fl, upto) out of the stage: the aligned 16-byte piece in one store, anything else byte by byte
   auto flush = [&](uint32_t upto) {
     while (fl < upto) {
@@ -1025,18 +1062,30 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
       const uint64_t b0 = P.byte_off[s], b1 = P.byte_off[s + 1];
       decw_start(D, P.bytes + b0, (uint32_t)(b1 - b0));
       i = 0; fl = 0; row = 0; node = tree0; seen = 0;
+      ld_node(nd, node);
       active = true;
     }
     if (!__any_sync(0xffffffffu, active)) break;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (active && i < cnt) {
-        uint2 nd;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nd.x), "=r"(nd.y) : "r"(node));
+        // nd = the node of this bin, never a run node (a run is taken in the step of the bin that leads to it)
         const uint32_t bin = decw_op<0>(D, nd.y & 0xffffu, ctx, tab, n_ctx);
-        const uint32_t child = bin ? nd.x >> 16 : nd.x & 0xffffu;
+        uint32_t child = bin ? nd.x >> 16 : nd.x & 0xffffu;
         seen |= child;
-        node = tree0 + child * 8u;
+        if (!(child & kLeaf)) {
+          node = tree0 + child * 8u;
+          ld_node(nd, node);
+          if (TREE_EP_RUNS && (nd.y & 0xffffu) == kTreeEpRun) {
+            // n bypass bins in one step; the window is topped up first only if the run would read unfilled bits, and
+            // afterwards so that the remaining bins of this group of four find theirs (f <= 31 <= kLazyDec - 1)
+            const uint32_t n = nd.x & 0xffffu;
+            if (D.f + (int32_t)n > 54) decw_refill(D);
+            const uint32_t q = decw_ep_bits(D, n);
+            decw_refill(D);
+            child = (nd.x >> 16) | ((nd.y >> 16) + q);
+          }
+        }
         if (child & kLeaf) {                       // the symbol is complete
           asm volatile("st.shared.u8 [%0], %1;" :: "r"(stage0 + ((a0 + i) & 31u)), "r"(child) : "memory");
           ++i;
@@ -1052,6 +1101,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
             }
             node = tree0 + (child == kEscape ? 0u : nv * var_bytes);
           }
+          ld_node(nd, node);
         }
       }
     }
@@ -1358,6 +1408,16 @@ int cabac_decode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const u
                          const uint8_t* d_bytes, const uint64_t* d_sym_off,
                          const uint8_t* d_ctx_init, uint32_t n_ctx, int per_stream_init,
                          void* d_symbols, int sym_width, uint8_t* d_finish_ok, void* stream) {
+  if (cfg && getenv("ISSCABAC_DEBUG_TREE")) {
+    std::vector<TreeNode> nodes;
+    TreeInfo ti{0, 0};
+    const bool ok = build_code_tree(*cfg, nodes, ti);
+    uint32_t n_ep = 0;
+    for (const TreeNode& nd : nodes) n_ep += nd.code == kTreeEpRun;
+    fprintf(stderr, "code tree: built %d, %u nodes, stride %u, %u run nodes\n", (int)ok, ti.n_nodes, ti.var_stride, n_ep);
+    for (size_t k = 0; k < nodes.size() && k < 24; ++k)
+      fprintf(stderr, "  node %zu: child %04x %04x code %04x pad %u\n", k, nodes[k].child[0], nodes[k].child[1], nodes[k].code, nodes[k].pad);
+  }
   int rc = check_cfg(cfg, n_ctx, sym_width, true, true);
   if (rc) return rc;
   if (n_streams == 0) return ISSCABAC_OK;

@@ -264,6 +264,50 @@ int emul_decode_ops_wide_runs(uint32_t n_streams, const uint64_t* byte_off, cons
   return 0;
 }
 
+// the bypass runs as the tree decoder codes them (k_decode_symbols_tree): restoring division on the upper word
+// (decw_ep_bits), the window topped up before the run only when the run would read unfilled bits, and after it
+int emul_decode_ops_wide_runs_loop(uint32_t n_streams, const uint64_t* byte_off, const uint8_t* bytes,
+                                   const uint64_t* op_off, const uint8_t* ops,
+                                   const uint8_t* ctx_init, uint32_t n_ctx, int per_stream,
+                                   uint8_t* bins, uint8_t* ok, uint32_t max_run) {
+  std::vector<uint32_t> cs(n_ctx + 1);
+  for (uint32_t s = 0; s < n_streams; ++s) {
+    for (uint32_t c = 0; c < n_ctx; ++c) cs[c] = ctx_init[(per_stream ? (uint64_t)s * n_ctx : 0) + c] & 127u;
+    cs[n_ctx] = kEpState;
+    HostCtx ctx{cs.data()};
+    HostTab tab;
+    DecWide D;
+    decw_start(D, bytes + byte_off[s], (uint32_t)(byte_off[s + 1] - byte_off[s]));
+    const uint8_t* p = ops + op_off[s];
+    uint8_t* q = bins + op_off[s];
+    const uint64_t n = op_off[s + 1] - op_off[s];
+    uint32_t since = 0;     // context bins since the window was last known to hold f <= 35
+    for (uint64_t i = 0; i < n;) {
+      if ((p[i] >> 1) > kOpTrmCode) {
+        uint32_t c = 0;
+        while (i + c < n && (p[i + c] >> 1) > kOpTrmCode && c < max_run) ++c;
+        if (D.f + (int32_t)c > 54) decw_refill(D);
+        const uint32_t v = decw_ep_bits(D, c);
+        decw_refill(D);
+        since = 0;
+        for (uint32_t k = 0; k < c; ++k) q[i + k] = (uint8_t)((v >> (c - 1 - k)) & 1u);
+        i += c;
+      } else if ((p[i] >> 1) == kOpTrmCode) {
+        q[i] = (uint8_t)decw_general(D, p[i], ctx, tab, n_ctx);
+        ++i;
+        since = 0;
+      } else {
+        // the kernel's group schedule: up to four context bins between two (voted) refills at f >= kLazyDec
+        q[i] = (uint8_t)decw_op<0>(D, p[i] >> 1, ctx, tab, n_ctx);
+        ++i;
+        if (++since == 4u) { if (D.f >= kLazyDec) decw_refill(D); since = 0; }
+      }
+    }
+    ok[s] = (uint8_t)decw_finish(D);
+  }
+  return 0;
+}
+
 // direct hook for the (practically unreachable) carry walk past a 0xFFFFFFFF pending word
 void emul_carry_walk(uint32_t* row, uint32_t wp, uint32_t cap_words) { encw_carry_walk(wp, cap_words, row + wp); }
 

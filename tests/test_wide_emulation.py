@@ -245,6 +245,13 @@ def test_wide_bypass_runs(emul, max_run):
                                    p(off, u64p), p(ops, u8p), p(ci.reshape(-1), u8p), C.c_uint32(n_ctx), 1,
                                    p(out, u8p), p(ok, u8p), C.c_uint32(max_run))
     assert ok.all() and (out[:n] == bins).all()
+    # the tree decoder's form of a run: restoring division on the upper word of the window (decw_ep_bits)
+    out[:] = 0
+    ok[:] = 0
+    emul.emul_decode_ops_wide_runs_loop(C.c_uint32(n_streams), p(np.ascontiguousarray(boff, dtype=np.uint64), u64p), p(pb, u8p),
+                                        p(off, u64p), p(ops, u8p), p(ci.reshape(-1), u8p), C.c_uint32(n_ctx), 1,
+                                        p(out, u8p), p(ok, u8p), C.c_uint32(max_run))
+    assert ok.all() and (out[:n] == bins).all()
 
 
 def test_out_of_range_codes_are_bypass_bins(emul):
