@@ -384,6 +384,36 @@ CB_HD void decw_refill(DecWide& D) {
   }
 }
 
+// decw_refill without a branch on the lane's own fill level: meant for call sites the WARP reaches together (behind a
+// vote) and where some lanes top up and others do not.  Inside the divergent `if (f >= 32)` of decw_refill the rotation
+// cur <- nxt <- load ends in a register move FROM the load's destination at the join, i.e. the warp waits there for the
+// word it has only just requested (ncu on a warp of long streams in the tree decoder: 180 cycles per top-up on that one
+// move, long_scoreboard).  Here the new word is loaded IN PLACE by a predicated load (the asm operand is read-write, so
+// no copy can follow it) and everything else is a select.  Words past the end of the stream are not loaded; what the
+// register then holds does not matter, decw_fetch's end-of-stream rule overwrites those bytes with 0xFF.
+CB_HD void decw_refill_p(DecWide& D) {
+#if defined(__CUDA_ARCH__) && !CABAC_DEC_TMA
+  const bool need = D.f >= 32;
+  uint32_t w = cb_prmt(D.cur, D.nxt, D.sel);
+  D.cur = need ? D.nxt : D.cur;
+  const uint32_t ld = (need && D.widx < D.wcnt) ? 1u : 0u;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u32 %0, [%1];\n\t}" : "+r"(D.nxt) : "l"(D.wbase + D.widx), "r"(ld));
+  D.widx += need ? 1u : 0u;
+  if (need && D.p + 4u > D.len) {             // only at the very end of a stream
+    const uint32_t rem = D.len > D.p ? D.len - D.p : 0u;
+    w = rem ? (w | (0xffffffffu >> (8u * rem))) : 0xffffffffu;
+  }
+  w = need ? w : 0u;
+  const uint32_t k = (uint32_t)D.f & 31u;     // need: f - 32 (0..23)
+  D.lo |= w << k;
+  D.hi |= cb_funnel_l(w, 0u, k);              // w >> (32-k), 0 when k == 0 or w == 0
+  D.p += need ? 4u : 0u;
+  D.f -= need ? 32 : 0;
+#else
+  decw_refill(D);
+#endif
+}
+
 // start, Decoder.cpp:54-60: the reference reads two bytes; here the first seven go in.
 CB_HD void decw_start(DecWide& D, const uint8_t* in, uint32_t len) {
   D.in = in; D.len = len; D.range = 510;
@@ -464,6 +494,7 @@ CB_HD uint32_t decw_ep_run(DecWide& D, uint32_t n) {
 // a small exp-Golomb value this is both shorter and far lower in latency than decw_ep_run's quotient.
 CB_HD uint32_t decw_ep_bits(DecWide& D, uint32_t n) {
   uint32_t S = D.range << 21, H = D.hi, q = 0;
+#pragma unroll 1
   for (uint32_t k = 0; k < n; ++k) {
     const uint32_t t = H - S;
     const bool p = H >= S;
@@ -476,6 +507,28 @@ CB_HD uint32_t decw_ep_bits(DecWide& D, uint32_t n) {
   D.f += (int32_t)n;
   return q;
 }
+
+// The same n bypass decisions (0 <= n <= 13, f <= 54 - n on entry) as ONE division by a reciprocal from a table: the
+// quotient of decw_ep_run is floor(A / range) with A = hi >> (22 - n) < range << n < 2^23, and with M = floor(2^32 /
+// range) + 1 the product A * M >> 32 equals it exactly (the excess A * (M - 2^32 / range) / 2^32 stays below 2^-9 <
+// 1 / range).  rcp = shared-window address of the table M[range & 255], range = 256 .. 511 (a corrupt stream may leave
+// a range outside 256 .. 510: the index stays inside the table whatever it is).  n = 0 leaves the window as it is, so
+// the call needs no branch around it; device only.
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t decw_ep_recip(DecWide& D, uint32_t n, uint32_t rcp) {
+  uint32_t M;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(M) : "r"(rcp + 4u * (D.range & 255u)));
+  const uint32_t sh = 22u - n;
+  const uint32_t A = D.hi >> sh;
+  const uint32_t q = __umulhi(A, M);
+  const uint32_t rem = A - q * D.range;
+  const uint32_t h = D.hi & ~(0xffffffffu << sh);
+  D.hi = (rem << 22) | cb_funnel_l(D.lo, h, n);   // (h:lo) << n
+  D.lo <<= n;
+  D.f += (int32_t)n;
+  return q;
+}
+#endif
 
 // decodeBinTrm, Decoder.cpp:423-472
 CB_HD uint32_t decw_trm(DecWide& D) {

@@ -907,6 +907,7 @@ constexpr uint16_t kLeaf = 0x8000, kEscape = 0xffff;     // bit 14 is set in kEs
 // code = kTreeEpRun, child[0] = n, child[1] = the leaf entry of value 0 (kLeaf | next variant << 8), pad = base, and the
 // decoder takes it in one step with decw_ep_bits (decodeBinsEP, Decoder.cpp:333-421 == n single decodeBinEP calls).
 constexpr uint16_t kTreeEpRun = 0xfffe;
+constexpr uint32_t kTreeRunMax = 13;        // bins per run node: decw_ep_recip is exact up to 13
 #ifndef TREE_EP_RUNS
 #define TREE_EP_RUNS 1
 #endif
@@ -935,7 +936,7 @@ static bool tree_ep_complete(const std::vector<TreeNode>& t, uint32_t at, uint32
 static void tree_collapse_ep(std::vector<TreeNode>& t, uint32_t at, bool is_root) {
   uint32_t depth, base, nv;
   // the root stays a plain node: the kernel looks for a run only behind a decoded bin
-  if (!is_root && tree_ep_complete(t, at, depth, base, nv) && depth <= kEpRunMax) {
+  if (!is_root && tree_ep_complete(t, at, depth, base, nv) && depth <= kTreeRunMax) {
     t[at] = TreeNode{{(uint16_t)depth, (uint16_t)(kLeaf | (nv << 8))}, kTreeEpRun, (uint16_t)base};
     return;
   }
@@ -1004,11 +1005,56 @@ static bool build_code_tree(const isscabac_symcfg& c, std::vector<TreeNode>& nod
   return true;
 }
 
+// ---------------------------------------------------------------------------
+// The tree as the kernel walks it: 16-byte nodes {entry by bin 0, entry by bin 1, byte offset of the context slot,
+// bypass flag}.  An entry is what follows the bin:
+//   inner child     bits 0-15 = byte offset of the child node
+//   symbol complete bit 31 set; bits 16-23 = value (the base value when a run follows), bits 24-27 = n, the number of
+//                   bypass bins still to read as one number (a collapsed run node; 0 = none), bit 30 = escape (no such
+//                   codeword), bits 0-15 = byte offset of the root the NEXT symbol starts at (its variant's)
+// so a run node is never loaded: the step that decodes the bin in front of it has n and the base value in the entry,
+// and "n = 0" makes the run code a no-op for every other entry.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kEntLeaf = 0x80000000u, kEntEscape = 0x40000000u;
+
+static void flatten_tree(const std::vector<TreeNode>& nodes, const TreeInfo& ti, uint32_t n_ctx, std::vector<uint4>& out, bool& has_runs) {
+  out.assign(nodes.size(), make_uint4(kEntLeaf | kEntEscape, kEntLeaf | kEntEscape, 0u, 0u));
+  has_runs = false;
+  for (size_t k = 0; k < nodes.size(); ++k) {
+    const TreeNode& nd = nodes[k];
+    if (nd.code == kTreeEpRun) continue;                    // reached through its parent's entry only
+    uint32_t e[2];
+    for (int b = 0; b < 2; ++b) {
+      const uint16_t c = nd.child[b];
+      if (c == kEscape) e[b] = kEntLeaf | kEntEscape;       // restart at variant 0
+      else if (c & kLeaf) e[b] = kEntLeaf | ((uint32_t)(c & 0xffu) << 16) | (((c >> 8) & 0x3fu) * ti.var_stride * 16u);
+      else if (nodes[c].code == kTreeEpRun) {
+        const TreeNode& r = nodes[c];
+        e[b] = kEntLeaf | ((uint32_t)r.child[0] << 24) | ((uint32_t)r.pad << 16) | (((r.child[1] >> 8) & 0x3fu) * ti.var_stride * 16u);
+        has_runs = true;
+      } else e[b] = (uint32_t)c * 16u;
+    }
+    const bool ep = nd.code >= n_ctx;                       // ISSCABAC_OP8_EP, or a context this call does not have
+    out[k] = make_uint4(e[0], e[1], (ep ? n_ctx : nd.code) * WIDE_CTX_STRIDE, ep ? 1u : 0u);
+  }
+}
+
 // MODE: how the next symbol's variant follows from the one just decoded -- 0: one variant (FLAT profiles), 1: always the
-// decoded symbol's (DEMO), 2: the decoded symbol's unless the next symbol starts a column (ISS)
-template <int MODE>
+// decoded symbol's (DEMO), 2: the decoded symbol's unless the next symbol starts a column (ISS).  RUNS: the tree holds run
+// entries (collapsed bypass subtrees).
+//
+// A step is written WITHOUT branches on the lane's own state: every lane of the warp decodes one bin per step whether or
+// not it still has symbols (a lane past its last symbol works on a window nobody reads any more: all its loads stay
+// inside the stream or the tables), what distinguishes lanes -- symbol complete or not, run behind the bin or not,
+// symbols left or not -- is predication.  Measured for a warp of long streams of C5's profile
+// (profiles/r2_tree_decoder_latency.txt): the branchy step spent more cycles in BSSY / BSYNC / taken branches than in
+// the arithmetic (560 - 680 cycles per step at 0.18 instructions per cycle).
+// The stream's finish() checks are evaluated at the moment its last symbol is complete, while the window is the
+// reference decoder's.
+template <int MODE, bool RUNS>
 __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode_symbols_tree(SymParams P, uint32_t* next_stream, const uint32_t* order,
-                                                                                               const uint2* tree, TreeInfo ti) {
+                                                                                               const uint4* tree, TreeInfo ti) {
+  static_assert(WIDE_CTX_ROWS == 0, "the tree decoder addresses token slots");
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t s, n_ctx;
   WCtx ctx;
@@ -1016,25 +1062,32 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
   wide_setup(P.n_streams, P.n_ctx, P.ctx_init, 0, smem, s, ctx, tab, n_ctx);
   const LaneCtx lc{ctx, tab, n_ctx, P.ctx_init, P.per_stream_init};
   uint8_t* tp = smem + WIDE_TAB_BYTES + (size_t)(blockDim.x >> 5) * (P.n_ctx + 1) * WIDE_CTX_STRIDE;
-  for (uint32_t e = threadIdx.x; e < ti.n_nodes; e += blockDim.x) reinterpret_cast<uint2*>(tp)[e] = __ldg(tree + e);
+  for (uint32_t e = threadIdx.x; e < ti.n_nodes; e += blockDim.x) reinterpret_cast<uint4*>(tp)[e] = __ldg(tree + e);
+  // 2^32 / range for range = 256 .. 511 (decw_ep_recip), behind the tree
+  uint32_t* rcp = reinterpret_cast<uint32_t*>(tp + (size_t)ti.n_nodes * 16u);
+  if (RUNS) for (uint32_t e = threadIdx.x; e < 256u; e += blockDim.x) rcp[e] = (uint32_t)(0x100000000ull / (256u + e)) + 1u;
   __syncthreads();
   const uint32_t tree0 = (uint32_t)__cvta_generic_to_shared(tp);
-  const uint32_t var_bytes = ti.var_stride * 8u, rows = P.cfg.rows;
+  const uint32_t rcp0 = tree0 + ti.n_nodes * 16u;
+  const uint32_t ctxs = cb_keep32((uint32_t)__cvta_generic_to_shared(ctx.p));   // this lane's slot 0
+  const uint32_t rows = P.cfg.rows;
   // Decoded symbols leave through a 32-byte stage per lane: one byte store to shared memory per symbol, one 16-byte store
   // to global memory per 16 symbols (a byte store per symbol and lane is a 32-byte sector write each: at C4 that was
   // the bound of the launch, not the instruction count).  Stage position = low address bits of the symbol's place in
   // the output, so the 16-byte pieces are the aligned pieces of the output array.
-  const uint32_t stage0 = tree0 + ((ti.n_nodes * 8u + 15u) & ~15u) + ((threadIdx.x >> 5) * 32u + (threadIdx.x & 31u)) * TREE_STAGE_STRIDE;
+  const uint32_t stage0 = rcp0 + (RUNS ? 1024u : 0u) + ((threadIdx.x >> 5) * 32u + (threadIdx.x & 31u)) * TREE_STAGE_STRIDE;
   DecWide D;
   decw_start(D, P.bytes, 0);
   uint8_t* dst = nullptr;       // output position of symbol 0 of the stream
   uint32_t a0 = 0;              // low address bits of dst
   uint32_t fl = 0;              // symbols [0, fl) of the stream have been written to global memory
-  uint32_t i = 0, cnt = 0, row = 0, node = tree0, seen = 0;   // seen: OR of every child taken; bit 14 = an escape leaf was hit
+  uint32_t i = 0, cnt = 0, row = 0, seen = 0;   // seen: OR of every entry taken; bit 30 = an escape was hit
+  uint32_t fin = 0;             // the stream's finish() verdict, taken when its last symbol was complete
   bool active = false, have = s < P.n_streams;
   if (have && order) s = order[s];
-  uint2 nd = make_uint2(0u, 0u);                 // the node at `node`, loaded as soon as `node` is known
-  auto ld_node = [](uint2& v, uint32_t a) { asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); };
+  auto ld_node = [](uint4& v, uint32_t a) { asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); };
+  uint4 nd;                     // the node of the next bin
+  ld_node(nd, tree0);
   // write symbols [fl, upto) out of the stage: the aligned 16-byte piece in one store, anything else byte by byte
   auto flush = [&](uint32_t upto) {
     while (fl < upto) {
@@ -1061,62 +1114,72 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
       a0 = (uint32_t)reinterpret_cast<uintptr_t>(dst);
       const uint64_t b0 = P.byte_off[s], b1 = P.byte_off[s + 1];
       decw_start(D, P.bytes + b0, (uint32_t)(b1 - b0));
-      i = 0; fl = 0; row = 0; node = tree0; seen = 0;
-      ld_node(nd, node);
+      i = 0; fl = 0; row = 0; seen = 0;
+      ld_node(nd, tree0);
+      fin = 0;
+      if (cnt == 0) { DecWide E = D; fin = decw_finish(E); }
       active = true;
     }
     if (!__any_sync(0xffffffffu, active)) break;
+    do {       // groups of four steps until some lane has decoded its last symbol
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (active && i < cnt) {
-        // nd = the node of this bin, never a run node (a run is taken in the step of the bin that leads to it)
-        const uint32_t bin = decw_op<0>(D, nd.y & 0xffffu, ctx, tab, n_ctx);
-        uint32_t child = bin ? nd.x >> 16 : nd.x & 0xffffu;
-        seen |= child;
-        if (!(child & kLeaf)) {
-          node = tree0 + child * 8u;
-          ld_node(nd, node);
-          if (TREE_EP_RUNS && (nd.y & 0xffffu) == kTreeEpRun) {
-            // n bypass bins in one step; the window is topped up first only if the run would read unfilled bits, and
-            // afterwards so that the remaining bins of this group of four find theirs (f <= 31 <= kLazyDec - 1)
-            const uint32_t n = nd.x & 0xffffu;
-            if (D.f + (int32_t)n > 54) decw_refill(D);
-            const uint32_t q = decw_ep_bits(D, n);
-            decw_refill(D);
-            child = (nd.x >> 16) | ((nd.y >> 16) + q);
-          }
+      for (int j = 0; j < 4; ++j) {
+        const bool live = active && i < cnt;
+        // ---- one bin at node nd
+        uint32_t tok;
+        const uint32_t slot = ctxs + nd.z;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tok) : "r"(slot) : "memory");
+        const WRow rw = tab.row(tok);
+        bool is_lps;
+        const uint32_t bin = decw_bin<0>(D, nd.w != 0u, is_lps, rw);
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot), "r"(is_lps ? rw.next_lps : rw.next_mps) : "memory");
+        const uint32_t e = bin ? nd.y : nd.x;
+        const bool leaf = (int32_t)e < 0;
+        // ---- the next node: the child, or the root of the next symbol's variant -- its neighbour is this symbol,
+        // unless it starts a column (ISS, cabacEncode.m:52)
+        uint32_t off = e & 0xffffu, next_row = 0;
+        if (MODE == 2) {
+          next_row = row + 1u == rows ? 0u : row + 1u;
+          if (leaf && rows && next_row == 0u) off = 0u;
         }
-        if (child & kLeaf) {                       // the symbol is complete
-          asm volatile("st.shared.u8 [%0], %1;" :: "r"(stage0 + ((a0 + i) & 31u)), "r"(child) : "memory");
+        ld_node(nd, tree0 + off);
+        // ---- the run behind the bin (n = 0: none)
+        uint32_t q = 0;
+        if (RUNS) {
+          const uint32_t n = (e >> 24) & 0xfu;
+          // runs of more than 4 bins -- rare: large symbol values -- may need the window topped up around them; the
+          // voted top-up below is scheduled for <= 6 + 4 bits per step
+          if (__builtin_expect(n > 4u && D.f + (int32_t)n > 54, 0)) decw_refill_p(D);
+          q = decw_ep_recip(D, n, rcp0);
+          if (__builtin_expect(n > 4u, 0)) decw_refill_p(D);
+        }
+        // ---- a complete symbol
+        seen |= e;
+        if (leaf && live) {
+          asm volatile("st.shared.u8 [%0], %1;" :: "r"(stage0 + ((a0 + i) & 31u)), "r"((e >> 16) + q) : "memory");
           ++i;
-          if (MODE == 0) {
-            node = tree0;
-          } else {
-            // the next symbol's variant: its neighbour is this symbol, unless it starts a column (ISS, cabacEncode.m:52);
-            // an escape leaf (corrupt stream) carries variant bits 0x3f: clamp to the root
-            uint32_t nv = (child >> 8) & 0x3fu;
-            if (MODE == 2) {
-              if (++row == rows) row = 0;
-              if (rows && row == 0u) nv = 0u;
-            }
-            node = tree0 + (child == kEscape ? 0u : nv * var_bytes);
+          if (MODE == 2) row = next_row;
+          if (__builtin_expect(i == cnt, 0)) {         // the last one: the window is the reference decoder's right now
+            DecWide E = D;
+            fin = decw_finish(E) & (((seen >> 30) & 1u) ^ 1u);
           }
-          ld_node(nd, node);
+        }
+        // ---- window top-up, voted (cabac_wide.cuh, kLazyDec).  With runs a step consumes up to 6 + 4 bits: a lane that
+        // enters a pair of steps with f <= 34 reaches its second run with f <= 50 = 54 - 4, so the vote is every other step
+        if (RUNS) {
+          if ((j & 1) && __any_sync(0xffffffffu, D.f >= 35)) decw_refill_p(D);
+        } else {
+          if (j == 3 && __any_sync(0xffffffffu, D.f >= kLazyDec)) decw_refill_p(D);
         }
       }
-    }
-    if (__any_sync(0xffffffffu, D.f >= kLazyDec)) decw_refill(D);
-    // at most 4 symbols per group: the stage (two 16-byte pieces) never holds more than one complete aligned piece + 4
-    {
-      const bool crossed = active && (((a0 + i) ^ (a0 + fl)) & ~15u) != 0u;
-      if (__any_sync(0xffffffffu, crossed)) {
-        if (crossed) flush(i - ((a0 + i) & 15u));      // up to the last 16-byte boundary reached
-      }
-    }
+      // at most 4 symbols per group: the stage (two 16-byte pieces) never holds more than one complete aligned piece + 4
+      if (active && (((a0 + i) ^ (a0 + fl)) & ~15u) != 0u) flush(i - ((a0 + i) & 15u));      // up to the last 16-byte boundary reached
+    } while (!__any_sync(0xffffffffu, active && i >= cnt));
     if (active && i >= cnt) {
       flush(cnt);
-      if (P.finish_ok) P.finish_ok[s] = (uint8_t)(decw_finish(D) & (((seen >> 14) & 1u) ^ 1u));
+      if (P.finish_ok) P.finish_ok[s] = (uint8_t)fin;
       decw_start(D, P.bytes, 0);
+      ld_node(nd, tree0);
       active = false;
       s = gridDim.x * blockDim.x + atomicAdd(next_stream, 1u);
       have = s < P.n_streams;
@@ -1221,7 +1284,10 @@ int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
   uint32_t nw, grid;
   size_t smem;
   if (!wide_geometry(P.n_streams, P.n_ctx, nw, grid, smem)) return ISSCABAC_OK;
-  const size_t tree_b = ((size_t)ti.n_nodes * sizeof(TreeNode) + 15) & ~(size_t)15;
+  std::vector<uint4> flat;
+  bool has_runs = false;
+  flatten_tree(nodes, ti, P.n_ctx, flat, has_runs);
+  const size_t tree_b = (size_t)ti.n_nodes * sizeof(uint4) + (has_runs ? 1024 : 0);      // nodes + the reciprocal table
   const size_t lim = smem_limit();
   const size_t per_warp = ((size_t)P.n_ctx + 1) * WIDE_CTX_STRIDE + 32 * TREE_STAGE_STRIDE;
   if (WIDE_TAB_BYTES + tree_b + per_warp > lim) return ISSCABAC_OK;
@@ -1230,11 +1296,12 @@ int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
   smem = WIDE_TAB_BYTES + tree_b + per_warp * nw;
   int rc = keep_pool_cached();
   if (rc) return rc;
-  uint2* d_tree = nullptr;
-  CK(cudaMallocAsync(reinterpret_cast<void**>(&d_tree), tree_b, st));
-  CK(cudaMemcpyAsync(d_tree, nodes.data(), (size_t)ti.n_nodes * sizeof(TreeNode), cudaMemcpyHostToDevice, st));
-  auto kernel = P.cfg.profile == ISSCABAC_PROFILE_ISS ? k_decode_symbols_tree<2>
-              : P.cfg.profile == ISSCABAC_PROFILE_DEMO ? k_decode_symbols_tree<1> : k_decode_symbols_tree<0>;
+  uint4* d_tree = nullptr;
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&d_tree), flat.size() * sizeof(uint4), st));
+  CK(cudaMemcpyAsync(d_tree, flat.data(), flat.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+  auto kernel = P.cfg.profile == ISSCABAC_PROFILE_ISS ? (has_runs ? k_decode_symbols_tree<2, true> : k_decode_symbols_tree<2, false>)
+              : P.cfg.profile == ISSCABAC_PROFILE_DEMO ? (has_runs ? k_decode_symbols_tree<1, true> : k_decode_symbols_tree<1, false>)
+              : has_runs ? k_decode_symbols_tree<0, true> : k_decode_symbols_tree<0, false>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(nw * 32), smem));
