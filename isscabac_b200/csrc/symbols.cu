@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <cstdio>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/isscabac.h"
@@ -1121,60 +1122,64 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
       active = true;
     }
     if (!__any_sync(0xffffffffu, active)) break;
-    do {       // groups of four steps until some lane has decoded its last symbol
+    // One step: the bin at node nd, the run behind it, the window top-up, the symbol if one is complete.  No branch in it;
+    // LAST = this may be the stream's last symbol (then, and only then, its finish() verdict is taken -- a branch).
+    auto step = [&](auto last_tag, int j) {
+      constexpr bool LAST = decltype(last_tag)::value;
+      const bool live = LAST ? active && i < cnt : active;
+      uint32_t tok;
+      const uint32_t slot = ctxs + nd.z;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tok) : "r"(slot) : "memory");
+      const WRow rw = tab.row(tok);
+      bool is_lps;
+      const uint32_t bin = decw_bin<0>(D, nd.w != 0u, is_lps, rw);
+      asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot), "r"(is_lps ? rw.next_lps : rw.next_mps) : "memory");
+      const uint32_t e = bin ? nd.y : nd.x;
+      const bool leaf = (int32_t)e < 0;
+      // the next node: the child, or the root of the next symbol's variant -- its neighbour is this symbol, unless it
+      // starts a column (ISS, cabacEncode.m:52)
+      uint32_t off = e & 0xffffu, next_row = 0;
+      if (MODE == 2) {
+        next_row = row + 1u == rows ? 0u : row + 1u;
+        if (leaf && rows && next_row == 0u) off = 0u;
+      }
+      ld_node(nd, tree0 + off);
+      // the run behind the bin (n = 0: none), then the window top-up.  With runs: every step, unconditionally -- a lane
+      // enters a step with f <= 31, its bin takes <= 6 bits, its run <= 13 and finds f <= 37 <= 54 - 13.  Without: voted
+      // every fourth step (cabac_wide.cuh, kLazyDec).
+      uint32_t q = 0;
+      if (RUNS) {
+        q = decw_ep_recip(D, (e >> 24) & 0xfu, rcp0);
+        decw_refill_p(D);
+      } else {
+        if (j == 3 && __any_sync(0xffffffffu, D.f >= kLazyDec)) decw_refill_p(D);
+      }
+      // a complete symbol
+      seen |= e;
+      const bool sym = leaf && live;
+      if (sym) asm volatile("st.shared.u8 [%0], %1;" :: "r"(stage0 + ((a0 + i) & 31u)), "r"((e >> 16) + q) : "memory");
+      i += sym ? 1u : 0u;
+      if (MODE == 2) row = sym ? next_row : row;
+      if (LAST) {
+        if (__builtin_expect(sym && i == cnt, 0)) {       // the last one: the window is the reference decoder's right now
+          DecWide E = D;
+          fin = decw_finish(E) & (((seen >> 30) & 1u) ^ 1u);
+        }
+      }
+    };
+    for (;;) {       // groups of four steps until some lane has decoded its last symbol
+      // a group completes at most 4 symbols per lane: only when some lane is that close to its end do the steps look for it
+      if (__any_sync(0xffffffffu, active && cnt - i <= 4u)) {
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) step(std::true_type{}, j);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool live = active && i < cnt;
-        // ---- one bin at node nd
-        uint32_t tok;
-        const uint32_t slot = ctxs + nd.z;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tok) : "r"(slot) : "memory");
-        const WRow rw = tab.row(tok);
-        bool is_lps;
-        const uint32_t bin = decw_bin<0>(D, nd.w != 0u, is_lps, rw);
-        asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot), "r"(is_lps ? rw.next_lps : rw.next_mps) : "memory");
-        const uint32_t e = bin ? nd.y : nd.x;
-        const bool leaf = (int32_t)e < 0;
-        // ---- the next node: the child, or the root of the next symbol's variant -- its neighbour is this symbol,
-        // unless it starts a column (ISS, cabacEncode.m:52)
-        uint32_t off = e & 0xffffu, next_row = 0;
-        if (MODE == 2) {
-          next_row = row + 1u == rows ? 0u : row + 1u;
-          if (leaf && rows && next_row == 0u) off = 0u;
-        }
-        ld_node(nd, tree0 + off);
-        // ---- the run behind the bin (n = 0: none)
-        uint32_t q = 0;
-        if (RUNS) {
-          const uint32_t n = (e >> 24) & 0xfu;
-          // runs of more than 4 bins -- rare: large symbol values -- may need the window topped up around them; the
-          // voted top-up below is scheduled for <= 6 + 4 bits per step
-          if (__builtin_expect(n > 4u && D.f + (int32_t)n > 54, 0)) decw_refill_p(D);
-          q = decw_ep_recip(D, n, rcp0);
-          if (__builtin_expect(n > 4u, 0)) decw_refill_p(D);
-        }
-        // ---- a complete symbol
-        seen |= e;
-        if (leaf && live) {
-          asm volatile("st.shared.u8 [%0], %1;" :: "r"(stage0 + ((a0 + i) & 31u)), "r"((e >> 16) + q) : "memory");
-          ++i;
-          if (MODE == 2) row = next_row;
-          if (__builtin_expect(i == cnt, 0)) {         // the last one: the window is the reference decoder's right now
-            DecWide E = D;
-            fin = decw_finish(E) & (((seen >> 30) & 1u) ^ 1u);
-          }
-        }
-        // ---- window top-up, voted (cabac_wide.cuh, kLazyDec).  With runs a step consumes up to 6 + 4 bits: a lane that
-        // enters a pair of steps with f <= 34 reaches its second run with f <= 50 = 54 - 4, so the vote is every other step
-        if (RUNS) {
-          if ((j & 1) && __any_sync(0xffffffffu, D.f >= 35)) decw_refill_p(D);
-        } else {
-          if (j == 3 && __any_sync(0xffffffffu, D.f >= kLazyDec)) decw_refill_p(D);
-        }
+        for (int j = 0; j < 4; ++j) step(std::false_type{}, j);
       }
       // at most 4 symbols per group: the stage (two 16-byte pieces) never holds more than one complete aligned piece + 4
       if (active && (((a0 + i) ^ (a0 + fl)) & ~15u) != 0u) flush(i - ((a0 + i) & 15u));      // up to the last 16-byte boundary reached
-    } while (!__any_sync(0xffffffffu, active && i >= cnt));
+      if (__any_sync(0xffffffffu, active && i >= cnt)) break;
+    }
     if (active && i >= cnt) {
       flush(cnt);
       if (P.finish_ok) P.finish_ok[s] = (uint8_t)fin;
