@@ -397,12 +397,18 @@ CB_HD void decw_refill_p(DecWide& D) {
   uint32_t w = cb_prmt(D.cur, D.nxt, D.sel);
   D.cur = need ? D.nxt : D.cur;
   const uint32_t ld = (need && D.widx < D.wcnt) ? 1u : 0u;
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u32 %0, [%1];\n\t}" : "+r"(D.nxt) : "l"(D.wbase + D.widx), "r"(ld));
+  // The scoreboard of a load is the WARP's: whatever lane issued it, the next instruction that reads the register waits
+  // for it -- with 32 lanes topping up in turn that is the prmt above, in every step.  So the sector after the one being
+  // read is asked into L1 now (a hint: no register, no scoreboard); by the time a lane loads from it, eight top-ups
+  // later, the load is an L1 hit.
+  const uint32_t pf = (need && D.widx + 8u < D.wcnt) ? 1u : 0u;
+  asm volatile("{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %2, 0;\n\tsetp.ne.u32 r, %3, 0;\n\t@q ld.global.u32 %0, [%1];\n\t@r prefetch.global.L1 [%1+32];\n\t}"
+               : "+r"(D.nxt) : "l"(D.wbase + D.widx), "r"(ld), "r"(pf));
   D.widx += need ? 1u : 0u;
-  if (need && D.p + 4u > D.len) {             // only at the very end of a stream
-    const uint32_t rem = D.len > D.p ? D.len - D.p : 0u;
-    w = rem ? (w | (0xffffffffu >> (8u * rem))) : 0xffffffffu;
-  }
+  // end of the stream: bytes past it read as 0xFF (decw_fetch), without a branch -- rem = stream bytes left, 0 .. 4
+  const int32_t left = (int32_t)D.len - (int32_t)D.p;
+  const uint32_t rem = (uint32_t)(left < 0 ? 0 : (left > 4 ? 4 : left));
+  w |= __funnelshift_rc(0xffffffffu, 0u, 8u * rem);      // 0xffffffff >> (8 * rem), 0 for rem = 4
   w = need ? w : 0u;
   const uint32_t k = (uint32_t)D.f & 31u;     // need: f - 32 (0..23)
   D.lo |= w << k;

@@ -1169,7 +1169,8 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
     };
     for (;;) {       // groups of four steps until some lane has decoded its last symbol
       // a group completes at most 4 symbols per lane: only when some lane is that close to its end do the steps look for it
-      if (__any_sync(0xffffffffu, active && cnt - i <= 4u)) {
+      const bool careful = __any_sync(0xffffffffu, active && cnt - i <= 4u);
+      if (careful) {
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) step(std::true_type{}, j);
       } else {
@@ -1178,7 +1179,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
       }
       // at most 4 symbols per group: the stage (two 16-byte pieces) never holds more than one complete aligned piece + 4
       if (active && (((a0 + i) ^ (a0 + fl)) & ~15u) != 0u) flush(i - ((a0 + i) & 15u));      // up to the last 16-byte boundary reached
-      if (__any_sync(0xffffffffu, active && i >= cnt)) break;
+      if (careful && __any_sync(0xffffffffu, active && i >= cnt)) break;
     }
     if (active && i >= cnt) {
       flush(cnt);
