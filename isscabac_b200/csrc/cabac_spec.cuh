@@ -197,7 +197,12 @@ CB_HD void decs_block16(DecWide& D, const uint32_t cw[4], uint32_t r[4], const M
       if (CABAC_LAZY_DEC == 1 && j == 1 && D.f >= kLazyDec) decw_refill(D);
     }
     r[g] = acc;
-    if (cb_any<VOTE>(D.f >= kLazyDec)) decw_refill(D);
+    if (VOTE && CABAC_REFILL_P_LAT == 3) {
+      decw_refill_p<true>(D);
+    } else if (cb_any<VOTE>(D.f >= kLazyDec)) {
+      if (VOTE && CABAC_REFILL_P_LAT) decw_refill_p<(CABAC_REFILL_P_LAT > 1)>(D);   // cabac_wide.cuh, CABAC_REFILL_P
+      else decw_refill(D);
+    }
   }
 }
 

@@ -391,6 +391,19 @@ CB_HD void decw_refill(DecWide& D) {
 // move, long_scoreboard).  Here the new word is loaded IN PLACE by a predicated load (the asm operand is read-write, so
 // no copy can follow it) and everything else is a select.  Words past the end of the stream are not loaded; what the
 // register then holds does not matter, decw_fetch's end-of-stream rule overwrites those bytes with 0xFF.
+// CABAC_REFILL_P / CABAC_REFILL_P_LAT: the top-up behind the 16-op blocks of the op-array decoders (wide / latency
+// formulation) -- 0: voted, decw_refill (branch on the lane's fill level); 1: voted, decw_refill_p without the prefetch;
+// 2: voted, with it; 3: decw_refill_p after every group of four bins without a vote.  B200, decode of 65,536-bin streams:
+//   65,536 streams (wide kernel)   0: 7.48 ms   1: 7.23   2: 7.19   3: 7.04
+//    8,192 streams (latency kernel) 0: 5.43 ms   1: 4.98   2: 4.84   3: 5.26
+//       32 streams (latency kernel) 0: 134.7 cycles per bin   1: 127.7   2: 129.5   3: 127.6
+#ifndef CABAC_REFILL_P
+#define CABAC_REFILL_P 3
+#endif
+#ifndef CABAC_REFILL_P_LAT
+#define CABAC_REFILL_P_LAT 2
+#endif
+template <bool PF = true>
 CB_HD void decw_refill_p(DecWide& D) {
 #if defined(__CUDA_ARCH__) && !CABAC_DEC_TMA
   const bool need = D.f >= 32;
@@ -401,7 +414,7 @@ CB_HD void decw_refill_p(DecWide& D) {
   // for it -- with 32 lanes topping up in turn that is the prmt above, in every step.  So the sector after the one being
   // read is asked into L1 now (a hint: no register, no scoreboard); by the time a lane loads from it, eight top-ups
   // later, the load is an L1 hit.
-  const uint32_t pf = (need && D.widx + 8u < D.wcnt) ? 1u : 0u;
+  const uint32_t pf = (PF && need && D.widx + 8u < D.wcnt) ? 1u : 0u;
   asm volatile("{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %2, 0;\n\tsetp.ne.u32 r, %3, 0;\n\t@q ld.global.u32 %0, [%1];\n\t@r prefetch.global.L1 [%1+32];\n\t}"
                : "+r"(D.nxt) : "l"(D.wbase + D.widx), "r"(ld), "r"(pf));
   D.widx += need ? 1u : 0u;
@@ -645,7 +658,12 @@ CB_HD void decw_block16(DecWide& D, const uint32_t cw[4], uint32_t r[4],
     acc |= decw_op<2, true>(D, cb_prmt(codes, 0, 0x4442u), ctx, tab, n_ctx);
     acc |= decw_op<3, true>(D, cb_prmt(codes, 0, 0x4443u), ctx, tab, n_ctx);
     r[g] = acc;
-    if (cb_any<(VOTE && CABAC_LAZY_DEC)>(D.f >= kLazyDec)) decw_refill(D);
+    if (VOTE && CABAC_LAZY_DEC && CABAC_REFILL_P == 3) {
+      decw_refill_p<true>(D);                     // no vote: every lane holding 32 unfilled bits tops up, after every group
+    } else if (cb_any<(VOTE && CABAC_LAZY_DEC)>(D.f >= kLazyDec)) {
+      if (VOTE && CABAC_LAZY_DEC && CABAC_REFILL_P) decw_refill_p<(CABAC_REFILL_P > 1)>(D);   // the warp is here together
+      else decw_refill(D);
+    }
   }
 }
 
