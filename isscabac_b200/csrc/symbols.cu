@@ -389,6 +389,7 @@ struct SymParams {
   uint8_t* finish_ok;
   const uint4* lut;        // op strings by table (k_bin_lut) for the fused encoder, or NULL
   uint32_t lut_entries, lut_dom;
+  uint32_t pair_dom;            // ring encoder: op strings of symbol PAIRS for values below it (0: no pair table)
 };
 
 __device__ __forceinline__ uint32_t* setup_smem(const SymParams& P, uint8_t* smem, uint32_t s, bool valid) {
@@ -695,14 +696,38 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_ring(Sym
     lut8[e] = (len >= 1 && len <= 7) ? make_uint2(q.x, (q.y & 0x00ffffffu) | (len << 24)) : make_uint2(0u, 0u);
   }
   __syncthreads();
+  // Where a symbol's string depends on nothing but its value (FLAT profiles) and the alphabet is small, the strings of
+  // symbol PAIRS sit behind the single ones: 14 op bytes + length in 16 bytes, so that a refill trip expands two symbols
+  // with one LDS.128 and one append (the trip, not the coding, was the larger half of the kernel: 66 instructions per
+  // symbol against 29 per bin, profiles/r2_ring_encoder_pairs.txt).  Pairs with a string of more than 7 ops stay single.
+  constexpr bool PAIRS = PROF == PROFILE_FLAT || PROF == PROFILE_FLAT_EPSUF;
+  const uint32_t pd = PAIRS ? P.pair_dom : 0u;
+  uint4* pairs = reinterpret_cast<uint4*>(lp + ((P.lut_entries * 8u + 15u) & ~15u));
+  if (PAIRS) {
+    for (uint32_t e = threadIdx.x; e < pd * pd; e += blockDim.x) {
+      const uint2 a = lut8[e % pd], b = lut8[e / pd];
+      const uint32_t la = a.y >> 24, lb = b.y >> 24;
+      uint4 q = make_uint4(0u, 0u, 0u, 0u);
+      if (la && lb) {
+        const uint64_t A = (uint64_t)a.x | ((uint64_t)(a.y & 0x00ffffffu) << 32), B = (uint64_t)b.x | ((uint64_t)(b.y & 0x00ffffffu) << 32);
+        const uint64_t lo = A | (B << (8u * la)), hi = B >> (64u - 8u * la);
+        q = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, ((uint32_t)(hi >> 32) & 0xffffu) | ((la + lb) << 24));
+      }
+      pairs[e] = q;
+    }
+    __syncthreads();
+  }
   const uint32_t lut0 = (uint32_t)__cvta_generic_to_shared(lp);
-  const uint32_t ring0 = lut0 + ((P.lut_entries * 8u + 15u) & ~15u) + warp * RING_WARP_BYTES + lane * RING_LANE_STRIDE;
+  const uint32_t pair0 = lut0 + ((P.lut_entries * 8u + 15u) & ~15u);
+  const uint32_t ring0 = pair0 + pd * pd * 16u + warp * RING_WARP_BYTES + lane * RING_LANE_STRIDE;
 
   EncWide E;
   encw_start(E, nullptr, 0);
   const uint8_t* src = nullptr;
   uint32_t cnt = 0, si = 0, row = 0;      // symbols in the stream, symbols expanded, row of the next symbol in its column
   uint32_t curv = 0, nextv = 0;           // value of the symbol expanded last / of symbol si (loaded one symbol ahead)
+  uint32_t next2 = 0, next3 = 0, next4 = 0;   // with a pair table: the values of symbols si + 1 .. si + 3, loaded two trips ahead
+                                              // (one trip ahead the pair's table lookup waited for its symbols: 10 % of all stall samples)
   uint32_t wr = 0, buffered = 0, pw = 0;  // ring: bytes appended (mod 64 = write position), ops not yet coded, the partial word at wr
   uint32_t rd = 0;                        // ring read position (multiple of 16 until the tail)
   // a symbol whose string does not come out of the table in one piece: produced 7 ops per trip by the closed form
@@ -726,6 +751,34 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_ring(Sym
     buffered += len;
   };
 
+  // the same for the `len` (2..14) op bytes of a pair held in q.x, q.y, q.z and the low half of q.w; no branch: the lanes of
+  // a warp end on different words, so every arm would run anyway
+  auto sts_if = [&](uint32_t addr, uint32_t v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u32 [%0], %1;\n\t}" :: "r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
+  };
+  auto append_pair = [&](const uint4& q, uint32_t len) {
+    const uint32_t b8 = (wr & 3u) * 8u, d3 = q.w & 0xffffu;
+    const uint32_t t0 = pw | (q.x << b8);
+    const uint32_t t1 = cb_funnel_l(q.x, q.y, b8);
+    const uint32_t t2 = cb_funnel_l(q.y, q.z, b8);
+    const uint32_t t3 = cb_funnel_l(q.z, d3, b8);
+    const uint32_t t4 = cb_funnel_l(d3, 0u, b8);
+    const uint32_t k0 = wr & 60u, end = (wr & 3u) + len;           // <= 17
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(ring0 + k0), "r"(t0) : "memory");
+    sts_if(ring0 + ((k0 + 4u) & 60u), t1, end > 4u);
+    sts_if(ring0 + ((k0 + 8u) & 60u), t2, end > 8u);
+    sts_if(ring0 + ((k0 + 12u) & 60u), t3, end > 12u);
+    sts_if(ring0 + ((k0 + 16u) & 60u), t4, end > 16u);
+    uint32_t tl = t0;
+    tl = end >= 4u ? t1 : tl;
+    tl = end >= 8u ? t2 : tl;
+    tl = end >= 12u ? t3 : tl;
+    tl = end >= 16u ? t4 : tl;
+    pw = (end & 3u) == 0u ? 0u : tl;
+    wr += len;
+    buffered += len;
+  };
+
   for (;;) {
     if (!active && have) {               // claim the stream
       lc.reset(s);
@@ -736,6 +789,11 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_ring(Sym
       si = 0; row = 0; curv = 0; wr = 0; rd = 0; buffered = 0; pw = 0; mb = 1; mlen = 0; up = false;
       cur = SymCode{0, 0, 0}; prevc = cur;
       nextv = cnt ? src[0] : 0u;
+      if (PAIRS) {
+        next2 = cnt > 1u ? src[1] : 0u;
+        next3 = cnt > 2u ? src[2] : 0u;
+        next4 = cnt > 3u ? src[3] : 0u;
+      }
       active = true;
     }
     if (!__any_sync(0xffffffffu, active)) break;
@@ -747,11 +805,34 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_ring(Sym
       const bool must = more && buffered < 16u;
       const bool need = more && buffered < 32u;
       if (!__any_sync(0xffffffffu, must)) break;
-      if (need) {
+      bool single = need;
+      if (PAIRS) {
+        if (need && mb > mlen && si + 2u <= cnt && (nextv | next2) < 256u && nextv < pd && next2 < pd) {   // two symbols at once
+          uint4 q;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(pair0 + (nextv + next2 * pd) * 16u));
+          const uint32_t len = q.w >> 24;
+          if (len) {
+            append_pair(q, len);
+            curv = next2;
+            si += 2u;
+            nextv = next3;
+            next2 = next4;
+            if (si + 2u < cnt) next3 = src[si + 2u];
+            if (si + 3u < cnt) next4 = src[si + 3u];
+            single = false;
+          }
+        }
+      }
+      if (single) {
         if (mb > mlen) {                 // next symbol
           const uint32_t prevv = curv;
           curv = nextv;
-          if (si + 1 < cnt) nextv = src[si + 1];
+          if (PAIRS) {
+            nextv = next2;
+            next2 = next3;
+            next3 = next4;
+            if (si + 4u < cnt) next4 = src[si + 4u];
+          } else if (si + 1 < cnt) nextv = src[si + 1];
           up = has_up_row(cfg, si, row);
           ++si;
           if (++row == cfg.rows) row = 0;
@@ -1207,7 +1288,10 @@ int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char
     // the ring encoder: 8-byte op strings + one ring per lane behind the context blocks; fewer warps per CTA if needed
     const LutGeom rg = lut_geom(P.cfg.profile, P.cfg.method, P.cfg.Nq);
     if (!rg.entries) return ISSCABAC_OK;
-    const size_t lut_b = ((size_t)rg.entries * 8 + 15) & ~(size_t)15;
+    // strings of symbol pairs behind the single ones, for the profiles whose strings depend on the value alone
+    const bool pairs_ok = (P.cfg.profile == ISSCABAC_PROFILE_FLAT || P.cfg.profile == ISSCABAC_PROFILE_FLAT_EPSUF) && rg.dom <= 32u && !getenv("ISSCABAC_RING_NOPAIRS");
+    P.pair_dom = pairs_ok ? rg.dom : 0u;
+    const size_t lut_b = (((size_t)rg.entries * 8 + 15) & ~(size_t)15) + (size_t)P.pair_dom * P.pair_dom * 16;
     const size_t per_warp = ((size_t)P.n_ctx + 1) * WIDE_CTX_STRIDE + RING_WARP_BYTES;
     const size_t lim = smem_limit();
     if (WIDE_TAB_BYTES + lut_b + per_warp > lim) return ISSCABAC_OK;
