@@ -65,11 +65,16 @@ def fuzz_ops(rng):
 
 
 def fuzz_symbols(rng):
-    prof, meth, Nq, dt = [(O.PROFILE_DEMO, O.BIN_TU, 4, np.uint8), (O.PROFILE_DEMO, O.BIN_EG0, 4, np.uint8),
-                          (O.PROFILE_ISS, O.BIN_EG0, 8, np.uint8), (O.PROFILE_ISS, O.BIN_EG1, 40, np.uint16),
-                          (O.PROFILE_ISS, O.BIN_TU, 8, np.uint8), (O.PROFILE_FLAT, O.BIN_EG0, 16, np.uint8),
-                          (O.PROFILE_FLAT, O.BIN_EG2, 300, np.uint16), (O.PROFILE_FLAT_EPSUF, O.BIN_EG2, 256, np.uint8),
-                          (O.PROFILE_FLAT_EPSUF, O.BIN_EG0, 70000, np.uint32), (O.PROFILE_FLAT, O.BIN_FL32, 0, np.uint32)][int(rng.integers(0, 10))]
+    cases = [(O.PROFILE_DEMO, O.BIN_TU, 4, np.uint8), (O.PROFILE_DEMO, O.BIN_EG0, 4, np.uint8),
+             (O.PROFILE_ISS, O.BIN_EG0, 8, np.uint8), (O.PROFILE_ISS, O.BIN_EG1, 40, np.uint16),
+             (O.PROFILE_ISS, O.BIN_TU, 8, np.uint8), (O.PROFILE_FLAT, O.BIN_EG0, 16, np.uint8),
+             (O.PROFILE_FLAT, O.BIN_EG2, 300, np.uint16), (O.PROFILE_FLAT_EPSUF, O.BIN_EG2, 256, np.uint8),
+             (O.PROFILE_FLAT_EPSUF, O.BIN_EG0, 70000, np.uint32), (O.PROFILE_FLAT, O.BIN_FL32, 0, np.uint32),
+             # small alphabets of the value-only profiles: symbol PAIRS in the ring encoder (with strings too long for the
+             # pair table among them), bypass RUNS of every length in the tree decoder
+             (O.PROFILE_FLAT_EPSUF, O.BIN_EG0, 16, np.uint8), (O.PROFILE_FLAT, O.BIN_EG1, 30, np.uint8),
+             (O.PROFILE_FLAT_EPSUF, O.BIN_EG1, 200, np.uint8), (O.PROFILE_FLAT, O.BIN_TU, 7, np.uint8)]
+    prof, meth, Nq, dt = cases[int(rng.integers(0, len(cases)))]
     rows = int(rng.choice([0, 1, 7, 109])) if prof == O.PROFILE_ISS else 0
     n_streams = int(rng.choice([1, 5, 33, 300]))
     counts = rng.integers(0, int(rng.choice([2, 50, 900])), size=n_streams)
