@@ -72,6 +72,16 @@ CB_HD uint32_t cb_bswap(uint32_t x) { return cb_perm(x, 0, 0x0123); }
 #endif
 // VOTE = all 32 lanes of the warp execute this call together (the caller guarantees it: the kernels
 // walk the blocks every lane of a full warp has in lockstep); otherwise this lane decides alone
+// CABAC_EXPECT: rare branches marked as such, so that the straight path of a block has no taken branch (a taken branch or
+// the BSYNC behind it costs a lone warp 15 - 45 cycles, profiles/r2_tree_decoder_latency.txt)
+#ifndef CABAC_EXPECT
+#define CABAC_EXPECT 1
+#endif
+#if CABAC_EXPECT
+#define CB_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define CB_UNLIKELY(x) (x)
+#endif
 template <bool VOTE>
 CB_HD bool cb_any(bool p) {
 #if defined(__CUDA_ARCH__) && CABAC_LAZY
@@ -617,7 +627,7 @@ CB_HD void encw_block16(EncWide& E, const uint32_t w[4], const uint32_t cw[4],
     const uint32_t codes = cw[g];   // the four op codes, one per byte
     encw_op<0, true>(E, cb_prmt(codes, 0, 0x4440u), w[g], ctx, tab, n_ctx);
     encw_op<1, true>(E, cb_prmt(codes, 0, 0x4441u), w[g], ctx, tab, n_ctx);
-    if (E.n >= kLazy) encw_emit(E);
+    if (CB_UNLIKELY(E.n >= kLazy)) encw_emit(E);   // the guard: practically never taken, kept off the straight path
     encw_op<2, true>(E, cb_prmt(codes, 0, 0x4442u), w[g], ctx, tab, n_ctx);
     encw_op<3, true>(E, cb_prmt(codes, 0, 0x4443u), w[g], ctx, tab, n_ctx);
     if (cb_any<VOTE>(E.n >= kLazy)) encw_emit(E);

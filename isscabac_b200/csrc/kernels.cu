@@ -546,30 +546,42 @@ __global__ void __launch_bounds__(2 * SPLIT_MAX_PAIRS * 32) k_encode_ops_split(C
   for (uint32_t b = 0; b < Tmax; ++b) {
     const uint32_t st_off = (b & 1u) * SPLIT_STAGE;
     asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
+    // the whole block's sub-ranges and flags at once (eight loads in flight), and ONE vote on "some lane holds a terminate
+    // op or a position outside its stream" per block instead of one per group: a vote + branch costs a lone pair of warps
+    // as much as two bins' arithmetic (profiles/r2_tree_decoder_latency.txt, the same finding on this kernel's consumer)
+    uint32_t l[4][4], fl[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      uint32_t l0, l1, l2, l3, fl;
-      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(l0), "=r"(l1), "=r"(l2), "=r"(l3) : "r"(ring_s + st_off + g * SPLIT_GROUP) : "memory");
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(fl) : "r"(flag_s + st_off + g * SPLIT_GROUP) : "memory");
-      if (__any_sync(0xffffffffu, (fl & 0x0c0c0c0cu) != 0u)) {
-        // some lane holds a terminate op or a position outside its stream: one bin at a time
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(l[g][0]), "=r"(l[g][1]), "=r"(l[g][2]), "=r"(l[g][3]) : "r"(ring_s + st_off + g * SPLIT_GROUP) : "memory");
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(fl[g]) : "r"(flag_s + st_off + g * SPLIT_GROUP) : "memory");
+    }
+    if (__any_sync(0xffffffffu, ((fl[0] | fl[1] | fl[2] | fl[3]) & 0x0c0c0c0cu) != 0u)) {
+      // one bin at a time
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t l0, l1, l2, l3, f4;      // read again: this path is rare, the registers above are indexed at compile time only
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(l0), "=r"(l1), "=r"(l2), "=r"(l3) : "r"(ring_s + st_off + g * SPLIT_GROUP) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(f4) : "r"(flag_s + st_off + g * SPLIT_GROUP) : "memory");
         const uint32_t l4[4] = {l0, l1, l2, l3};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t f = (fl >> (8 * k)) & 0xffu;
+          const uint32_t f = (f4 >> (8 * k)) & 0xffu;
           if (f & SF_NOP) continue;
           if (f & SF_TRM) encw_trm(E, f & 1u);
           else split_bin<0>(E, l4[k], f);
           encw_emit(E);
         }
-      } else {
-        split_bin<0>(E, l0, fl);
-        split_bin<1>(E, l1, fl);
-        if (E.n >= kLazy) encw_emit(E);
-        split_bin<2>(E, l2, fl);
-        split_bin<3>(E, l3, fl);
       }
-      if (__any_sync(0xffffffffu, E.n >= kLazy)) encw_emit(E);
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        split_bin<0>(E, l[g][0], fl[g]);
+        split_bin<1>(E, l[g][1], fl[g]);
+        if (E.n >= kLazy) encw_emit(E);
+        split_bin<2>(E, l[g][2], fl[g]);
+        split_bin<3>(E, l[g][3], fl[g]);
+        if (__any_sync(0xffffffffu, E.n >= kLazy)) encw_emit(E);
+      }
     }
   }
   if (valid) {
