@@ -16,6 +16,10 @@
 
 #include "../../include/isscabac.h"
 #include "cabac_spec.cuh"
+
+#ifndef CABAC_OPS_ASYNC
+#define CABAC_OPS_ASYNC 0     // op blocks of the latency decoder through shared memory (cp.async) instead of registers
+#endif
 #include "codec_params.h"
 #include "internal.h"
 
@@ -156,12 +160,30 @@ __global__ void __launch_bounds__(LAT_MAX_WARPS * 32) k_decode_ops_lat(CodecPara
   const bool out_vec = (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
   const uint32_t common = __reduce_min_sync(vmask, (uint32_t)(nblk > 0xffffffffull ? 0xffffffffull : nblk));
   if (nblk) {
+#if CABAC_OPS_ASYNC
+    // The op blocks come in through shared memory (cp.async, two blocks ahead, four 16-byte slots per lane) instead of a
+    // register pair rotated with moves: the rotation's `cur = nxt` waited ~120 cycles per block on the load scoreboard it
+    // shares with the window top-up (a word some lane requested a moment ago), although its own load was 16 bins old.
+    const uint32_t ostage = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)LAT_TAB_BYTES + (blockDim.x >> 5) * (n_ctx + 1u) * 32u * (uint32_t)sizeof(SRow)
+                            + threadIdx.x * 64u;
+    const uint8_t* const pbase = p;
+    auto feed = [&](uint64_t blk) {
+      if (blk < nblk) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(ostage + ((uint32_t)blk & 3u) * 16u), "l"(pbase + 16ull * blk) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#endif
     uint4 cur = __ldg(reinterpret_cast<const uint4*>(p));
     uint64_t b = 0;
+#if CABAC_OPS_ASYNC
+    feed(1);
+    feed(2);
+#endif
     auto block = [&](auto lock) {
       constexpr bool LOCK = decltype(lock)::value;
+#if !CABAC_OPS_ASYNC
       uint4 nxt = cur;
       if (b + 1 < nblk) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
+#endif
       const uint32_t cw[4] = {op_codes4(cur.x), op_codes4(cur.y), op_codes4(cur.z), op_codes4(cur.w)};
       if (cb_any<LOCK>(block_has_trm(cw))) {
         for (int k = 0; k < 16; ++k) q[k] = (uint8_t)decs_general(D, p[k], mem, n_ctx);
@@ -175,9 +197,17 @@ __global__ void __launch_bounds__(LAT_MAX_WARPS * 32) k_decode_ops_lat(CodecPara
           for (int k = 0; k < 16; ++k) q[k] = (uint8_t)(r[k >> 2] >> (8 * (k & 3)));
         }
       }
+#if CABAC_OPS_ASYNC
+      p += 16;
+      q += 16;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");       // block b + 1 has landed (block b + 2 may be on its way)
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(cur.x), "=r"(cur.y), "=r"(cur.z), "=r"(cur.w) : "r"(ostage + ((uint32_t)(b + 1) & 3u) * 16u) : "memory");
+      feed(b + 3);
+#else
       cur = nxt;
       p += 16;
       q += 16;
+#endif
     };
     if (vmask == 0xffffffffu)
       for (; b < common; ++b) block(std::true_type{});
@@ -199,7 +229,7 @@ int launch_lat_codec(bool encode, const CodecParams& P, cudaStream_t st, bool& d
   if (!lim || P.n_ctx > 125 || LAT_TAB_BYTES + warp_ctx > lim) return ISSCABAC_OK;
   const uint32_t sms = (uint32_t)sm_count();
   const uint32_t tiles = (P.n_streams + 31) / 32;
-  uint32_t nw_max = (uint32_t)((lim - LAT_TAB_BYTES) / warp_ctx);
+  uint32_t nw_max = (uint32_t)((lim - LAT_TAB_BYTES) / (warp_ctx + (CABAC_OPS_ASYNC ? 32 * 64 : 0)));
   if (nw_max > LAT_MAX_WARPS) nw_max = LAT_MAX_WARPS;
   // tiles spread evenly over the SMs in whole CTAs
   const uint32_t ctas_per_sm = (tiles + sms * nw_max - 1) / (sms * nw_max);
@@ -207,7 +237,7 @@ int launch_lat_codec(bool encode, const CodecParams& P, cudaStream_t st, bool& d
   if (nw > nw_max) nw = nw_max;
   if (nw < 1) nw = 1;
   const uint32_t grid = (tiles + nw - 1) / nw;
-  const size_t smem = LAT_TAB_BYTES + warp_ctx * nw;
+  const size_t smem = LAT_TAB_BYTES + warp_ctx * nw + (CABAC_OPS_ASYNC && !encode ? (size_t)nw * 32 * 64 : 0);
   auto kernel = encode ? k_encode_ops_lat : k_decode_ops_lat;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel<<<grid, nw * 32, smem, st>>>(P);
