@@ -1008,6 +1008,19 @@ def run_b200(a):
         traffic_src = "profiles/traffic.json was captured from other kernel sources (csrc hash mismatch): re-run tools/profile_round.sh"
     except Exception:
         pass
+    # both hot kernels side by side (they are within a few per cent of each other, so which one is "dominant" can change
+    # from run to run; the decoder moves twice the bytes per bin)
+    def _traffic(name):
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                t = json.load(f)[name]
+            if t.get("csrc_hash") != hot_kernel_hash():
+                return None
+            return float(t["dram_bytes_per_launch"]) * (total_bins / float(t["bins_per_launch"]))
+        except Exception:
+            return None
+    per_kernel = {n: {"ms": m, "algorithmic_bytes": b, "achieved": b / (m * 1e-3) / 1e9, "frac": b / (m * 1e-3) / 1e9 / hbm_peak, "traffic": _traffic(n)}
+                  for n, m, b in (("k_encode_ops_wide", ms_enc, enc_bytes), ("k_decode_ops_wide", ms_dec, dec_bytes))}
     # integer-issue roofline (the binding one): algorithmic int32 ops
     sm, _, _ = (torch.cuda.get_device_properties(dev).multi_processor_count, 0, 0)
     f_sm = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
@@ -1045,7 +1058,7 @@ def run_b200(a):
         "e2e_u8_bins": e2e_u8,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                      "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                     "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
+                     "algorithmic_bytes": dom_bytes, "peak_source": peak_src, "kernels": per_kernel,
                      "note": "the path is integer-issue bound, not HBM bound: see roofline_int"},
         "roofline_int": roof_int,
         "cpu_baseline": cpu,
