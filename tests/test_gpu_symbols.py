@@ -236,3 +236,53 @@ def test_binarizer_unaligned_and_short_buffers(I, shift, short):
     assert int(op_off[-1].item()) == total
     assert (got[shift:shift + cap] == want[:cap]).all()
     assert (got[:shift] == 0xAB).all() and (got[shift + cap:] == 0xAB).all()
+
+
+@pytest.mark.parametrize("prof,meth,Nq,rows", [(O.PROFILE_FLAT_EPSUF, O.BIN_EG2, 256, 0), (O.PROFILE_FLAT, O.BIN_EG0, 16, 0),
+                                               (O.PROFILE_ISS, O.BIN_EG0, 8, 50), (O.PROFILE_DEMO, O.BIN_TU, 4, 0)])
+def test_corrupt_symbol_streams_are_decoded_without_harm(I, prof, meth, Nq, rows):
+    """A payload of random bytes (and a good payload with bytes flipped) goes through both fused decoders: the call returns,
+    every decoded symbol is a value of the alphabet, nothing outside the output is written, and the streams whose bytes were
+    replaced fail their finish() check (CABAC_ArithmeticDecoder.cpp:73-85) almost always.  The tree decoder's lanes keep
+    decoding past the end of their stream inside a step group: this is the test that what they touch stays inside the tables."""
+    rng = np.random.default_rng(77)
+    n_streams = 257
+    counts = rng.integers(0, 700, size=n_streams)
+    counts[:2] = [0, 1]
+    off = np.zeros(n_streams + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    n = int(off[-1])
+    sym = np.minimum(np.floor(rng.exponential(Nq / 6.0 + 0.5, size=n)), Nq - 1).astype(np.uint8)
+    nctx = O.num_ctx(prof, 3)
+    ci = rng.integers(0, 126, size=nctx).astype(np.uint8)
+    cfg = I.make_cfg(prof, meth, Nq, 3, ALLT, rows)
+    enc = I.encode_symbols(cfg, sym, off, ci, slab_stride=4096)
+    pay = I.compact(enc)
+    enc.check_overflow()
+    good = pay.payload.clone()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    for what in ("random", "flipped"):
+        if what == "random":
+            pay.payload.copy_(torch.randint(0, 256, good.shape, generator=g, device="cuda", dtype=torch.uint8))
+        else:
+            pay.payload.copy_(good)
+            idx = torch.randint(0, good.numel(), (good.numel() // 50 + 1,), generator=g, device="cuda")
+            pay.payload[idx] ^= 0x5A
+        for tree in ("1", "0"):
+            os.environ["ISSCABAC_SYM_TREE"] = tree
+            try:
+                guard = torch.full((n + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+                dec, ok = I.decode_symbols(cfg, pay, off, ci, sym_dtype=torch.uint8)
+                torch.cuda.synchronize()
+            finally:
+                os.environ.pop("ISSCABAC_SYM_TREE")
+            d = dec.cpu().numpy()
+            assert d.shape[0] == n
+            if tree == "1":      # the tree has no leaf outside the alphabet (an escape restarts at the root with value 0);
+                assert (d < Nq).all(), what      # the closed-form decoder returns whatever the bins spell, like the reference
+            assert int(ok.sum().item()) < n_streams, (what, tree)       # not every stream can pass with its bytes replaced
+            del guard
+    pay.payload.copy_(good)
+    dec, ok = I.decode_symbols(cfg, pay, off, ci, sym_dtype=torch.uint8)
+    assert bool(ok.all().item()) and (dec.cpu().numpy() == sym).all()
