@@ -736,26 +736,34 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_ring(Sym
   bool up = false, active = false, have = s < P.n_streams;
   if (have && order) s = order[s];
 
-  // append `len` (1..7) op bytes held in (lo, hi) -- little-endian, zero above len -- to the ring
+  auto sts_if = [&](uint32_t addr, uint32_t v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u32 [%0], %1;\n\t}" :: "r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
+  };
+  // a symbol byte loaded IN PLACE when p holds (the queue entries are read-write asm operands: no register move can follow the
+  // load and wait for it, cabac_wide.cuh decw_refill_p)
+  auto ldsym_if = [](uint32_t& dst, const uint8_t* a, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u8 %0, [%1];\n\t}" : "+r"(dst) : "l"(a), "r"((uint32_t)p));
+  };
+  // append `len` (0..7) op bytes held in (lo, hi) -- little-endian, zero above len -- to the ring; no branch, length 0
+  // changes nothing
   auto append = [&](uint32_t lo, uint32_t hi, uint32_t len) {
     const uint32_t b8 = (wr & 3u) * 8u;
     const uint32_t t0 = pw | (lo << b8);
     const uint32_t t1 = cb_funnel_l(lo, hi, b8);
     const uint32_t t2 = cb_funnel_l(hi, 0u, b8);
     const uint32_t k0 = wr & 60u, end = (wr & 3u) + len;           // bytes of the touched words that are valid afterwards
-    asm volatile("st.shared.u32 [%0], %1;" :: "r"(ring0 + k0), "r"(t0) : "memory");
-    if (end > 4u) asm volatile("st.shared.u32 [%0], %1;" :: "r"(ring0 + ((k0 + 4u) & 60u)), "r"(t1) : "memory");
-    if (end > 8u) asm volatile("st.shared.u32 [%0], %1;" :: "r"(ring0 + ((k0 + 8u) & 60u)), "r"(t2) : "memory");
-    pw = (end & 3u) == 0u ? 0u : (end < 4u ? t0 : (end < 8u ? t1 : t2));
+    sts_if(ring0 + k0, t0, len != 0u);
+    sts_if(ring0 + ((k0 + 4u) & 60u), t1, end > 4u);
+    sts_if(ring0 + ((k0 + 8u) & 60u), t2, end > 8u);
+    uint32_t tl = t0;
+    tl = end >= 4u ? t1 : tl;
+    tl = end >= 8u ? t2 : tl;
+    pw = (end & 3u) == 0u ? 0u : tl;
     wr += len;
     buffered += len;
   };
-
   // the same for the `len` (2..14) op bytes of a pair held in q.x, q.y, q.z and the low half of q.w; no branch: the lanes of
   // a warp end on different words, so every arm would run anyway
-  auto sts_if = [&](uint32_t addr, uint32_t v, bool p) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u32 [%0], %1;\n\t}" :: "r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
-  };
   auto append_pair = [&](const uint4& q, uint32_t len) {
     const uint32_t b8 = (wr & 3u) * 8u, d3 = q.w & 0xffffu;
     const uint32_t t0 = pw | (q.x << b8);
@@ -789,8 +797,8 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_ring(Sym
       si = 0; row = 0; curv = 0; wr = 0; rd = 0; buffered = 0; pw = 0; mb = 1; mlen = 0; up = false;
       cur = SymCode{0, 0, 0}; prevc = cur;
       nextv = cnt ? src[0] : 0u;
+      next2 = cnt > 1u ? src[1] : 0u;
       if (PAIRS) {
-        next2 = cnt > 1u ? src[1] : 0u;
         next3 = cnt > 2u ? src[2] : 0u;
         next4 = cnt > 3u ? src[3] : 0u;
       }
@@ -823,33 +831,38 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_symbols_ring(Sym
           }
         }
       }
-      if (single) {
-        if (mb > mlen) {                 // next symbol
-          const uint32_t prevv = curv;
-          curv = nextv;
-          if (PAIRS) {
-            nextv = next2;
-            next2 = next3;
-            next3 = next4;
-            if (si + 4u < cnt) next4 = src[si + 4u];
-          } else if (si + 1 < cnt) nextv = src[si + 1];
-          up = has_up_row(cfg, si, row);
-          ++si;
-          if (++row == cfg.rows) row = 0;
-          const uint32_t key = lut_index(cfg, P.lut_dom, curv, prevv, up);
-          uint2 e = make_uint2(0u, 0u);
-          if (key != LUT_ESC) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(lut0 + key * 8u));
-          const uint32_t len = e.y >> 24;
-          if (len) {
-            append(e.x, e.y & 0x00ffffffu, len);
-          } else {                       // not in the table in one piece: closed form, 7 ops per trip
-            prevc = sym_code(prevv, cfg.Nq, cfg.method);
-            cur = sym_code(curv, cfg.Nq, cfg.method);
-            mb = 1;
-            mlen = cur.len;
-          }
+      // ---- one symbol, the common case without a branch: the queue moves up, the string comes out of the table, a string
+      // of length 0 (lane not in this trip, symbol not in the table in one piece) appends nothing.  With a pair table the
+      // block is skipped when every lane of the trip took a pair (nearly always).
+      if (!PAIRS || __any_sync(0xffffffffu, single)) {
+        const bool fetch = single && mb > mlen;
+        const uint32_t prevv = curv;
+        curv = fetch ? nextv : curv;
+        nextv = fetch ? next2 : nextv;
+        if (PAIRS) {
+          next2 = fetch ? next3 : next2;
+          next3 = fetch ? next4 : next3;
+          ldsym_if(next4, src + si + 4u, fetch && si + 4u < cnt);
+        } else {
+          ldsym_if(next2, src + si + 2u, fetch && si + 2u < cnt);
         }
-        if (mb <= mlen) {
+        const bool upn = has_up_row(cfg, si, row);
+        up = fetch ? upn : up;
+        const uint32_t key = lut_index(cfg, P.lut_dom, curv, prevv, upn);
+        uint2 e = make_uint2(0u, 0u);
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.shared.v2.u32 {%0, %1}, [%2];\n\t}"
+                     : "+r"(e.x), "+r"(e.y) : "r"(lut0 + (key & 0x3ffu) * 8u), "r"((uint32_t)(fetch && key != LUT_ESC)));
+        const uint32_t len = e.y >> 24;
+        append(e.x, e.y & 0x00ffffffu, len);
+        si += fetch ? 1u : 0u;
+        if (cfg.rows) row = fetch ? (row + 1u == cfg.rows ? 0u : row + 1u) : row;
+        if (__builtin_expect(fetch && len == 0u, 0)) {     // not in the table in one piece: closed form, 7 ops per trip
+          prevc = sym_code(prevv, cfg.Nq, cfg.method);
+          cur = sym_code(curv, cfg.Nq, cfg.method);
+          mb = 1;
+          mlen = cur.len;
+        }
+        if (__builtin_expect(single && mb <= mlen, 0)) {
           uint32_t lo = 0, hi = 0, k = 0;
           for (; k < 7u && mb <= mlen; ++k, ++mb) {
             const int cx = select_ctx(cfg, mb, cur.np, prevc, up);
