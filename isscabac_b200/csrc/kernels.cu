@@ -934,7 +934,7 @@ int launch_codec(K kernel, const CodecParams& P, size_t smem, cudaStream_t st, c
 
 // picks the context-storage policy; allocates the global scratch when needed
 #ifndef LAT_TILES_PER_SM
-#define LAT_TILES_PER_SM 4
+#define LAT_TILES_PER_SM 0      // 0: the latency kernels run only when forced (see run_codec)
 #endif
 constexpr uint32_t kLatTilesPerSm = LAT_TILES_PER_SM;
 
@@ -963,6 +963,10 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   // kernel at 32 / 8,192 / 16,384 streams, 6.51 against 5.98 at 32,768 -- so up to kLatTilesPerSm tiles per SM.  The latency
   // ENCODER (4.63 ms) loses to the two-warp encoder (4.24 ms) and is only used when forced.  ISSCABAC_LAT=0 / 1 forces
   // the choice for both directions.
+  // Second half of round 2: with the window top-up of decw_refill_p the WIDE decoder is ahead at every size -- 3.95 / 4.52 /
+  // 4.47 / 4.99 ms against 4.33 / 4.83 / 4.80 / 6.33 ms at 32 / 8,192 / 16,384 / 32,768 streams (118.6 against 129.7 cycles per
+  // bin for a lone tile): what the latency formulation bought was the wait on the top-up's load, and it pays for it with 47
+  // instructions per bin against 37 at one ALU-pipe instruction per 2.14 cycles.  kLatTilesPerSm = 0: forced use only.
   const char* lat_env = getenv("ISSCABAC_LAT");
   const bool lat_forced = lat_env && (lat_env[0] == '0' || lat_env[0] == '1');
   const bool lat_on = lat_forced ? lat_env[0] == '1' : (!ENC && split_tiles <= kLatTilesPerSm * (uint32_t)sm_count());
