@@ -23,6 +23,8 @@ struct CodecParams {
   const uint8_t* bytes;
   uint8_t* bins;
   uint8_t* finish_ok;
+  // launch-dependent choices made by the host (run_codec)
+  uint32_t prefetch_ops;   // wide decoder: ask the op stream into L1 four blocks ahead (pays with few tiles per SM only)
 };
 
 // Latency kernels (cabac_spec.cuh) for the u8 op format.  done = false: the geometry does not fit (too many contexts for

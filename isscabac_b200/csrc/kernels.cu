@@ -631,6 +631,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, WIDE_DEC_MINBLOCKS) k_dec
   const uint32_t tail = (uint32_t)((n - head) & 15u);
   const bool out_vec = (reinterpret_cast<uintptr_t>(q) & 15u) == 0;  // true whenever ops and bins share their alignment
   // lockstep blocks first, like the encoder
+  const bool pf_ops = P.prefetch_ops != 0u;
   const uint32_t common = __reduce_min_sync(vmask, (uint32_t)(nblk > 0xffffffffull ? 0xffffffffull : nblk));
   if (nblk) {
     uint4 cur = __ldg(reinterpret_cast<const uint4*>(p));
@@ -639,6 +640,12 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, WIDE_DEC_MINBLOCKS) k_dec
       constexpr bool LOCK = decltype(lock)::value;
       uint4 nxt = cur;
       if (b + 1 < nblk) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
+      // The op-block load and the window top-up's word share a load scoreboard: a top-up two groups into the block waited for
+      // the block's own next-op load when that went to DRAM (ncu, lone tile: 78 + 52 + 14 cycles per block on the top-ups'
+      // first instruction, 78 on the rotation's move).  Asking the op stream into L1 four blocks ahead makes that load an L1
+      // hit.  With few tiles per SM only (run_codec): 8,192 streams 4.43 -> 4.21 ms, 16,384 4.47 -> 4.24, but 65,536 7.05 ->
+      // 7.24 (the encoders gain nothing at any size).
+      if (pf_ops && b + 6 < nblk) asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 16 + 64));
       const uint32_t cw[4] = {op_codes4(cur.x), op_codes4(cur.y), op_codes4(cur.z), op_codes4(cur.w)};
       if (cb_any<LOCK>(block_has_trm(cw))) {
         for (int k = 0; k < 16; ++k) q[k] = (uint8_t)decw_general(D, p[k], ctx, tab, n_ctx);
@@ -937,6 +944,10 @@ int launch_codec(K kernel, const CodecParams& P, size_t smem, cudaStream_t st, c
 #define LAT_TILES_PER_SM 0      // 0: the latency kernels run only when forced (see run_codec)
 #endif
 constexpr uint32_t kLatTilesPerSm = LAT_TILES_PER_SM;
+#ifndef PF_OPS_TILES_PER_SM
+#define PF_OPS_TILES_PER_SM 8
+#endif
+constexpr uint32_t kPrefetchOpsTilesPerSm = PF_OPS_TILES_PER_SM;   // the wide decoder's op-stream prefetch (k_decode_ops_wide)
 
 template <bool ENC>
 int run_codec(CodecParams P, int op_width, cudaStream_t st) {
@@ -997,6 +1008,7 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   }
   if (op_width == 1 && wide_geometry(P.n_streams, P.n_ctx, nw, grid, wsmem)) {
     auto kernel = ENC ? k_encode_ops_wide : k_decode_ops_wide;
+    P.prefetch_ops = (!ENC && split_tiles <= kPrefetchOpsTilesPerSm * (uint32_t)sm_count()) ? 1u : 0u;
 #if CABAC_DEC_TMA
     if (!ENC) wsmem += (size_t)nw * 32 * (kTmaLaneStride + 16);     // rings + mbarriers of the bulk-copy experiment
 #endif
