@@ -300,6 +300,27 @@ def pcie_bandwidth(torch, dev, nbytes=1 << 30):
     return res
 
 
+def pcie_bandwidth_concurrent(torch, dist, dev, world, nbytes=1 << 30):
+    """All ranks copy host -> device AT THE SAME TIME (they share the host's PCIe root complexes and DRAM): aggregate and
+    per-rank bandwidth, the roof the e2e numbers at N > 1 are read against."""
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    del h, d
+    agg = world * 4 * nbytes / dt / 1e9
+    return {"h2d_aggregate": agg, "h2d_per_rank": agg / world, "ranks": world}
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -864,6 +885,7 @@ def run_b200(a):
     if not a.no_e2e:
         numa = bind_to_gpu_numa(local)
         pcie = pcie_bandwidth(torch, dev)
+        pcie_all = pcie_bandwidth_concurrent(torch, dist, dev, world) if world > 1 else None
         h_ops = torch.empty(total_bins, dtype=torch.uint8, pin_memory=True)
         h_ops.copy_(ops)
         h_off = np.arange(S + 1, dtype=np.uint64) * np.uint64(B)
@@ -914,6 +936,10 @@ def run_b200(a):
             # the roof of the call pair: its host-to-device bytes at the measured H2D bandwidth (the larger direction)
             e["pcie_gbs_measured"] = pcie
             e["frac_of_pcie"] = (e["h2d_bytes_per_step"] / (e["ms_per_step"] * 1e-3) / 1e9) / pcie["h2d"]
+            if pcie_all:
+                # N > 1: every rank moves its bytes through the same host; the roof is what the ranks reach copying together
+                e["pcie_gbs_all_ranks_concurrent"] = pcie_all
+                e["frac_of_pcie_concurrent"] = (e["h2d_bytes_per_step"] / (e["ms_per_step"] * 1e-3) / 1e9) / pcie_all["h2d_per_rank"]
         e2e["numa"] = numa
         e2e["note"] = ("host buffers in, host buffers out, every copy inside the timed calls; PCIe-bound: frac_of_pcie = achieved "
                        "host-to-device GB/s over the H2D bandwidth measured in this run (at N > 1 the ranks share the host's PCIe / DRAM)")
