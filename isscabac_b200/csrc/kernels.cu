@@ -648,6 +648,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, WIDE_DEC_MINBLOCKS) k_dec
       if (pf_ops && b + 6 < nblk) asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 16 + 64));
       const uint32_t cw[4] = {op_codes4(cur.x), op_codes4(cur.y), op_codes4(cur.z), op_codes4(cur.w)};
       if (cb_any<LOCK>(block_has_trm(cw))) {
+        if (LOCK && CABAC_REFILL_P == 3 && CABAC_REFILL_FIRST) decw_refill(D);
         for (int k = 0; k < 16; ++k) q[k] = (uint8_t)decw_general(D, p[k], ctx, tab, n_ctx);
       } else {
         uint32_t r[4];
@@ -663,8 +664,10 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, WIDE_DEC_MINBLOCKS) k_dec
       p += 16;
       q += 16;
     };
-    if (vmask == 0xffffffffu)
+    if (vmask == 0xffffffffu) {
       for (; b < common; ++b) block(std::true_type{});
+      if (CABAC_REFILL_P == 3 && CABAC_REFILL_FIRST) decw_refill(D);
+    }
     for (; b < nblk; ++b) block(std::false_type{});
   }
   for (uint32_t i = 0; i < tail; ++i) q[i] = (uint8_t)decw_general(D, p[i], ctx, tab, n_ctx);

@@ -261,3 +261,29 @@ def test_host_buffer_api_packed_bins(I, ragged):
     assert (np.unpackbits(bp, bitorder="little")[:n] == bins).all()
     if n % 8:    # padding bits of the last byte are zero
         assert (np.unpackbits(bp, bitorder="little")[n:] == 0).all()
+
+
+def test_worst_case_window_growth_on_device(I, enc_kernel):
+    """Every bin an LPS on a context parked at state 60..62 -- six shift bits per bin, the most the tables allow -- in FULL
+    warps of equally long streams, i.e. through the lockstep 16-op blocks with their voted / unvoted emissions and top-ups:
+    the encoder's early-emit guard and the decoder's look-ahead budget at their limits (the host emulation runs the same
+    input through the per-lane schedule, tests/test_wide_emulation.py::test_wide_worst_case_growth).  A mix of worst-case
+    and ordinary streams in one warp as well: the votes see both."""
+    n_ctx, n_ops, n_streams = 120, 4000, 96
+    rng = np.random.default_rng(61)
+    ctx_seq = (np.arange(n_ops) % n_ctx).astype(np.uint8)
+    off = (np.arange(n_streams + 1) * n_ops).astype(np.uint64)
+    for state in (62, 61, 60):
+        ci = np.zeros((n_streams, n_ctx), dtype=np.uint8)
+        ops = np.zeros(n_streams * n_ops, dtype=np.uint8)
+        for s in range(n_streams):
+            hot = s < 64 or s % 3 == 0          # two warps of worst-case streams, a third warp with a few among ordinary ones
+            ci[s] = ((state << 1) | 1) if hot else rng.integers(0, 126, size=n_ctx)
+            bins = np.zeros(n_ops, dtype=np.uint8) if hot else (rng.random(n_ops) < 0.4).astype(np.uint8)
+            ops[s * n_ops:(s + 1) * n_ops] = (ctx_seq << 1) | bins
+        s_ref, l_ref = O.encode_ops(ops, off, ci, out_stride=8192, n_threads=8)
+        slab, lens, payload, boff, bins_g, ok = gpu_roundtrip(I, ops, off, ci, stride=8192)
+        assert (lens == l_ref).all(), state
+        live = np.arange(8192)[None, :] < l_ref[:, None]
+        assert (slab[live] == s_ref[live]).all(), state
+        assert ok.all() and (bins_g == (ops & 1)).all(), state
