@@ -430,9 +430,12 @@ CB_HD void decw_refill_p(DecWide& D) {
   // for it -- with 32 lanes topping up in turn that is the prmt above, in every step.  So the sector after the one being
   // read is asked into L1 now (a hint: no register, no scoreboard); by the time a lane loads from it, eight top-ups
   // later, the load is an L1 hit.
-  const uint32_t pf = (PF && need && D.widx + 8u < D.wcnt) ? 1u : 0u;
-  asm volatile("{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %2, 0;\n\tsetp.ne.u32 r, %3, 0;\n\t@q ld.global.u32 %0, [%1];\n\t@r prefetch.global.L1 [%1+32];\n\t}"
-               : "+r"(D.nxt) : "l"(D.wbase + D.widx), "r"(ld), "r"(pf));
+#ifndef CABAC_PF_DIST
+#define CABAC_PF_DIST 8      // words ahead of the one being loaded: the next sector
+#endif
+  const uint32_t pf = (PF && CABAC_PF_DIST && need && D.widx + CABAC_PF_DIST < D.wcnt) ? 1u : 0u;
+  asm volatile("{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %2, 0;\n\tsetp.ne.u32 r, %3, 0;\n\t@q ld.global.u32 %0, [%1];\n\t@r prefetch.global.L1 [%4];\n\t}"
+               : "+r"(D.nxt) : "l"(D.wbase + D.widx), "r"(ld), "r"(pf), "l"(D.wbase + D.widx + CABAC_PF_DIST));
   D.widx += need ? 1u : 0u;
   // end of the stream: bytes past it read as 0xFF (decw_fetch), without a branch -- rem = stream bytes left, 0 .. 4
   const int32_t left = (int32_t)D.len - (int32_t)D.p;
