@@ -768,10 +768,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_u32_u64(const uint32_t* i
 // One warp per stream: copy lengths[s] bytes from the 16-byte aligned slab row to an
 // arbitrarily aligned payload position.  Destination-aligned 32-bit words are built from
 // two aligned source words with a funnel shift, so every store is a full, coalesced word.
+constexpr uint64_t kCompactShortRow = 2048;   // slab stride up to which a row is copied by 8 lanes
+// G lanes per stream: a whole warp for long rows; 8 lanes for short ones (C4: 2^20 rows of ~270 bytes -- with a warp per row the
+// launch is bound by how many rows are in flight, three dependent loads each, not by bandwidth: 0.48 -> see DESIGN.md 3.2)
+template <int G>
 __global__ void __launch_bounds__(256) k_compact_copy(const uint8_t* slab, uint64_t stride, const uint32_t* lengths,
                                                        const uint64_t* off, uint8_t* payload, uint64_t cap,
                                                        uint32_t n_streams, uint32_t* overflow) {
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;      // "warp" = the row's lane group
   if (warp >= n_streams) return;
   uint32_t len = lengths[warp];
   if (len > stride) len = (uint32_t)stride;
@@ -792,17 +796,17 @@ __global__ void __launch_bounds__(256) k_compact_copy(const uint8_t* slab, uint6
   const uint32_t sh = 8 * head;  // source byte offset of destination word 0 is `head` (0..3)
   // four independent word pairs in flight per lane: the copy is bound by the loads a warp keeps outstanding
   uint32_t w = lane;
-  for (; w + 96 < nwords; w += 128) {
+  for (; w + 3 * G < nwords; w += 4 * G) {
     uint32_t lo[4], hi[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      lo[k] = sw[w + 32 * k];
-      hi[k] = sh ? sw[w + 32 * k + 1] : 0u;   // sw[.. + 1] stays inside the slab row: head > 0 => bytes remain
+      lo[k] = sw[w + G * k];
+      hi[k] = sh ? sw[w + G * k + 1] : 0u;   // sw[.. + 1] stays inside the slab row: head > 0 => bytes remain
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dw[w + 32 * k] = sh ? __funnelshift_r(lo[k], hi[k], sh) : lo[k];
+    for (int k = 0; k < 4; ++k) dw[w + G * k] = sh ? __funnelshift_r(lo[k], hi[k], sh) : lo[k];
   }
-  for (; w < nwords; w += 32) {
+  for (; w < nwords; w += G) {
     uint32_t lo = sw[w], hi = sh ? sw[w + 1] : 0u;
     dw[w] = sh ? __funnelshift_r(lo, hi, sh) : lo;
   }
@@ -1142,9 +1146,13 @@ extern "C" int cabac_compact(uint32_t n_streams, const uint8_t* d_slab, uint64_t
   }
   int rc = exclusive_scan_u32_u64(d_lengths, d_byte_off, n_streams, d_scratch, st);
   if (rc || n_streams == 0 || !d_payload) return rc;
-  uint32_t blocks = (uint32_t)(((uint64_t)n_streams * 32 + 255) / 256);
-  k_compact_copy<<<blocks, 256, 0, st>>>(d_slab, slab_stride, d_lengths, d_byte_off, d_payload, payload_cap,
-                                         n_streams, d_overflow);
+  if (slab_stride <= kCompactShortRow) {      // short rows: 8 lanes per row, four times the rows in flight
+    const uint32_t blocks = (uint32_t)(((uint64_t)n_streams * 8 + 255) / 256);
+    k_compact_copy<8><<<blocks, 256, 0, st>>>(d_slab, slab_stride, d_lengths, d_byte_off, d_payload, payload_cap, n_streams, d_overflow);
+  } else {
+    const uint32_t blocks = (uint32_t)(((uint64_t)n_streams * 32 + 255) / 256);
+    k_compact_copy<32><<<blocks, 256, 0, st>>>(d_slab, slab_stride, d_lengths, d_byte_off, d_payload, payload_cap, n_streams, d_overflow);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_compact_copy");
 }

@@ -112,10 +112,11 @@ struct PeerList {
 // k_compact_copy (kernels.cu) with several destinations: one warp per local stream reads its slab row once and stores
 // it at the stream's GLOBAL byte offset into the assembled payload of every rank.  All destinations are 256-byte
 // aligned allocations, so the destination-word alignment -- and with it the funnel shift -- is the same for all of them.
+template <int G>      // lanes per row, as k_compact_copy
 __global__ void __launch_bounds__(256) k_compact_copy_peers(const uint8_t* slab, uint64_t stride, const uint32_t* lengths,
                                                              const uint64_t* off, PeerList dsts, int n_dst, uint64_t cap,
                                                              uint32_t n_streams, uint32_t* overflow) {
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
   if (warp >= n_streams) return;
   uint32_t len = lengths[warp];
   if (len > stride) len = (uint32_t)stride;
@@ -136,20 +137,20 @@ __global__ void __launch_bounds__(256) k_compact_copy_peers(const uint8_t* slab,
     for (int d = 0; d < n_dst; ++d) dsts.p[d][d0 + lane] = b;
   }
   uint32_t w = lane;
-  for (; w + 96 < nwords; w += 128) {
+  for (; w + 3 * G < nwords; w += 4 * G) {
     uint32_t v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const uint32_t lo = sw[w + 32 * k], hi = sh ? sw[w + 32 * k + 1] : 0u;
+      const uint32_t lo = sw[w + G * k], hi = sh ? sw[w + G * k + 1] : 0u;
       v[k] = sh ? __funnelshift_r(lo, hi, sh) : lo;
     }
     for (int d = 0; d < n_dst; ++d) {
       uint32_t* dw = reinterpret_cast<uint32_t*>(dsts.p[d] + d0 + head);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) dw[w + 32 * k] = v[k];
+      for (int k = 0; k < 4; ++k) dw[w + G * k] = v[k];
     }
   }
-  for (; w < nwords; w += 32) {
+  for (; w < nwords; w += G) {
     const uint32_t lo = sw[w], hi = sh ? sw[w + 1] : 0u;
     const uint32_t v = sh ? __funnelshift_r(lo, hi, sh) : lo;
     for (int d = 0; d < n_dst; ++d) reinterpret_cast<uint32_t*>(dsts.p[d] + d0 + head)[w] = v;
@@ -365,9 +366,15 @@ int cabac_multi_gpu_compact_p2p(isscabac_mgpu* mg, const uint32_t* h_first, cons
   PeerList pl;
   // the own buffer first, then the peers starting behind this rank (spreads the NVLink targets over the ranks)
   for (int k = 0; k < mg->world; ++k) pl.p[k] = mg->sym_peer[(mg->rank + k) % mg->world];
-  const uint32_t blocks = (uint32_t)(((uint64_t)n_local * 32 + 255) / 256);
-  k_compact_copy_peers<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_slab, slab_stride, d_local_lengths, d_byte_off + h_first[mg->rank], pl, mg->world, mg->sym_bytes, n_local, d_overflow);
+  if (slab_stride <= 2048) {       // short rows: 8 lanes per row (kernels.cu, kCompactShortRow)
+    const uint32_t blocks = (uint32_t)(((uint64_t)n_local * 8 + 255) / 256);
+    k_compact_copy_peers<8><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_slab, slab_stride, d_local_lengths, d_byte_off + h_first[mg->rank], pl, mg->world, mg->sym_bytes, n_local, d_overflow);
+  } else {
+    const uint32_t blocks = (uint32_t)(((uint64_t)n_local * 32 + 255) / 256);
+    k_compact_copy_peers<32><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_slab, slab_stride, d_local_lengths, d_byte_off + h_first[mg->rank], pl, mg->world, mg->sym_bytes, n_local, d_overflow);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_compact_copy_peers");
 }
