@@ -127,7 +127,12 @@ uint64_t cabac_slab_stride_bound(uint64_t max_ops_per_stream);
 
 /* Stream s is d_bytes[byte_off[s] .. byte_off[s+1]); the op array gives the kind of
  * every bin (bit 0 ignored); d_bins[i] = decoded bin of op i.  d_finish_ok[s]
- * (optional) = 1 when Decoder::finish()'s two checks hold (Decoder.cpp:75-81). */
+ * (optional) = 1 when Decoder::finish()'s two checks hold (Decoder.cpp:75-81).
+ * The decoders (this one and cabac_decode_symbols) read d_bytes in ALIGNED 32-bit words:
+ * the word that holds the last payload byte is read whole, so up to 3 bytes behind
+ * byte_off[n_streams] must be readable (their values are never used; every CUDA
+ * allocation is a multiple of 256 bytes, so a device buffer of exactly the payload's
+ * size qualifies -- compute-sanitizer's memcheck wants the size rounded up to 4). */
 int cabac_decode_ops(uint32_t n_streams, const uint64_t* d_byte_off, const uint8_t* d_bytes,
                      const uint64_t* d_op_off, const void* d_ops, int op_width,
                      const uint8_t* d_ctx_init, uint32_t n_ctx, int per_stream_init,

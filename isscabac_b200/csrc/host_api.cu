@@ -263,7 +263,7 @@ int cabac_encode_ops_host(uint32_t n_streams, const uint64_t* h_op_off, const vo
       set_error("payload needs %llu bytes, capacity %llu", (unsigned long long)total_bytes, (unsigned long long)payload_cap);
       return ISSCABAC_ERR_OVERFLOW;
     }
-    if ((rc = d_payload.alloc(total_bytes, s0))) return rc;
+    if ((rc = d_payload.alloc((total_bytes + 3) & ~(size_t)3, s0))) return rc;
     rc = cabac_compact(n_streams, d_slab.as<uint8_t>(), stride, d_len.as<uint32_t>(), d_payload.as<uint8_t>(), total_bytes,
                        d_boff.as<uint64_t>(), d_scr.p, d_flag.as<uint32_t>(), s0);
     if (rc) return rc;
@@ -461,7 +461,7 @@ int cabac_encode_symbols_host(const isscabac_symcfg* cfg, uint32_t n_streams, co
       set_error("payload needs %llu bytes, capacity %llu", (unsigned long long)total_bytes, (unsigned long long)payload_cap);
       return ISSCABAC_ERR_OVERFLOW;
     }
-    if ((rc = d_payload.alloc(total_bytes, s0))) return rc;
+    if ((rc = d_payload.alloc((total_bytes + 3) & ~(size_t)3, s0))) return rc;
     rc = cabac_compact(n_streams, d_slab.as<uint8_t>(), stride, d_len.as<uint32_t>(), d_payload.as<uint8_t>(), total_bytes,
                        d_boff.as<uint64_t>(), d_scr.p, d_flag.as<uint32_t>(), s0);
     if (rc) return rc;

@@ -146,7 +146,9 @@ def compact(enc: Encoded, payload_cap: int | None = None, *, payload: torch.Tens
             check(L.cabac_compact(C.c_uint32(n), vp(enc.slab), C.c_uint64(enc.slab.shape[1]), vp(enc.lengths),
                                   None, C.c_uint64(0), vp(byte_off), vp(scratch), vp(enc.overflow), _stream_ptr()))
             payload_cap = int(byte_off[-1].item())
-        payload = torch.empty(max(int(payload_cap), 1), dtype=torch.uint8, device=dev)
+        # the decoders read the payload in aligned 32-bit words (include/isscabac.h): the allocation covers the word that
+        # holds the last byte, the tensor handed out is the exact size
+        payload = torch.empty((max(int(payload_cap), 1) + 3) & ~3, dtype=torch.uint8, device=dev)[:max(int(payload_cap), 1)]
     check(L.cabac_compact(C.c_uint32(n), vp(enc.slab), C.c_uint64(enc.slab.shape[1]), vp(enc.lengths),
                           vp(payload), C.c_uint64(payload.numel()), vp(byte_off), vp(scratch), vp(enc.overflow),
                           _stream_ptr()))

@@ -106,7 +106,7 @@ def assemble_payload(local_payload: torch.Tensor, table: GlobalTable, group=None
     (NCCL runs them in order on its stream; over NVSwitch each is a full-bandwidth one-to-all)."""
     rank, world = _world(group)
     total = int(table.byte_off[-1].item()) if table.byte_off.numel() else 0
-    out = torch.empty(max(total, 1), dtype=torch.uint8, device=local_payload.device)
+    out = torch.empty((max(total, 1) + 3) & ~3, dtype=torch.uint8, device=local_payload.device)[:max(total, 1)]
     mine = table.rank_bytes[rank]
     out[table.rank_base[rank]: table.rank_base[rank] + mine] = local_payload[:mine]
     if world > 1:
@@ -268,7 +268,7 @@ def encode_ops_sharded(ops_local, op_off_local, ctx_init, group=None, assemble: 
     if assemble and fused_p2p:
         # capacity: host-known bound (2 bits per op is never reached by adaptive CABAC; the kernel flags an excess)
         rb_total = int(byte_off[-1].item())
-        full_buf = mg.symmetric_alloc(max(rb_total, 16))
+        full_buf = mg.symmetric_alloc((max(rb_total, 16) + 3) & ~3)      # whole 32-bit words: the decoders read the payload in them
         mg.compact_p2p(first, enc, byte_off)
         mg.barrier()
         pay = E.Payload(full_buf[int(byte_off[int(first[rank])].item()): int(byte_off[int(first[rank + 1])].item())],
@@ -279,7 +279,7 @@ def encode_ops_sharded(ops_local, op_off_local, ctx_init, group=None, assemble: 
         pay = E.compact(enc)
         if assemble:
             total = int(byte_off[-1].item())
-            full = torch.empty(max(total, 1), dtype=torch.uint8, device=enc.slab.device)
+            full = torch.empty((max(total, 1) + 3) & ~3, dtype=torch.uint8, device=enc.slab.device)[:max(total, 1)]
             rbf = [int(x) for x in mg.assemble(first, byte_off, pay.payload, full)]
             full = full[:total]
         else:
