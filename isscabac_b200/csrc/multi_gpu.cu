@@ -366,7 +366,10 @@ int cabac_multi_gpu_compact_p2p(isscabac_mgpu* mg, const uint32_t* h_first, cons
   PeerList pl;
   // the own buffer first, then the peers starting behind this rank (spreads the NVLink targets over the ranks)
   for (int k = 0; k < mg->world; ++k) pl.p[k] = mg->sym_peer[(mg->rank + k) % mg->world];
-  if (slab_stride <= 2048) {       // short rows: 8 lanes per row (kernels.cu, kCompactShortRow)
+  // A warp per row whatever the row length: the local copy gains from 8 lanes per short row (kernels.cu), the peer stores do not --
+  // 32-byte store groups over NVLink instead of 128-byte ones: C4 on 8 GPUs 1.81 -> 2.15 ms with 8 lanes (profiles/r2_v15_bench_n8.json)
+  // (a single rank has no peer: 8 lanes per short row like the local copy)
+  if (mg->world == 1 && slab_stride <= 2048) {
     const uint32_t blocks = (uint32_t)(((uint64_t)n_local * 8 + 255) / 256);
     k_compact_copy_peers<8><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         d_slab, slab_stride, d_local_lengths, d_byte_off + h_first[mg->rank], pl, mg->world, mg->sym_bytes, n_local, d_overflow);
