@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <cstdio>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -1015,7 +1016,11 @@ constexpr uint32_t TREE_MAX_NODES = 4096;
 #endif
 constexpr uint32_t TREE_STAGE_STRIDE = 48;     // 32-byte output stage per lane + 16 B (bank spread, keeps 16-byte alignment)
 
-struct TreeInfo { uint32_t n_nodes, var_stride; };   // var_stride: nodes per variant (variant v's root = node v * var_stride)
+struct TreeInfo {
+  uint32_t n_nodes, var_stride;   // var_stride: nodes per variant (variant v's root = node v * var_stride)
+  uint32_t first0;                // lane g of this launch starts with the stream at position first0 + g of the order
+  uint32_t claim_base;            // the work counter hands out positions claim_base, claim_base + 1, ...
+};
 
 // host: is the subtree below node `at` a complete tree of bypass nodes over consecutive values with one next variant?
 static bool tree_ep_complete(const std::vector<TreeNode>& t, uint32_t at, uint32_t& depth, uint32_t& base, uint32_t& nv) {
@@ -1100,6 +1105,8 @@ static bool build_code_tree(const isscabac_symcfg& c, std::vector<TreeNode>& nod
     }
   info.n_nodes = stride * n_var;
   info.var_stride = stride;
+  info.first0 = 0;
+  info.claim_base = 0;
   return true;
 }
 
@@ -1149,7 +1156,10 @@ static void flatten_tree(const std::vector<TreeNode>& nodes, const TreeInfo& ti,
 // the arithmetic (560 - 680 cycles per step at 0.18 instructions per cycle).
 // The stream's finish() checks are evaluated at the moment its last symbol is complete, while the window is the
 // reference decoder's.
-template <int MODE, bool RUNS>
+// SOLO: the same code as a second function, for the lone CTA of launch_sym_tree (a function's shared-memory attribute -- and
+// with it the L1 / shared-memory split of the SMs it runs on -- belongs to the function: raising it for the lone CTA on the one
+// function cost the main launch 9 % at C4)
+template <int MODE, bool RUNS, bool SOLO = false>
 __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode_symbols_tree(SymParams P, uint32_t* next_stream, const uint32_t* order,
                                                                                                const uint4* tree, TreeInfo ti) {
   static_assert(WIDE_CTX_ROWS == 0, "the tree decoder addresses token slots");
@@ -1181,6 +1191,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
   uint32_t fl = 0;              // symbols [0, fl) of the stream have been written to global memory
   uint32_t i = 0, cnt = 0, row = 0, seen = 0;   // seen: OR of every entry taken; bit 30 = an escape was hit
   uint32_t fin = 0;             // the stream's finish() verdict, taken when its last symbol was complete
+  s += ti.first0;
   bool active = false, have = s < P.n_streams;
   if (have && order) s = order[s];
   auto ld_node = [](uint4& v, uint32_t a) { asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); };
@@ -1288,7 +1299,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
       decw_start(D, P.bytes, 0);
       ld_node(nd, tree0);
       active = false;
-      s = gridDim.x * blockDim.x + atomicAdd(next_stream, 1u);
+      s = ti.claim_base + atomicAdd(next_stream, 1u);
       have = s < P.n_streams;
       if (have && order) s = order[s];
     }
@@ -1386,6 +1397,37 @@ int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, name);
 }
 
+constexpr unsigned kSoloHeadStartNs = 30000;
+__global__ void k_hold(unsigned ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(1000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+
+// a high-priority stream and a fork / join event pair per device for the lone CTA of launch_sym_tree
+static std::mutex g_solo_mutex;
+static int solo_stream(cudaStream_t* ss, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) {
+  constexpr int kDevs = 64;
+  static cudaStream_t s_stream[kDevs] = {};
+  static cudaEvent_t s_fork[kDevs] = {}, s_join[kDevs] = {};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kDevs) { set_error("device index out of range"); return ISSCABAC_ERR_CUDA; }
+  std::lock_guard<std::mutex> lock(g_solo_mutex);
+  if (!s_stream[dev]) {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&s_stream[dev], cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&s_fork[dev], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s_join[dev], cudaEventDisableTiming));
+  }
+  *ss = s_stream[dev]; *ev_fork = s_fork[dev]; *ev_join = s_join[dev];
+  return ISSCABAC_OK;
+}
+
 int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
   done = false;
   std::vector<TreeNode> nodes;
@@ -1412,6 +1454,9 @@ int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
   auto kernel = P.cfg.profile == ISSCABAC_PROFILE_ISS ? (has_runs ? k_decode_symbols_tree<2, true> : k_decode_symbols_tree<2, false>)
               : P.cfg.profile == ISSCABAC_PROFILE_DEMO ? (has_runs ? k_decode_symbols_tree<1, true> : k_decode_symbols_tree<1, false>)
               : has_runs ? k_decode_symbols_tree<0, true> : k_decode_symbols_tree<0, false>;
+  auto kernel_solo = P.cfg.profile == ISSCABAC_PROFILE_ISS ? (has_runs ? k_decode_symbols_tree<2, true, true> : k_decode_symbols_tree<2, false, true>)
+                   : P.cfg.profile == ISSCABAC_PROFILE_DEMO ? (has_runs ? k_decode_symbols_tree<1, true, true> : k_decode_symbols_tree<1, false, true>)
+                   : has_runs ? k_decode_symbols_tree<0, true, true> : k_decode_symbols_tree<0, false, true>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(nw * 32), smem));
@@ -1428,8 +1473,53 @@ int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
     k_order_hist<<<blocks, 256, 0, st>>>(P.sym_off, P.n_streams, hist);
     k_order_scatter<<<blocks, 256, 0, st>>>(P.sym_off, P.n_streams, hist, hist + ORDER_BUCKETS, order);
   }
-  kernel<<<grid, nw * 32, smem, st>>>(P, counter, order, d_tree, ti);
-  cudaError_t e = cudaGetLastError();
+  // More streams than lanes, i.e. lanes will claim further streams, longest first: the launch ends with its longest streams'
+  // serial chains, and while there is other work those chains share their SM with 31 busy warps and advance at less than half
+  // their speed (C5 on one GPU: 3.5 ms of such sharing in front of a 6.9 ms chain).  So the 128 longest streams get an SM of
+  // their own: a second launch of the same kernel, ONE CTA of four warps (one per scheduler) that asks for all of the SM's shared
+  // memory, on a high-priority stream beside the main launch, which runs on the other SMs.  Both take further streams from the
+  // same counter, so the lone CTA is not idle when its own streams are short.
+  // OPT-IN (ISSCABAC_TREE_SOLO=1), not the default: C5 decode 9.0 -> 7.2 ms every time it was measured, but with equally long
+  // streams (C4) the same call took 5.2, 6.5, 16.6 and 57 ms in four runs, and kernels launched after it were slow as well --
+  // the lone CTA's shared-memory configuration differs from every other kernel's, and what that does to the SMs' L1 / shared
+  // split between launches was not pinned down (profiles/r2_tree_solo_experiment.txt).
+  const char* solo_env = getenv("ISSCABAC_TREE_SOLO");
+  const bool solo = order && sm_count() > 8 && solo_env && solo_env[0] == '1';
+  cudaError_t e;
+  if (solo) {
+    constexpr uint32_t kSoloWarps = 4, kSoloLanes = kSoloWarps * 32;
+    cudaStream_t ss;
+    cudaEvent_t ev_fork, ev_join;
+    if ((rc = solo_stream(&ss, &ev_fork, &ev_join))) return rc;
+    const uint32_t grid_b = (uint32_t)(per_sm > 0 ? per_sm : 1) * ((uint32_t)sm_count() - 1u);
+    TreeInfo ta = ti, tb = ti;
+    ta.first0 = 0;
+    tb.first0 = kSoloLanes;
+    ta.claim_base = tb.claim_base = kSoloLanes + grid_b * nw * 32;
+    CK(cudaFuncSetAttribute(kernel_solo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+    {
+      std::lock_guard<std::mutex> lock(g_solo_mutex);      // the two events are shared by the calls of a device
+      // The lone CTA needs an EMPTY SM: it has to be placed before the main launch's CTAs spread over all of them, and the
+      // main launch, straight behind the ordering kernels in its own stream, is pending a few microseconds before the side
+      // stream has seen its event (then the lone CTA starts when the first SM drains and the call takes 9.7 instead of 7.1
+      // ms; an event wait on the main stream did not change the order reliably).  A one-thread kernel holds the main stream
+      // back for kSoloHeadStartNs.
+      CK(cudaEventRecord(ev_fork, st));
+      CK(cudaStreamWaitEvent(ss, ev_fork, 0));
+      kernel_solo<<<1, kSoloLanes, lim, ss>>>(P, counter, order, d_tree, ta);
+      e = cudaGetLastError();
+      CK(cudaEventRecord(ev_join, ss));
+      k_hold<<<1, 1, 0, st>>>(kSoloHeadStartNs);
+      kernel<<<grid_b, nw * 32, smem, st>>>(P, counter, order, d_tree, tb);
+      if (e == cudaSuccess) e = cudaGetLastError();
+      CK(cudaStreamWaitEvent(st, ev_join, 0));
+    }
+  } else {
+    ti.first0 = 0;
+    ti.claim_base = grid * nw * 32;
+    kernel<<<grid, nw * 32, smem, st>>>(P, counter, order, d_tree, ti);
+    e = cudaGetLastError();
+  }
   if (order) cudaFreeAsync(order, st);
   cudaFreeAsync(d_tree, st);
   done = true;
@@ -1587,7 +1677,7 @@ int cabac_decode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const u
                          void* d_symbols, int sym_width, uint8_t* d_finish_ok, void* stream) {
   if (cfg && getenv("ISSCABAC_DEBUG_TREE")) {
     std::vector<TreeNode> nodes;
-    TreeInfo ti{0, 0};
+    TreeInfo ti{0, 0, 0, 0};
     const bool ok = build_code_tree(*cfg, nodes, ti);
     uint32_t n_ep = 0;
     for (const TreeNode& nd : nodes) n_ep += nd.code == kTreeEpRun;
