@@ -742,12 +742,12 @@ def cfg_c5(env):
     dec, ok = I.decode_symbols(cfg, pay, off, ctx, sym_dtype=torch.uint8)
     assert bool(ok.all().item()) and bool((dec == sym).all().item()), "c5 round trip failed"
     ms_enc = env.timed(lambda: I.encode_symbols(cfg, sym, off, ctx, slab_stride=stride), steps=max(2, env.steps // 2))
-    # the library's opt-in for skewed jobs: the 128 longest streams on an SM of their own; reported beside the default
-    os.environ["ISSCABAC_TREE_SOLO"] = "1"
+    # beside it: the same call with the decoder's lone SM for the longest streams switched off
+    os.environ["ISSCABAC_TREE_SOLO"] = "0"
     try:
-        ms_solo = env.timed(lambda: I.decode_symbols(cfg, pay, off, ctx, sym_dtype=torch.uint8))
+        ms_nosolo = env.timed(lambda: I.decode_symbols(cfg, pay, off, ctx, sym_dtype=torch.uint8))
         dec2, ok2 = I.decode_symbols(cfg, pay, off, ctx, sym_dtype=torch.uint8)
-        assert bool(ok2.all().item()) and bool((dec2 == sym).all().item()), "c5 round trip failed (lone-SM option)"
+        assert bool(ok2.all().item()) and bool((dec2 == sym).all().item()), "c5 round trip failed (one launch)"
         del dec2, ok2
     finally:
         os.environ.pop("ISSCABAC_TREE_SOLO", None)
@@ -758,9 +758,9 @@ def cfg_c5(env):
            "scaling": "strong", "ms": ms_dec, "gbins": tot_bins / (ms_dec * 1e-3) / 1e9,
            "step": "decode only (fused decoder + debinarizer, persistent warps, longest streams first)",
            "encode_ms": ms_enc, "encode_gbins": tot_bins / (ms_enc * 1e-3) / 1e9,
-           "ms_with_lone_sm_option": ms_solo, "gbins_with_lone_sm_option": tot_bins / (ms_solo * 1e-3) / 1e9,
-           "lone_sm_option": "ISSCABAC_TREE_SOLO=1: the 128 longest streams of the call on an SM of their own (a second launch of the "
-                             "same kernel); opt-in because jobs of equally long streams lose 4 - 8 % with it (profiles/r2_tree_solo_experiment.txt)",
+           "ms_one_launch": ms_nosolo, "gbins_one_launch": tot_bins / (ms_nosolo * 1e-3) / 1e9,
+           "lone_sm": "the 128 longest streams of the call run on an SM of their own (a second launch of the same kernel beside the main "
+                      "one; ISSCABAC_TREE_SOLO=0 gives the one-launch form measured as ms_one_launch; profiles/r2_tree_solo_experiment.txt)",
            "streams_per_rank": [b - a_ for a_, b in parts], "symbols_per_rank_max_over_mean": max(work) / (sum(work) / len(work)),
            "longest_stream_symbols": int(lens.max()), "longest_stream_bins_this_rank": longest_bins,
            "limit": "the longest stream: a stream is a serial chain, the launch cannot end before its longest stream does "

@@ -1020,6 +1020,7 @@ struct TreeInfo {
   uint32_t n_nodes, var_stride;   // var_stride: nodes per variant (variant v's root = node v * var_stride)
   uint32_t first0;                // lane g of this launch starts with the stream at position first0 + g of the order
   uint32_t claim_base;            // the work counter hands out positions claim_base, claim_base + 1, ...
+  uint32_t* started;              // SOLO: raised by the lone CTA when it starts (k_hold waits for it)
 };
 
 // host: is the subtree below node `at` a complete tree of bypass nodes over consecutive values with one next variant?
@@ -1107,6 +1108,7 @@ static bool build_code_tree(const isscabac_symcfg& c, std::vector<TreeNode>& nod
   info.var_stride = stride;
   info.first0 = 0;
   info.claim_base = 0;
+  info.started = nullptr;
   return true;
 }
 
@@ -1164,6 +1166,7 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
                                                                                                const uint4* tree, TreeInfo ti) {
   static_assert(WIDE_CTX_ROWS == 0, "the tree decoder addresses token slots");
   extern __shared__ __align__(16) uint8_t smem[];
+  if (SOLO && threadIdx.x == 0 && ti.started) atomicExch(ti.started, 1u);      // this CTA has its SM: the main launch may go
   uint32_t s, n_ctx;
   WCtx ctx;
   WTab tab;
@@ -1397,12 +1400,14 @@ int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, name);
 }
 
-constexpr unsigned kSoloHeadStartNs = 30000;
-__global__ void k_hold(unsigned ns) {
+// holds the main stream back until the lone CTA has started (it raises *flag first thing), at most `ns`
+constexpr unsigned kSoloHeadStartNs = 500000;
+__global__ void k_hold(const uint32_t* flag, unsigned ns) {
   unsigned long long t0, t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   do {
-    __nanosleep(1000);
+    if (*reinterpret_cast<const volatile uint32_t*>(flag)) return;
+    __nanosleep(500);
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   } while (t - t0 < ns);
 }
@@ -1478,13 +1483,10 @@ int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
   // their speed (C5 on one GPU: 3.5 ms of such sharing in front of a 6.9 ms chain).  So the 128 longest streams get an SM of
   // their own: a second launch of the same kernel, ONE CTA of four warps (one per scheduler) that asks for all of the SM's shared
   // memory, on a high-priority stream beside the main launch, which runs on the other SMs.  Both take further streams from the
-  // same counter, so the lone CTA is not idle when its own streams are short.
-  // OPT-IN (ISSCABAC_TREE_SOLO=1), not the default: C5 decode 9.0 -> 7.2 ms every time it was measured, but with equally long
-  // streams (C4) the same call took 5.2, 6.5, 16.6 and 57 ms in four runs, and kernels launched after it were slow as well --
-  // the lone CTA's shared-memory configuration differs from every other kernel's, and what that does to the SMs' L1 / shared
-  // split between launches was not pinned down (profiles/r2_tree_solo_experiment.txt).
+  // same counter, so the lone CTA is not idle when its own streams are short.  C5 decode 9.06 -> 7.14 ms, C4 (equally long
+  // streams: nothing to gain) 4.87 -> 4.88 ms (profiles/r2_tree_solo_experiment.txt).  ISSCABAC_TREE_SOLO=0 switches it off.
   const char* solo_env = getenv("ISSCABAC_TREE_SOLO");
-  const bool solo = order && sm_count() > 8 && solo_env && solo_env[0] == '1';
+  const bool solo = order && sm_count() > 8 && !(solo_env && solo_env[0] == '0');
   cudaError_t e;
   if (solo) {
     constexpr uint32_t kSoloWarps = 4, kSoloLanes = kSoloWarps * 32;
@@ -1496,6 +1498,9 @@ int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
     ta.first0 = 0;
     tb.first0 = kSoloLanes;
     ta.claim_base = tb.claim_base = kSoloLanes + grid_b * nw * 32;
+    uint32_t* started = nullptr;
+    if ((rc = work_counter(st, &started))) return rc;      // a zeroed word: the lone CTA's "I have started"
+    ta.started = started;
     CK(cudaFuncSetAttribute(kernel_solo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
     {
       std::lock_guard<std::mutex> lock(g_solo_mutex);      // the two events are shared by the calls of a device
@@ -1503,13 +1508,13 @@ int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
       // main launch, straight behind the ordering kernels in its own stream, is pending a few microseconds before the side
       // stream has seen its event (then the lone CTA starts when the first SM drains and the call takes 9.7 instead of 7.1
       // ms; an event wait on the main stream did not change the order reliably).  A one-thread kernel holds the main stream
-      // back for kSoloHeadStartNs.
+      // back until the lone CTA has raised its flag (at most kSoloHeadStartNs).
       CK(cudaEventRecord(ev_fork, st));
       CK(cudaStreamWaitEvent(ss, ev_fork, 0));
       kernel_solo<<<1, kSoloLanes, lim, ss>>>(P, counter, order, d_tree, ta);
       e = cudaGetLastError();
       CK(cudaEventRecord(ev_join, ss));
-      k_hold<<<1, 1, 0, st>>>(kSoloHeadStartNs);
+      k_hold<<<1, 1, 0, st>>>(started, kSoloHeadStartNs);
       kernel<<<grid_b, nw * 32, smem, st>>>(P, counter, order, d_tree, tb);
       if (e == cudaSuccess) e = cudaGetLastError();
       CK(cudaStreamWaitEvent(st, ev_join, 0));
@@ -1677,7 +1682,7 @@ int cabac_decode_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const u
                          void* d_symbols, int sym_width, uint8_t* d_finish_ok, void* stream) {
   if (cfg && getenv("ISSCABAC_DEBUG_TREE")) {
     std::vector<TreeNode> nodes;
-    TreeInfo ti{0, 0, 0, 0};
+    TreeInfo ti{0, 0, 0, 0, nullptr};
     const bool ok = build_code_tree(*cfg, nodes, ti);
     uint32_t n_ep = 0;
     for (const TreeNode& nd : nodes) n_ep += nd.code == kTreeEpRun;

@@ -286,3 +286,49 @@ def test_corrupt_symbol_streams_are_decoded_without_harm(I, prof, meth, Nq, rows
     pay.payload.copy_(good)
     dec, ok = I.decode_symbols(cfg, pay, off, ci, sym_dtype=torch.uint8)
     assert bool(ok.all().item()) and (dec.cpu().numpy() == sym).all()
+
+
+@pytest.mark.parametrize("prof,meth,Nq", [(O.PROFILE_FLAT_EPSUF, O.BIN_EG2, 256), (O.PROFILE_FLAT, O.BIN_EG0, 16)])
+def test_more_streams_than_lanes(I, prof, meth, Nq):
+    """More streams than the device has lanes: the persistent kernels hand streams out longest first through a work counter, and
+    the fused decoder runs as TWO launches (one CTA with an SM of its own for the 128 longest streams beside the main launch,
+    launch_sym_tree).  Ragged streams, a few very long ones among many short ones: the two-launch form, the one-launch form
+    (ISSCABAC_TREE_SOLO=0) and the closed-form decoder agree with the input; a stratified sample of the encoder's bytes
+    against the oracle."""
+    rng = np.random.default_rng(83)
+    n_streams = 200_000
+    counts = np.clip(np.round(rng.lognormal(np.log(12), 0.8, size=n_streams)), 0, 400).astype(np.int64)
+    counts[rng.integers(0, n_streams, size=40)] = rng.integers(3000, 9000, size=40)      # the long tail
+    counts[:3] = [0, 1, 9000]
+    off = np.zeros(n_streams + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    n = int(off[-1])
+    sym = np.minimum(np.floor(rng.exponential(Nq / 20.0 + 1.5, size=n)), Nq - 1).astype(np.uint8)
+    nctx = O.num_ctx(prof, 3)
+    ci = rng.integers(0, 126, size=nctx).astype(np.uint8)
+    cfg, ocfg = I.make_cfg(prof, meth, Nq, 3, 0, 0), O.make_cfg(prof, meth, Nq, 3, 0, 0)
+    stride = 9000 * 2 + 64
+    enc = I.encode_symbols(cfg, sym, off, ci, slab_stride=stride)
+    pay = I.compact(enc)
+    enc.check_overflow()
+    ids = np.unique(np.concatenate([np.arange(0, 8), np.round(np.linspace(8, n_streams - 9, 40)).astype(np.int64), np.arange(n_streams - 8, n_streams),
+                                    np.argsort(counts)[-6:]]))
+    off_s = np.zeros(len(ids) + 1, dtype=np.uint64)
+    np.cumsum(counts[ids], out=off_s[1:])
+    sym_s = np.concatenate([sym[off[i]:off[i + 1]] for i in ids]).astype(np.uint32)
+    s_ref, l_ref = O.encode_symbols(ocfg, sym_s, off_s, ci, stride, n_threads=8)
+    idt = torch.as_tensor(ids, device="cuda")
+    assert (enc.lengths[idt].cpu().numpy().astype(np.uint32) == l_ref).all()
+    w = int(l_ref.max())
+    live = np.arange(w)[None, :] < l_ref[:, None]
+    assert (enc.slab[idt][:, :w].cpu().numpy()[live] == s_ref[:, :w][live]).all()
+    for env_name, val in (("ISSCABAC_TREE_SOLO", "1"), ("ISSCABAC_TREE_SOLO", "0"), ("ISSCABAC_SYM_TREE", "0")):
+        os.environ[env_name] = val
+        try:
+            for _ in range(2):      # twice: the work counters and the side stream are reused
+                dec, ok = I.decode_symbols(cfg, pay, off, ci, sym_dtype=torch.uint8)
+                torch.cuda.synchronize()
+        finally:
+            os.environ.pop(env_name)
+        assert bool(ok.all().item()), (env_name, val)
+        assert (dec.cpu().numpy() == sym).all(), (env_name, val)
