@@ -1309,6 +1309,32 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, TREE_MIN_BLOCKS) k_decode
   }
 }
 
+// The op-string table of a configuration (k_bin_lut), computed once per (configuration, device) and kept: like the code
+// tree, a fixed cost of every small call otherwise.  own = true: the cache is full, the table belongs to this call (free it).
+constexpr size_t kTreeCacheMax = 64;     // entries of the per-configuration caches (op-string tables, code trees); nothing is evicted
+struct LutCacheEntry { isscabac_symcfg cfg; int dev; uint4* lut; };
+static std::mutex g_lut_cache_mutex;
+static std::vector<LutCacheEntry> g_lut_cache;
+static int cached_lut(const isscabac_symcfg& cfg, uint32_t entries, cudaStream_t st, uint4** lut, bool* own) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  *own = false;
+  std::lock_guard<std::mutex> lock(g_lut_cache_mutex);
+  for (const LutCacheEntry& e : g_lut_cache)
+    if (e.dev == dev && memcmp(&e.cfg, &cfg, sizeof cfg) == 0) { *lut = e.lut; return ISSCABAC_OK; }
+  if (g_lut_cache.size() >= kTreeCacheMax) {
+    CK(cudaMallocAsync(reinterpret_cast<void**>(lut), entries * sizeof(uint4), st));
+    k_bin_lut<<<(entries + 127) / 128, 128, 0, st>>>(cfg, *lut);
+    *own = true;
+    return ISSCABAC_OK;
+  }
+  CK(cudaMalloc(reinterpret_cast<void**>(lut), entries * sizeof(uint4)));
+  k_bin_lut<<<(entries + 127) / 128, 128, 0, st>>>(cfg, *lut);
+  CK(cudaStreamSynchronize(st));      // once: any stream may read it from now on
+  g_lut_cache.push_back(LutCacheEntry{cfg, dev, *lut});
+  return ISSCABAC_OK;
+}
+
 // persistent launch: as many warps as the streams need, at most what is resident on the device
 template <class K>
 int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char* name, bool& done, bool want_lut = false,
@@ -1335,8 +1361,8 @@ int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char
     int rc = keep_pool_cached();
     if (rc) return rc;
     uint4* lut = nullptr;
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&lut), rg.entries * sizeof(uint4), st));
-    k_bin_lut<<<(rg.entries + 127) / 128, 128, 0, st>>>(P.cfg, lut);
+    bool lut_own = false;
+    if ((rc = cached_lut(P.cfg, rg.entries, st, &lut, &lut_own))) return rc;
     P.lut = lut; P.lut_entries = rg.entries; P.lut_dom = rg.dom;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -1357,7 +1383,7 @@ int launch_sym_wide(K kernel, const SymParams& P_in, cudaStream_t st, const char
     kernel<<<grid, nw * 32, smem, st>>>(P, counter, order);
     cudaError_t e = cudaGetLastError();
     if (order) cudaFreeAsync(order, st);
-    cudaFreeAsync(lut, st);
+    if (lut_own) cudaFreeAsync(lut, st);
     done = true;
     return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, name);
   }
@@ -1433,17 +1459,60 @@ static int solo_stream(cudaStream_t* ss, cudaEvent_t* ev_fork, cudaEvent_t* ev_j
   return ISSCABAC_OK;
 }
 
+// The flattened tree of a configuration, built and copied to the device once per (configuration, context count, device): a call
+// on a small job is a few hundred microseconds, of which building the tree on the host, a stream-ordered allocation and a copy
+// from pageable memory were a noticeable part.  A handful of configurations per process; beyond kTreeCacheMax a call uploads its own.
+struct TreeCacheEntry {
+  isscabac_symcfg cfg;
+  uint32_t n_ctx;
+  int dev;
+  bool covered, has_runs;
+  TreeInfo ti;
+  uint4* d_tree;
+};
+static std::mutex g_tree_cache_mutex;
+static std::vector<TreeCacheEntry> g_tree_cache;
+
+// `spill`: filled instead of out.d_tree when the cache is full (the caller then uploads it for this call only)
+static int cached_tree(const isscabac_symcfg& cfg, uint32_t n_ctx, TreeCacheEntry& out, std::vector<uint4>& spill) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_tree_cache_mutex);
+  for (const TreeCacheEntry& e : g_tree_cache)
+    if (e.dev == dev && e.n_ctx == n_ctx && memcmp(&e.cfg, &cfg, sizeof cfg) == 0) { out = e; return ISSCABAC_OK; }
+  TreeCacheEntry e;
+  memset(&e, 0, sizeof e);
+  e.cfg = cfg; e.n_ctx = n_ctx; e.dev = dev;
+  std::vector<TreeNode> nodes;
+  e.covered = build_code_tree(cfg, nodes, e.ti);
+  const bool full = g_tree_cache.size() >= kTreeCacheMax;      // nothing is ever evicted: an entry may be in use by another thread's launch
+  if (e.covered) {
+    std::vector<uint4> flat;
+    flatten_tree(nodes, e.ti, n_ctx, flat, e.has_runs);
+    if (full) {
+      spill.swap(flat);
+    } else {
+      CK(cudaMalloc(reinterpret_cast<void**>(&e.d_tree), flat.size() * sizeof(uint4)));
+      CK(cudaMemcpy(e.d_tree, flat.data(), flat.size() * sizeof(uint4), cudaMemcpyHostToDevice));   // synchronous: any stream may use it next
+    }
+  }
+  if (!full) g_tree_cache.push_back(e);
+  out = e;
+  return ISSCABAC_OK;
+}
+
 int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
   done = false;
-  std::vector<TreeNode> nodes;
-  TreeInfo ti;
-  if (!build_code_tree(P.cfg, nodes, ti)) return ISSCABAC_OK;
+  TreeCacheEntry tc;
+  std::vector<uint4> spill;
+  int rc = cached_tree(P.cfg, P.n_ctx, tc, spill);
+  if (rc) return rc;
+  if (!tc.covered) return ISSCABAC_OK;
+  TreeInfo ti = tc.ti;
+  const bool has_runs = tc.has_runs;
   uint32_t nw, grid;
   size_t smem;
   if (!wide_geometry(P.n_streams, P.n_ctx, nw, grid, smem)) return ISSCABAC_OK;
-  std::vector<uint4> flat;
-  bool has_runs = false;
-  flatten_tree(nodes, ti, P.n_ctx, flat, has_runs);
   const size_t tree_b = (size_t)ti.n_nodes * sizeof(uint4) + (has_runs ? 1024 : 0);      // nodes + the reciprocal table
   const size_t lim = smem_limit();
   const size_t per_warp = ((size_t)P.n_ctx + 1) * WIDE_CTX_STRIDE + 32 * TREE_STAGE_STRIDE;
@@ -1451,11 +1520,14 @@ int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
   const uint32_t nw_fit = (uint32_t)((lim - WIDE_TAB_BYTES - tree_b) / per_warp);
   if (nw > nw_fit) { nw = nw_fit; grid = ((P.n_streams + 31) / 32 + nw - 1) / nw; }
   smem = WIDE_TAB_BYTES + tree_b + per_warp * nw;
-  int rc = keep_pool_cached();
-  if (rc) return rc;
-  uint4* d_tree = nullptr;
-  CK(cudaMallocAsync(reinterpret_cast<void**>(&d_tree), flat.size() * sizeof(uint4), st));
-  CK(cudaMemcpyAsync(d_tree, flat.data(), flat.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+  if ((rc = keep_pool_cached())) return rc;
+  const uint4* d_tree = tc.d_tree;
+  uint4* d_own = nullptr;
+  if (!d_tree) {      // cache full: this call's own copy
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&d_own), spill.size() * sizeof(uint4), st));
+    CK(cudaMemcpyAsync(d_own, spill.data(), spill.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+    d_tree = d_own;
+  }
   auto kernel = P.cfg.profile == ISSCABAC_PROFILE_ISS ? (has_runs ? k_decode_symbols_tree<2, true> : k_decode_symbols_tree<2, false>)
               : P.cfg.profile == ISSCABAC_PROFILE_DEMO ? (has_runs ? k_decode_symbols_tree<1, true> : k_decode_symbols_tree<1, false>)
               : has_runs ? k_decode_symbols_tree<0, true> : k_decode_symbols_tree<0, false>;
@@ -1526,7 +1598,7 @@ int launch_sym_tree(const SymParams& P, cudaStream_t st, bool& done) {
     e = cudaGetLastError();
   }
   if (order) cudaFreeAsync(order, st);
-  cudaFreeAsync(d_tree, st);
+  if (d_own) cudaFreeAsync(d_own, st);
   done = true;
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_decode_symbols_tree");
 }
