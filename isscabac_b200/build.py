@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libisscabac.so")
 SOURCES = ["kernels.cu", "kernels_lat.cu", "symbols.cu", "iss_stats.cu", "stats.cu", "quantize.cu", "multi_gpu.cu", "host_api.cu", "handle.cu", "dispatch.cpp", "container.cpp"]
-HEADERS = ["cabac_lane.cuh", "cabac_wide.cuh", "cabac_spec.cuh", "wide_common.cuh", "internal.h", "codec_params.h", os.path.join("..", "..", "include", "isscabac.h"),
+HEADERS = ["cabac_lane.cuh", "cabac_wide.cuh", "cabac_spec.cuh", "wide_common.cuh", "bin_emit.cuh", "internal.h", "codec_params.h", os.path.join("..", "..", "include", "isscabac.h"),
            os.path.join("..", "..", "include", "SimpleCABAC.hpp")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--shared", "-cudart", "shared", "--threads", "0", "-ldl"]

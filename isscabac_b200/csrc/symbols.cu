@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/isscabac.h"
+#include "bin_emit.cuh"
 #include "cabac_lane.cuh"
 #include "internal.h"
 #include "wide_common.cuh"
@@ -152,11 +153,21 @@ __device__ __forceinline__ uint32_t find_stream(const uint64_t* sym_off, uint32_
 // binary search per thread, all tiles in parallel -- inside k_bin_emit the same search would be one
 // thread walking 20 dependent loads while the other 255 of its CTA wait
 __global__ void k_bin_tile_streams(const uint64_t* sym_off, uint32_t n_streams, uint64_t n, uint32_t n_tiles,
-                                   uint32_t* tile_stream) {
+                                   uint32_t* tile_stream, uint32_t* tile_first) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n_tiles) return;
   const uint64_t i = t < n_tiles ? (uint64_t)t * BIN_TILE : n - 1;
   tile_stream[t] = find_stream(sym_off, 0, n_streams, i);
+  // tile_first[t] = the first entry of sym_off[0 .. n_streams] that is >= the tile's first symbol (>= n for slot n_tiles):
+  // the streams -- empty ones too -- that START in tile t are [tile_first[t], tile_first[t + 1]), and the entries from
+  // tile_first[n_tiles] on are the empty streams at the very end and the total
+  const uint64_t x = t < n_tiles ? (uint64_t)t * BIN_TILE : n;
+  uint32_t lo = 0, hi = n_streams;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (sym_off[mid] >= x) hi = mid; else lo = mid + 1;
+  }
+  tile_first[t] = lo;
 }
 
 // Op strings by table.  For the alphabets the applications use, the ops of a symbol -- bins AND
@@ -167,60 +178,21 @@ __global__ void k_bin_tile_streams(const uint64_t* sym_off, uint32_t n_streams, 
 // sym_bin); the emit kernel then fetches ops with one byte load each.  Entry = 15 op bytes + the
 // length; symbols outside the table (value beyond its domain, more than 15 bins) take the
 // closed-form route op by op.
-constexpr uint32_t LUT_MAX = 1024, LUT_ESC = 0xffffu;
-struct LutGeom { uint32_t dom, entries; };
-__host__ __device__ inline LutGeom lut_geom(int profile, int method, uint32_t Nq) {
-  if (method == BIN_FL32) return LutGeom{0u, 0u};
-  const uint32_t nq = Nq ? Nq : 256u;
-  if (profile == PROFILE_ISS) { const uint32_t d = nq < 31u ? nq : 31u; return LutGeom{d, d * (d + 1u)}; }
-  const uint32_t d = nq < 256u ? nq : 256u;
-  return LutGeom{d, profile == PROFILE_DEMO ? 3u * d : d};
-}
-// key of a symbol: v = its value, u = the value of its neighbour, has_up = the neighbour exists
-__device__ __forceinline__ uint32_t lut_index(const SymCfg& cfg, uint32_t dom, uint32_t v, uint32_t u, bool has_up) {
-  if (v >= dom) return LUT_ESC;
-  if (cfg.profile == PROFILE_ISS) return (has_up && u >= dom) ? LUT_ESC : v * (dom + 1u) + (has_up ? u + 1u : 0u);
-  if (cfg.profile == PROFILE_DEMO) return v + dom * (has_up ? (sym_code(u, cfg.Nq, cfg.method).np > 1u ? 1u : 2u) : 0u);
-  return v;
-}
+// (LUT_MAX, lut_geom, lut_index, lut_entry: bin_emit.cuh, shared with the host emulation)
 __global__ void k_bin_lut(isscabac_symcfg c, uint4* lut) {
   const SymCfg cfg = to_cfg(c);
   const LutGeom g = lut_geom(cfg.profile, cfg.method, cfg.Nq);
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.entries) return;
-  uint32_t v, u = 0;
-  bool has_up = false;
-  SymCode uc = {0, 0, 0};
-  if (cfg.profile == PROFILE_ISS) {
-    v = e / (g.dom + 1u);
-    const uint32_t r = e % (g.dom + 1u);
-    has_up = r != 0;
-    u = has_up ? r - 1u : 0u;
-    uc = sym_code(u, cfg.Nq, cfg.method);
-  } else if (cfg.profile == PROFILE_DEMO) {
-    v = e % g.dom;
-    const uint32_t t = e / g.dom;
-    has_up = t != 0;
-    uc = SymCode{1u, t == 1 ? 2u : 1u, 0u};      // only the neighbour's first bin matters: 1 (np > 1) or 0 (np == 1)
-  } else {
-    v = e;
-  }
-  const SymCode code = sym_code(v, cfg.Nq, cfg.method);
-  uint32_t w[4] = {0u, 0u, 0u, 0u};
-  if (code.len <= 15u) {
-    for (uint32_t b = 1; b <= code.len; ++b) {
-      const int cx = select_ctx(cfg, b, code.np, uc, has_up);
-      const uint32_t cd = cx < 0 ? ISSCABAC_OP8_EP : (uint32_t)cx;
-      const uint32_t byte = (cd << 1) | sym_bin(code, b);
-      const uint32_t at = b - 1u;
-      if (at < 4) w[0] |= byte << (8 * at);
-      else if (at < 8) w[1] |= byte << (8 * (at - 4));
-      else if (at < 12) w[2] |= byte << (8 * (at - 8));
-      else w[3] |= byte << (8 * (at - 12));
-    }
-    w[3] |= code.len << 24;
-  }
+  uint32_t w[4];
+  lut_entry(cfg, e, w);
   lut[e] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+// bin count of every 8-bit symbol value (the u8 kernels sum and scan table entries instead of evaluating the closed form)
+__global__ void k_bin_lentab(isscabac_symcfg c, uint16_t* len_tab) {
+  const SymCfg cfg = to_cfg(c);
+  const uint32_t l = sym_code(threadIdx.x, cfg.Nq, cfg.method).len;
+  len_tab[threadIdx.x] = (uint16_t)(l < 0xffffu ? l : 0xffffu);
 }
 
 // Pass 2.  Phase A (symbol-parallel, 8 symbols per thread): codes, block scan, the op_off entries of the streams that
@@ -368,6 +340,328 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, con
           if (e >= e0 && e < e1) dst[e] = (uint8_t)(w[e >> 2] >> (8u * (e & 3u)));
       }
     }
+  }
+}
+
+// ---- u8 symbols: counts by table, ops appended word-wise (round 2) -------------------------------
+// Round 2's ncu on the kernels above: instruction-bound, 64 thread-instructions per symbol in phase A (the closed form per
+// symbol, the codes kept in 24 registers) and 27 per op in phase B (a byte load, a byte store and the loop around them).
+// For 8-bit symbols -- what every application alphabet is -- both halves are table work:
+//   k_bin_count8   a warp per tile, 16 symbols per 16-byte load, bin counts out of a 256-entry table in shared memory;
+//   k_bin_emit8    phase A sums table entries; phase B appends each symbol's op string (one 8-byte table load: 7 op
+//                  bytes + length) to a running word in a register and stores every completed word with one aligned
+//                  store -- bin_emit.cuh has the scheme, its proof obligations and the host emulation's entry points.
+//                  A CTA walks `tpc` consecutive tiles, so the tables are set up once per 8 K symbols or more.
+constexpr uint32_t BIN8_ESC = LUT_MAX;       // fast-table slot of "not in the table" (all zero)
+
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_count8(const uint8_t* __restrict__ sym, uint64_t n, const uint16_t* __restrict__ len_tab,
+                                                             uint32_t n_tiles, uint32_t* __restrict__ tile_sums) {
+  __shared__ uint16_t s_len[256];
+  s_len[threadIdx.x] = len_tab[threadIdx.x];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t tile = blockIdx.x * (BIN_THREADS / 32) + (threadIdx.x >> 5);
+  if (tile >= n_tiles) return;
+  const uint64_t t0 = (uint64_t)tile * BIN_TILE;
+  uint32_t tot = 0;
+#pragma unroll
+  for (int j = 0; j < BIN_TILE / (32 * 16); ++j) {
+    const uint64_t b = t0 + (uint64_t)(lane + 32u * j) * 16u;
+    if (b + 16u <= n) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(sym + b));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tot += s_len[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
+    } else {
+      for (uint64_t i = b; i < n && i < b + 16u; ++i) tot += s_len[sym[i]];
+    }
+  }
+  tot = __reduce_add_sync(0xffffffffu, tot);
+  if (lane == 0) tile_sums[tile] = tot;
+}
+
+struct StageStore {            // the whole tile is in the stage; `stage` = its shared-window address
+  uint32_t stage;
+  __device__ __forceinline__ void word(uint32_t a, uint32_t w) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(stage + a), "r"(w) : "memory"); }
+  __device__ __forceinline__ void byte(uint32_t a, uint32_t b) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(stage + a), "r"(b) : "memory"); }
+  __device__ __forceinline__ void words(BinAcc& A, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t nfb) {
+    asm volatile("{\n\t.reg .pred p1, p2;\n\t"
+                 "setp.ge.u32 p1, %6, 32;\n\t"
+                 "setp.ge.u32 p2, %6, 64;\n\t"
+                 "@p1 st.shared.u32 [%2], %3;\n\t"
+                 "@p2 st.shared.u32 [%2+4], %4;\n\t"
+                 "selp.u32 %0, %4, %3, p1;\n\t"
+                 "selp.u32 %0, %5, %0, p2;\n\t"
+                 "@p1 add.u32 %1, %1, 4;\n\t"
+                 "@p2 add.u32 %1, %1, 4;\n\t}"
+                 : "=&r"(A.a0), "+r"(A.wp) : "r"(stage + A.wp), "r"(w0), "r"(w1), "r"(w2), "r"(nfb) : "memory");
+  }
+};
+struct StageWindow {           // only stage positions [w0, w0 + BIN_STAGE) are in the stage this round
+  uint8_t* stage;
+  uint32_t w0;
+  __device__ __forceinline__ void word(uint32_t a, uint32_t w) { if (a - w0 < BIN_STAGE) *reinterpret_cast<volatile uint32_t*>(stage + (a - w0)) = w; }
+  __device__ __forceinline__ void byte(uint32_t a, uint32_t b) { if (a - w0 < BIN_STAGE) *reinterpret_cast<volatile uint8_t*>(stage + (a - w0)) = (uint8_t)b; }
+  __device__ __forceinline__ void words(BinAcc& A, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t nfb) { bin_words_plain(*this, A, x0, x1, x2, nfb); }
+};
+
+// fast-table entry of a symbol: v = its value, u = its neighbour's, up = the neighbour exists
+__device__ __forceinline__ uint2 bin8_entry(const SymCfg& cfg, uint32_t dom, uint32_t lut8, uint32_t v, uint32_t u, bool up, uint32_t& idx) {
+  idx = lut_index(cfg, dom, v, u, up);
+  if (idx == LUT_ESC) idx = BIN8_ESC;
+  uint2 e;       // the table does not change after the set-up barrier: a plain (movable) load
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(lut8 + idx * 8u));
+  return e;
+}
+// one symbol, whatever its string
+template <class St>
+__device__ __forceinline__ void bin8_symbol(const SymCfg& cfg, uint32_t dom, uint32_t entries, uint32_t lut8, const uint4* lut16,
+                                            BinAcc& A, St& st, uint32_t v, uint32_t u, bool up) {
+  uint32_t idx;
+  const uint2 e = bin8_entry(cfg, dom, lut8, v, u, up, idx);
+  if (e.y >> 24) {
+    bin_append(A, st, e.x, e.y & 0x00ffffffu, e.y >> 24);
+  } else {
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (idx < entries) q = __ldg(lut16 + idx);
+    A = bin_append_long(A, st, cfg, q.x, q.y, q.z, q.w, v, u, up);
+  }
+}
+__device__ __forceinline__ uint32_t pinned(uint32_t x) {      // a value the compiler must keep instead of recomputing
+  uint32_t y;
+  asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
+constexpr uint32_t BIN_SOFF = BIN_THREADS + 2;      // stream offsets of a tile kept in shared memory (profiles with neighbours)
+
+template <int PROF, int METH>
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_emit8(isscabac_symcfg c, const uint8_t* __restrict__ sym, uint64_t n,
+                                                            const uint64_t* __restrict__ sym_off, uint32_t n_streams,
+                                                            const uint32_t* __restrict__ tile_stream, const uint32_t* __restrict__ tile_first,
+                                                            const uint64_t* __restrict__ tile_prefix, uint64_t* op_off, uint8_t* ops,
+                                                            uint64_t cap, const uint4* __restrict__ lut, const uint16_t* __restrict__ len_tab,
+                                                            uint32_t n_tiles, uint32_t tpc) {
+  __shared__ uint32_t s_warp[BIN_THREADS / 32];
+  __shared__ uint32_t s_pre[BIN_THREADS];
+  __shared__ __align__(16) uint8_t s_stage[BIN_STAGE];
+  __shared__ __align__(8) uint2 s_lut8[LUT_MAX + 1];
+  __shared__ __align__(8) uint64_t s_soff[BIN_SOFF];
+  __shared__ uint16_t s_len[256];
+  const SymCfg cfg = fixed_cfg<PROF, METH>(c);
+  const LutGeom geom = lut_geom(cfg.profile, cfg.method, cfg.Nq);
+  const bool need_up = cfg.profile == PROFILE_ISS || cfg.profile == PROFILE_DEMO;   // the other profiles' ops do not depend on the position
+  s_len[threadIdx.x] = len_tab[threadIdx.x];
+  if (ops) {
+    for (uint32_t e = threadIdx.x; e < geom.entries; e += BIN_THREADS) {
+      const uint4 q = __ldg(lut + e);
+      uint2 f;
+      lut8_from16(q.x, q.y, q.w, f.x, f.y);
+      s_lut8[e] = f;
+    }
+    if (threadIdx.x == 0) s_lut8[BIN8_ESC] = make_uint2(0u, 0u);
+  }
+  __syncthreads();
+  const uint32_t lut8 = pinned((uint32_t)__cvta_generic_to_shared(s_lut8)), stage0 = pinned((uint32_t)__cvta_generic_to_shared(s_stage));
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const bool vec = (reinterpret_cast<uintptr_t>(sym) & 7u) == 0;
+  // the 8 symbols of this thread in tile t (zero past the end)
+  auto load_run = [&](uint32_t t, uint32_t& qx, uint32_t& qy) {
+    const uint64_t i0 = (uint64_t)t * BIN_TILE + (uint64_t)threadIdx.x * BIN_ITEMS;
+    qx = qy = 0u;
+    if (vec && i0 + BIN_ITEMS <= n) {
+      const uint2 q = __ldg(reinterpret_cast<const uint2*>(sym + i0));
+      qx = q.x;
+      qy = q.y;
+    } else {
+      for (uint32_t k = 0; k < BIN_ITEMS && i0 + k < n; ++k) {
+        const uint32_t b = sym[i0 + k];
+        if (k < 4u) qx |= b << (8u * k); else qy |= b << (8u * (k - 4u));
+      }
+    }
+  };
+  const uint32_t tile_begin = blockIdx.x * tpc;
+  const uint32_t tile_end = tile_begin + tpc < n_tiles ? tile_begin + tpc : n_tiles;
+  if (tile_begin >= tile_end) return;
+  // A tile's inputs are asked for one tile ahead: its symbols, its first op position, the streams it touches
+  // ([s_lo, s_hi], tile_stream) and the streams that start in it ([f0, f1), tile_first).  Without this the kernel is a chain
+  // of dependent load latencies per tile (first measurement: phase A alone 2.25 ms at C4, phase B 1.25).
+  uint32_t nqx, nqy;
+  load_run(tile_begin, nqx, nqy);
+  uint64_t nbase = tile_prefix[tile_begin];
+  uint32_t nf0 = tile_first[tile_begin], nf1 = tile_first[tile_begin + 1];
+  uint32_t ns_lo = need_up ? tile_stream[tile_begin] : 0u, ns_hi = need_up ? tile_stream[tile_begin + 1] : 0u;
+  for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
+    const uint64_t t0 = (uint64_t)tile * BIN_TILE;
+    const uint64_t i0 = t0 + (uint64_t)threadIdx.x * BIN_ITEMS;
+    const uint32_t nvalid = i0 >= n ? 0u : (n - i0 < BIN_ITEMS ? (uint32_t)(n - i0) : (uint32_t)BIN_ITEMS);
+    const uint32_t qx = nqx, qy = nqy, f0 = nf0, f1 = nf1, s_lo = ns_lo, s_hi = ns_hi;
+    const uint64_t tile_base = nbase;
+    if (tile + 1 < tile_end) {
+      load_run(tile + 1, nqx, nqy);
+      nbase = tile_prefix[tile + 1];
+      nf0 = f1;
+      nf1 = tile_first[tile + 2];
+      if (need_up) { ns_lo = s_hi; ns_hi = tile_stream[tile + 2]; }
+    }
+    // ---- phase A: bin counts by table, the block scan (per-thread part in s_pre, per-warp totals in s_warp: the stream
+    // pass at the end of the tile reads other threads' positions out of them)
+    uint32_t tot = 0;
+#pragma unroll
+    for (int k = 0; k < BIN_ITEMS; ++k) {
+      const uint32_t vk = ((k < 4 ? qx : qy) >> (8 * (k & 3))) & 0xffu;
+      const uint32_t l = s_len[vk];
+      tot += (uint32_t)k < nvalid ? l : 0u;
+    }
+    // the offsets of the streams this tile touches, in shared memory: every thread looks its stream up in them
+    const uint32_t n_soff = s_hi - s_lo + 2u;
+    const bool soff_shared = need_up && n_soff <= BIN_SOFF;
+    if (soff_shared)
+      for (uint32_t j = threadIdx.x; j < n_soff; j += BIN_THREADS) s_soff[j] = sym_off[s_lo + j];
+    uint32_t inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= (uint32_t)d) inc += t;
+    }
+    s_pre[threadIdx.x] = inc - tot;
+    if (lane == 31u) s_warp[wid] = inc;
+    __syncthreads();
+    uint32_t lo = inc - tot, block_total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < BIN_THREADS / 32; ++w) {
+      const uint32_t t = s_warp[w];
+      if (w < wid) lo += t;
+      block_total += t;
+    }
+    // the first stream that starts in this tile, for this thread (asked for now, used at the end of the tile)
+    const uint64_t my_soff = f0 + threadIdx.x < f1 ? sym_off[f0 + threadIdx.x] : 0u;
+    uint32_t up_mask = 0;
+    if (need_up && nvalid) {
+      // generic pointer: the tile's slice in shared memory, re-based to stream indices, or the whole array
+      const uint64_t* so = soff_shared ? s_soff - s_lo : sym_off;
+      uint32_t s = find_stream(so, s_lo, s_hi + 1, i0);
+      uint64_t start = so[s], next = so[s + 1];
+      if (i0 > start && i0 + BIN_ITEMS <= next) {
+        // the whole run lies inside one stream, away from its first symbol: the neighbour flags follow from the row of
+        // the run's first symbol
+        if (cfg.profile == PROFILE_DEMO || cfg.rows == 0) {
+          up_mask = 0xffu;
+        } else {
+          const uint64_t rel = i0 - start;
+          uint32_t r = rel >> 32 ? (uint32_t)(rel % cfg.rows) : (uint32_t)rel % cfg.rows;
+#pragma unroll
+          for (int k = 0; k < BIN_ITEMS; ++k) {
+            if (r != 0) up_mask |= 1u << k;
+            if (++r == cfg.rows) r = 0;
+          }
+        }
+      } else {
+        for (uint32_t k = 0; k < nvalid; ++k) {
+          const uint64_t i = i0 + k;
+          if (i == next) {   // next non-empty stream
+            ++s;
+            while (s + 1 < n_streams && so[s + 1] == i) ++s;
+            start = i;
+            next = so[s + 1];
+          }
+          if (sym_has_up(cfg, i - start)) up_mask |= 1u << k;
+        }
+      }
+    }
+    if (ops) {
+      // ---- phase B (bin_emit.cuh): stage byte = tile position + skew, so that the stage's 16-byte pieces are the op
+      // array's aligned ones
+      const uint32_t skew = (uint32_t)((reinterpret_cast<uintptr_t>(ops) + tile_base) & 15u);
+      const uint32_t room = tile_base >= cap ? 0u : (cap - tile_base < block_total ? (uint32_t)(cap - tile_base) : block_total);
+      uint32_t before = 0;
+      if (up_mask & 1u) before = i0 > 0 ? sym[i0 - 1] : 0u;
+      const uint32_t pos = lo + skew, span = block_total + skew;
+      BinAcc A;
+      for (uint32_t w0 = 0; w0 < span; w0 += BIN_STAGE) {
+        bin_acc_start(A, pos);
+        const uint32_t wp_first = A.wp, fb_first = A.fb;
+        // the common case -- the whole tile in the stage, 8 symbols, all strings in the fast table -- is straight-line:
+        // 8 table loads, then 8 appends
+        bool fast = span <= BIN_STAGE && nvalid == BIN_ITEMS;
+        uint2 e[BIN_ITEMS];
+        if (fast) {
+          uint32_t all = 0xffffffffu;
+#pragma unroll
+          for (int k = 0; k < BIN_ITEMS; ++k) {
+            const uint32_t vk = ((k < 4 ? qx : qy) >> (8 * (k & 3))) & 0xffu;
+            const uint32_t uk = k == 0 ? before : (((k - 1 < 4 ? qx : qy) >> (8 * ((k - 1) & 3))) & 0xffu);
+            uint32_t idx;
+            e[k] = bin8_entry(cfg, geom.dom, lut8, vk, uk, (up_mask >> k) & 1u, idx);
+            all = min(all, e[k].y);
+          }
+          fast = all >> 24;        // every length is at least 1
+        }
+        if (fast) {
+          StageStore st{stage0};
+#pragma unroll
+          for (int k = 0; k < BIN_ITEMS; ++k) bin_append(A, st, e[k].x, e[k].y & 0x00ffffffu, e[k].y >> 24);
+        } else if (pos < w0 + BIN_STAGE && pos + tot + 4u > w0) {    // (span and w0 are the block's: the barriers below are met by all)
+          // a tile larger than the stage leaves in rounds (every thread appends all its symbols in every round it has a
+          // byte in, the stores outside the round's window are dropped); the last tile's short runs come here too
+          StageWindow st{s_stage, w0};
+#pragma unroll 1
+          for (uint32_t k = 0; k < nvalid; ++k) {
+            const uint32_t vk = ((k < 4u ? qx : qy) >> (8u * (k & 3u))) & 0xffu;
+            const uint32_t uk = k == 0u ? before : (((k - 1u < 4u ? qx : qy) >> (8u * ((k - 1u) & 3u))) & 0xffu);
+            bin8_symbol(cfg, geom.dom, geom.entries, lut8, lut, A, st, vk, uk, (up_mask >> k) & 1u);
+          }
+        } else {
+          A.a0 = 0u;                     // nothing of this thread in the window: neither words nor tail bytes
+          A.fb = 0u;
+        }
+        __syncthreads();       // every word is in the stage: now the incomplete last words, byte by byte
+        {
+          StageWindow st{s_stage, w0};
+          bin_tail(A, st, wp_first, fb_first);
+        }
+        __syncthreads();
+        // pieces of this window: stage bytes [16 p, 16 p + 16) <-> tile positions [w0 + 16 p - skew, ...)
+        const uint32_t w1 = w0 + BIN_STAGE;
+        const uint32_t wend = w1 < span ? w1 : span;
+        const uint32_t npieces = (wend - w0 + 15u) >> 4;
+        for (uint32_t pc = threadIdx.x; pc < npieces; pc += BIN_THREADS) {
+          const int32_t pbeg = (int32_t)(w0 + 16u * pc) - (int32_t)skew;           // tile position of byte 0 of the piece
+          const uint32_t e0 = pbeg < 0 ? (uint32_t)(-pbeg) : 0u;                   // valid bytes: [e0, e1)
+          const int32_t left = (int32_t)room - pbeg;
+          const uint32_t e1 = left <= 0 ? 0u : (left < 16 ? (uint32_t)left : 16u);
+          if (e0 >= e1) continue;
+          const uint4 q = *reinterpret_cast<const uint4*>(s_stage + 16u * pc);
+          uint8_t* dst = ops + tile_base + pbeg;       // 16-byte aligned by the choice of skew
+          if (e0 == 0 && e1 == 16) {
+            *reinterpret_cast<uint4*>(dst) = q;
+          } else {
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (uint32_t e = 0; e < 16; ++e)
+              if (e >= e0 && e < e1) dst[e] = (uint8_t)(w[e >> 2] >> (8u * (e & 3u)));
+          }
+        }
+        if (w1 < span) __syncthreads();          // the next round overwrites the stage
+      }
+    }
+    // ---- the stream pass: op_off of the streams that start in this tile, one stream per thread.  A stream that starts
+    // at tile position p begins with symbol p % 8 of thread p / 8: that thread's first op position is in s_pre / s_warp,
+    // the counts of the symbols in front are looked up again (at most 7 bytes, in L1 since the tile was loaded).
+    {
+      uint64_t so_e = my_soff;
+      for (uint32_t e = f0 + threadIdx.x; e < f1; e += BIN_THREADS) {
+        if (e != f0 + threadIdx.x) so_e = sym_off[e];
+        const uint32_t p = (uint32_t)(so_e - t0), owner = p >> 3;
+        uint32_t o = s_pre[owner];
+        for (uint32_t w = 0; w < (owner >> 5); ++w) o += s_warp[w];
+        for (uint32_t j = 0; j < (p & 7u); ++j) o += s_len[sym[t0 + (p & ~7u) + j]];
+        op_off[e] = tile_base + o;
+      }
+      if (tile + 1 == n_tiles)      // the streams at the very end are empty; op_off[n_streams] = the total
+        for (uint32_t e = f1 + threadIdx.x; e <= n_streams; e += BIN_THREADS) op_off[e] = tile_base + block_total;
+    }
+    __syncthreads();       // s_pre, s_warp, s_soff and the stage are free for the next tile
   }
 }
 
@@ -1643,7 +1937,7 @@ size_t cabac_binarize_scratch_bytes(uint64_t n_symbols, uint32_t n_streams) {
   const size_t sums = ((size_t)tiles * 4 + 255) & ~(size_t)255;
   const size_t pref = (((size_t)tiles + 1) * 8 + 255) & ~(size_t)255;
   const size_t tstr = (((size_t)tiles + 1) * 4 + 255) & ~(size_t)255;
-  return sums + pref + tstr + ((cabac_compact_scratch_bytes((uint32_t)tiles) + 255) & ~(size_t)255) + LUT_MAX * sizeof(uint4) + 256;
+  return sums + pref + 2 * tstr + ((cabac_compact_scratch_bytes((uint32_t)tiles) + 255) & ~(size_t)255) + LUT_MAX * sizeof(uint4) + 512 + 256;
 }
 
 int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_sym_off,
@@ -1668,13 +1962,22 @@ int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const
   uint64_t* tile_prefix = reinterpret_cast<uint64_t*>(scr + sums_b);
   const size_t tstr_b = (((size_t)tiles + 1) * 4 + 255) & ~(size_t)255;
   uint32_t* tile_stream = reinterpret_cast<uint32_t*>(scr + sums_b + pref_b);
-  void* scan_scr = scr + sums_b + pref_b + tstr_b;
-  k_bin_tile_streams<<<(tiles + 1 + 255) / 256, 256, 0, st>>>(d_sym_off, n_streams, n_symbols, tiles, tile_stream);
+  uint32_t* tile_first = reinterpret_cast<uint32_t*>(scr + sums_b + pref_b + tstr_b);
+  void* scan_scr = scr + sums_b + pref_b + 2 * tstr_b;
+  k_bin_tile_streams<<<(tiles + 1 + 255) / 256, 256, 0, st>>>(d_sym_off, n_streams, n_symbols, tiles, tile_stream, tile_first);
   uint4* lut = reinterpret_cast<uint4*>(static_cast<uint8_t*>(scan_scr) + ((cabac_compact_scratch_bytes(tiles) + 255) & ~(size_t)255));
   const LutGeom geom = lut_geom(cfg->profile, cfg->method, cfg->Nq);
+  uint16_t* len_tab = reinterpret_cast<uint16_t*>(lut + LUT_MAX);
   if (d_ops && geom.entries) k_bin_lut<<<(geom.entries + 127) / 128, 128, 0, st>>>(*cfg, lut);
+  // 8-bit symbols: counts by table, ops appended word-wise (k_bin_count8 / k_bin_emit8); ISSCABAC_BIN8=0 keeps the
+  // closed-form kernels (both run against the oracle in the tests)
+  const char* bin8_env = getenv("ISSCABAC_BIN8");
+  const bool bin8 = sym_width == 1 && !(bin8_env && bin8_env[0] == '0');
+  if (bin8) k_bin_lentab<<<1, 256, 0, st>>>(*cfg, len_tab);
 #define BIN_COUNT(WW, ME) k_bin_count<WW, ME><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, tile_sums)
-  if (sym_width == 1 && cfg->method == ISSCABAC_BIN_EG0) BIN_COUNT(1, ISSCABAC_BIN_EG0);
+  if (bin8 && (reinterpret_cast<uintptr_t>(d_symbols) & 15u) == 0)
+    k_bin_count8<<<(tiles + BIN_THREADS / 32 - 1) / (BIN_THREADS / 32), BIN_THREADS, 0, st>>>(static_cast<const uint8_t*>(d_symbols), n_symbols, len_tab, tiles, tile_sums);
+  else if (sym_width == 1 && cfg->method == ISSCABAC_BIN_EG0) BIN_COUNT(1, ISSCABAC_BIN_EG0);
   else if (sym_width == 1 && cfg->method == ISSCABAC_BIN_EG2) BIN_COUNT(1, ISSCABAC_BIN_EG2);
   else if (sym_width == 1 && cfg->method == ISSCABAC_BIN_TU) BIN_COUNT(1, ISSCABAC_BIN_TU);
   else if (sym_width == 1) BIN_COUNT(1, -1);
@@ -1682,19 +1985,28 @@ int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const
   else BIN_COUNT(4, -1);
 #undef BIN_COUNT
   if ((rc = exclusive_scan_u32_u64(tile_sums, tile_prefix, tiles, scan_scr, st))) return rc;
+  // tiles per CTA of the u8 emit kernel: the tables are set up once per CTA; keep at least ~8 CTAs per SM
+  uint32_t tpc = 1;
+  while (tpc < 8u && tiles / (tpc * 2u) >= (uint32_t)sm_count() * 8u) tpc *= 2u;
+#define BIN_EMIT8(PR, ME) \
+  k_bin_emit8<PR, ME><<<(tiles + tpc - 1) / tpc, BIN_THREADS, 0, st>>>(*cfg, static_cast<const uint8_t*>(d_symbols), n_symbols, d_sym_off, n_streams, \
+                                                                      tile_stream, tile_first, tile_prefix, d_op_off, d_ops, ops_cap, lut, len_tab, tiles, tpc)
 #define BIN_EMIT(WW, PR, ME) \
   k_bin_emit<WW, PR, ME><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, d_sym_off, n_streams, tile_stream, tile_prefix, d_op_off, d_ops, ops_cap, lut)
-#define BIN_EMIT_CASE(PR, ME) if (sym_width == 1 && cfg->profile == PR && cfg->method == ME) BIN_EMIT(1, PR, ME); else
+#define BIN_EMIT_CASE(PR, ME) \
+  if (sym_width == 1 && cfg->profile == PR && cfg->method == ME) { if (bin8) BIN_EMIT8(PR, ME); else BIN_EMIT(1, PR, ME); } else
   BIN_EMIT_CASE(ISSCABAC_PROFILE_ISS, ISSCABAC_BIN_EG0)
   BIN_EMIT_CASE(ISSCABAC_PROFILE_FLAT, ISSCABAC_BIN_EG0)
   BIN_EMIT_CASE(ISSCABAC_PROFILE_FLAT_EPSUF, ISSCABAC_BIN_EG2)
   BIN_EMIT_CASE(ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_TU)
   BIN_EMIT_CASE(ISSCABAC_PROFILE_DEMO, ISSCABAC_BIN_EG0)
-  if (sym_width == 1) BIN_EMIT(1, -1, -1);
+  if (bin8) BIN_EMIT8(-1, -1);
+  else if (sym_width == 1) BIN_EMIT(1, -1, -1);
   else if (sym_width == 2) BIN_EMIT(2, -1, -1);
   else BIN_EMIT(4, -1, -1);
 #undef BIN_EMIT_CASE
 #undef BIN_EMIT
+#undef BIN_EMIT8
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "cabac_binarize_symbols");
 }

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 #include "../../isscabac_b200/csrc/cabac_lane.cuh"
+#include "../../isscabac_b200/csrc/bin_emit.cuh"
 
 using namespace cabac;
 
@@ -102,6 +103,85 @@ int emul_decode_symbols(const int32_t* cfgv, const uint8_t* bytes, uint32_t len,
   }
   *ok = (uint8_t)dec_finish(D);
   return 0;
+}
+
+// The emit phase of the u8 binarizer (k_bin_emit8, symbols.cu) on the host: the same per-thread code (bin_emit.cuh) for
+// every "thread" of every tile of ONE stream of u8 symbols -- table set-up, scan, word-wise append into a stage of
+// `stage_bytes` (a small stage forces the rounds of an over-full tile), tail bytes after the "barrier", pieces out.
+// The threads of a phase run in the order `order` says (0: ascending, 1: descending, 2: odd lanes first): what they
+// store between two barriers must not depend on it.  `skew0` = the op array's byte alignment.
+struct EmulStage {
+  uint8_t* stage;
+  uint32_t w0, size;
+  void word(uint32_t a, uint32_t w) { if (a - w0 < size) memcpy(stage + (a - w0), &w, 4); }
+  void byte(uint32_t a, uint32_t b) { if (a - w0 < size) stage[a - w0] = (uint8_t)b; }
+  void words(BinAcc& A, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t nfb) { bin_words_plain(*this, A, x0, x1, x2, nfb); }
+};
+uint64_t emul_bin_emit8(const int32_t* cfgv, const uint8_t* sym, uint64_t n, uint8_t* ops, uint32_t skew0,
+                        uint32_t stage_bytes, int order) {
+  SymCfg cfg{cfgv[0], cfgv[1], (uint32_t)cfgv[2], cfgv[3], (uint32_t)cfgv[4], (uint32_t)cfgv[5]};
+  const uint32_t T = 256, ITEMS = 8, TILE = T * ITEMS;
+  const LutGeom geom = lut_geom(cfg.profile, cfg.method, cfg.Nq);
+  std::vector<uint32_t> lut16(4 * (LUT_MAX + 1), 0u), lut8(2 * (LUT_MAX + 1), 0u);
+  for (uint32_t e = 0; e < geom.entries; ++e) {
+    lut_entry(cfg, e, &lut16[4 * e]);
+    lut8_from16(lut16[4 * e], lut16[4 * e + 1], lut16[4 * e + 3], lut8[2 * e], lut8[2 * e + 1]);
+  }
+  uint32_t len_tab[256];
+  for (uint32_t v = 0; v < 256; ++v) len_tab[v] = sym_code(v, cfg.Nq, cfg.method).len;
+  std::vector<uint8_t> stage(stage_bytes + 16, 0xEE);
+  std::vector<uint32_t> perm(T);
+  for (uint32_t t = 0; t < T; ++t) perm[t] = order == 0 ? t : (order == 1 ? T - 1 - t : (t < T / 2 ? 2 * t + 1 : 2 * (t - T / 2)));
+  uint64_t tile_base = 0;
+  for (uint64_t t0 = 0; t0 < n; t0 += TILE) {
+    uint32_t lo[256], tot[256], nvalid[256];
+    uint32_t block_total = 0;
+    for (uint32_t t = 0; t < T; ++t) {
+      const uint64_t i0 = t0 + (uint64_t)t * ITEMS;
+      nvalid[t] = i0 >= n ? 0u : (n - i0 < ITEMS ? (uint32_t)(n - i0) : ITEMS);
+      tot[t] = 0;
+      for (uint32_t k = 0; k < nvalid[t]; ++k) tot[t] += len_tab[sym[i0 + k]];
+      lo[t] = block_total;
+      block_total += tot[t];
+    }
+    const uint32_t skew = (uint32_t)((skew0 + tile_base) & 15u), span = block_total + skew;
+    for (uint32_t w0 = 0; w0 < span; w0 += stage_bytes) {
+      std::fill(stage.begin(), stage.end(), (uint8_t)0xEE);
+      BinAcc acc[256];
+      uint32_t wpf[256], fbf[256];
+      EmulStage st{stage.data(), w0, stage_bytes};
+      for (uint32_t tt = 0; tt < T; ++tt) {
+        const uint32_t t = perm[tt];
+        const uint64_t i0 = t0 + (uint64_t)t * ITEMS;
+        const uint32_t pos = lo[t] + skew;
+        BinAcc& A = acc[t];
+        bin_acc_start(A, pos);
+        wpf[t] = A.wp;
+        fbf[t] = A.fb;
+        if (pos < w0 + stage_bytes && pos + tot[t] + 4u > w0) {
+          for (uint32_t k = 0; k < nvalid[t]; ++k) {
+            const uint64_t i = i0 + k;
+            const uint32_t v = sym[i], u = i ? sym[i - 1] : 0u;
+            const bool up = sym_has_up(cfg, i);
+            uint32_t idx = lut_index(cfg, geom.dom, v, u, up);
+            if (idx == LUT_ESC) idx = LUT_MAX;
+            const uint32_t ex = lut8[2 * idx], ey = lut8[2 * idx + 1];
+            if (ey >> 24) bin_append(A, st, ex, ey & 0x00ffffffu, ey >> 24);
+            else A = bin_append_long(A, st, cfg, lut16[4 * idx], lut16[4 * idx + 1], lut16[4 * idx + 2], lut16[4 * idx + 3], v, u, up);
+          }
+        } else {
+          A.a0 = 0u;
+          A.fb = 0u;
+        }
+      }
+      for (uint32_t tt = 0; tt < T; ++tt) bin_tail(acc[perm[tt]], st, wpf[perm[tt]], fbf[perm[tt]]);
+      const uint32_t wend = w0 + stage_bytes < span ? w0 + stage_bytes : span;
+      for (uint32_t b = w0; b < wend; ++b)
+        if (b >= skew) ops[tile_base + b - skew] = stage[b - w0];
+    }
+    tile_base += block_total;
+  }
+  return tile_base;
 }
 
 }  // extern "C"

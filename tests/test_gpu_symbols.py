@@ -116,9 +116,14 @@ def test_many_streams_vs_oracle(I, prof, meth, Nq, rows, dtype):
             assert bool(ok.all().item()), ("finish flags", tree)
             assert (dec.cpu().numpy().view(dtype) == sym).all(), ("decoded symbols", tree)
     # symbol-parallel binarizer against the oracle's op stream
-    ops, op_off = I.binarize_symbols(cfg, sym, off.astype(np.int64))
     want = np.concatenate([O.symbols_to_ops(ocfg, sym[int(off[s]):int(off[s + 1])]) for s in range(n_streams)])
-    assert (ops.cpu().numpy() == want).all()
+    for bin8 in ("1", "0"):       # u8 symbols: table kernels (k_bin_count8 / k_bin_emit8) and the closed-form ones
+        os.environ["ISSCABAC_BIN8"] = bin8
+        try:
+            ops, op_off = I.binarize_symbols(cfg, sym, off.astype(np.int64))
+        finally:
+            os.environ.pop("ISSCABAC_BIN8")
+        assert (ops.cpu().numpy() == want).all(), bin8
 
 
 def test_symbol_host_api(I):
@@ -332,3 +337,72 @@ def test_more_streams_than_lanes(I, prof, meth, Nq):
             os.environ.pop(env_name)
         assert bool(ok.all().item()), (env_name, val)
         assert (dec.cpu().numpy() == sym).all(), (env_name, val)
+
+
+@pytest.mark.parametrize("prof,meth,Nq,rows,shape", [
+    (O.PROFILE_FLAT, O.BIN_EG0, 16, 0, "ragged"),
+    (O.PROFILE_FLAT, O.BIN_EG0, 256, 0, "ragged"),          # strings of up to 17 ops: long table entries and the closed form
+    (O.PROFILE_FLAT, O.BIN_EG0, 32, 0, "uniform"),          # half the strings have 9 ops (two appends)
+    (O.PROFILE_FLAT_EPSUF, O.BIN_EG2, 256, 0, "ragged"),
+    (O.PROFILE_ISS, O.BIN_EG0, 8, 400, "columns"),
+    (O.PROFILE_ISS, O.BIN_EG0, 64, 0, "ragged"),            # values outside the neighbour table's domain
+    (O.PROFILE_DEMO, O.BIN_TU, 12, 0, "ragged"),
+    (O.PROFILE_FLAT, O.BIN_FL32, 256, 0, "ragged"),         # 32 ops per symbol: a tile's ops leave the stage in rounds
+    (O.PROFILE_FLAT, O.BIN_TU, 300, 0, "ragged"),           # strings of up to 256 ops
+    (O.PROFILE_FLAT, O.BIN_TR0 + 2, 16, 0, "ragged"),
+    (O.PROFILE_FLAT, O.BIN_EG0, 16, 0, "tiny"),             # ~1,400 streams start in every tile
+    (O.PROFILE_ISS, O.BIN_EG0, 16, 3, "tiny"),              # ... more than the shared-memory slice of stream offsets holds
+    (O.PROFILE_DEMO, O.BIN_EG0, 16, 0, "tiny"),
+])
+def test_binarizer_u8_table_kernels(I, prof, meth, Nq, rows, shape):
+    """k_bin_count8 / k_bin_emit8 (u8 symbols: bin counts by table, op strings appended word-wise) against the oracle's op
+    stream and offsets: empty streams, streams that start on tile and thread boundaries, a symbol buffer at odd byte
+    alignments (no vector loads), an input that ends inside a thread's run of 8, thousands of tiny and empty streams."""
+    import ctypes as C
+    from isscabac_b200 import engine as E
+    rng = np.random.default_rng(prof * 1000 + meth * 31 + Nq)
+    if shape == "columns":
+        counts = np.full(160, rows, dtype=np.int64)
+    elif shape == "tiny":
+        counts = rng.integers(0, 4, size=9000)
+        counts[4000:4600] = 0                                # hundreds of empty streams in a row, and at the very end
+        counts[-300:] = 0
+    else:
+        counts = rng.integers(0, 900, size=220)
+        counts[rng.integers(0, len(counts), size=30)] = 0
+        counts[[0, 5, 6]] = [2048, 8, 2040]             # boundaries of tiles (2,048 symbols) and of 8-symbol runs
+        counts[-2:] = 0
+    n_streams = len(counts)
+    off = np.zeros(n_streams + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    n = int(off[-1])
+    hi = min(Nq, 256)
+    sym = (rng.integers(0, hi, size=n) if shape == "uniform" else np.minimum(np.floor(rng.exponential(hi / 5.0, size=n)), hi - 1)).astype(np.uint8)
+    cfg = I.make_cfg(prof, meth, Nq, 3, 0x1b, rows)
+    ocfg = O.make_cfg(prof, meth, Nq, 3, 0x1b, rows)
+    per = [O.symbols_to_ops(ocfg, sym[int(off[s]):int(off[s + 1])]) for s in range(n_streams)]
+    want = np.concatenate(per)
+    want_off = np.zeros(n_streams + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in per], out=want_off[1:])
+    dev = torch.device("cuda")
+    L = I.lib()
+    off_t = torch.as_tensor(off, device=dev)
+    scratch = torch.empty(int(L.cabac_binarize_scratch_bytes(C.c_uint64(n), C.c_uint32(n_streams))), dtype=torch.uint8, device=dev)
+    for sym_shift, op_shift in ((0, 0), (1, 3), (8, 15), (13, 8)):
+        symbuf = torch.zeros(n + 32, dtype=torch.uint8, device=dev)
+        sym_t = symbuf[sym_shift:sym_shift + n]
+        sym_t.copy_(torch.as_tensor(sym, device=dev))
+        op_off = torch.full((n_streams + 1,), -1, dtype=torch.int64, device=dev)
+        E.check(L.cabac_binarize_symbols(C.byref(cfg), C.c_uint32(n_streams), E.vp(off_t), E.vp(sym_t), 1, C.c_uint64(n),
+                                         E.vp(op_off), None, C.c_uint64(0), E.vp(scratch), E._stream_ptr()))
+        assert (op_off.cpu().numpy() == want_off).all(), ("offsets-only call", sym_shift)
+        buf = torch.full((len(want) + 64,), 0xAB, dtype=torch.uint8, device=dev)
+        op_off.fill_(-1)
+        E.check(L.cabac_binarize_symbols(C.byref(cfg), C.c_uint32(n_streams), E.vp(off_t), E.vp(sym_t), 1, C.c_uint64(n),
+                                         E.vp(op_off), E.vp(buf[op_shift:]), C.c_uint64(len(want)), E.vp(scratch), E._stream_ptr()))
+        torch.cuda.synchronize()
+        got = buf.cpu().numpy()
+        assert (op_off.cpu().numpy() == want_off).all(), ("offsets", sym_shift)
+        bad = np.nonzero(got[op_shift:op_shift + len(want)] != want)[0]
+        assert len(bad) == 0, ("ops", sym_shift, op_shift, int(bad[0]), len(bad))
+        assert (got[:op_shift] == 0xAB).all() and (got[op_shift + len(want):] == 0xAB).all()

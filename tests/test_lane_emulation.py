@@ -21,11 +21,12 @@ u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uin
 def emul():
     src = os.path.join(HERE, "emul", "lane_emul.cpp")
     so = os.path.join(HERE, "emul", "liblane_emul.so")
-    hdrs = [os.path.join(HERE, "..", "isscabac_b200", "csrc", h) for h in ("cabac_lane.cuh", "cabac_wide.cuh", "cabac_spec.cuh")]
+    hdrs = [os.path.join(HERE, "..", "isscabac_b200", "csrc", h) for h in ("cabac_lane.cuh", "cabac_wide.cuh", "cabac_spec.cuh", "bin_emit.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src], check=True)
     L = C.CDLL(so)
     L.emul_symbols_to_ops.restype = C.c_uint64
+    L.emul_bin_emit8.restype = C.c_uint64
     return L
 
 
@@ -199,3 +200,38 @@ def test_lane_truncated_rice(emul, k):
     else:
         assert list(O.binarize(5, Nq, O.BIN_TR0 + k)) == [1] * (5 >> k) + [0] + [(5 >> (k - 1 - i)) & 1 for i in range(k)]
         assert list(O.binarize(15, Nq, O.BIN_TR0 + k)) == [1] * (15 >> k) + [0] + [1] * k        # v >= maxVal: escape TODO upstream
+
+
+@pytest.mark.parametrize("prof,meth,Nq,rows", [
+    (O.PROFILE_FLAT, O.BIN_EG0, 32, 0),          # C4's shape: strings of 1..9 ops (the long ones in pieces of 7)
+    (O.PROFILE_FLAT, O.BIN_EG0, 256, 0),         # up to 17 ops: closed form, 7 ops per append
+    (O.PROFILE_FLAT_EPSUF, O.BIN_EG2, 64, 0),    # C5's shape
+    (O.PROFILE_ISS, O.BIN_EG0, 20, 7),           # neighbour-conditioned table, rows of 7
+    (O.PROFILE_ISS, O.BIN_EG0, 64, 0),           # values outside the table's domain (31)
+    (O.PROFILE_DEMO, O.BIN_TU, 12, 0),
+    (O.PROFILE_DEMO, O.BIN_EG0, 16, 0),
+    (O.PROFILE_FLAT, O.BIN_FL32, 256, 0),        # 32 ops per symbol: no table at all, tiles larger than the stage
+    (O.PROFILE_FLAT, O.BIN_TR0 + 1, 16, 0),
+    (O.PROFILE_FLAT, O.BIN_TU, 300, 0),          # strings of up to 256 ops
+])
+def test_bin_emit8_tile_logic(emul, prof, meth, Nq, rows):
+    """The u8 binarizer's emit phase (isscabac_b200/csrc/bin_emit.cuh: op strings appended word-wise to a stage, tail
+    bytes after the barrier) run for whole tiles on the host, against the oracle's op stream: every op-array alignment,
+    a stage small enough to force the rounds of an over-full tile, three orders of the threads inside a phase, inputs
+    that end inside a thread's run of 8 and inside a tile."""
+    rng = np.random.default_rng(prof * 100 + meth * 7 + Nq)
+    cfgv = np.array([prof, meth, Nq, 3, 0x1b, rows], dtype=np.int32)
+    cfg = O.make_cfg(prof, meth, Nq, 3, 0x1b, rows)
+    hi = min(Nq, 256)
+    cases = [(1, 0, 16384, 0), (5, 3, 16384, 1), (8, 15, 16384, 2), (2048, 1, 16384, 0), (2049, 7, 16384, 1), (4999, 5, 16384, 2),
+             (4999, 9, 256, 0), (6000, 2, 64, 1), (2048 * 3, 0, 1024, 2)]
+    for n, skew, stage, order in cases:
+        skewed = rng.random() < 0.5
+        sym = (np.minimum(rng.geometric(0.45, n) - 1, hi - 1) if skewed else rng.integers(0, hi, n)).astype(np.uint8)
+        want = O.symbols_to_ops(cfg, sym.astype(np.uint32))
+        got = np.full(len(want) + 64, 0xAA, dtype=np.uint8)
+        k = emul.emul_bin_emit8(cfgv.ctypes.data_as(C.POINTER(C.c_int32)), p(sym, u8p), C.c_uint64(n), p(got, u8p),
+                                C.c_uint32(skew), C.c_uint32(stage), order)
+        assert k == len(want), (n, skew, stage, order)
+        assert (got[:k] == want).all(), (n, skew, stage, order, int(np.argmax(got[:k] != want)))
+        assert (got[k:] == 0xAA).all()
