@@ -352,7 +352,6 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, con
 //                  bytes + length) to a running word in a register and stores every completed word with one aligned
 //                  store -- bin_emit.cuh has the scheme, its proof obligations and the host emulation's entry points.
 //                  A CTA walks `tpc` consecutive tiles, so the tables are set up once per 8 K symbols or more.
-constexpr uint32_t BIN8_ESC = LUT_MAX;       // fast-table slot of "not in the table" (all zero)
 
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_count8(const uint8_t* __restrict__ sym, uint64_t n, const uint16_t* __restrict__ len_tab,
                                                              uint32_t n_tiles, uint32_t* __restrict__ tile_sums) {
@@ -398,19 +397,18 @@ struct StageStore {            // the whole tile is in the stage; `stage` = its 
   }
 };
 struct StageWindow {           // only stage positions [w0, w0 + BIN_STAGE) are in the stage this round
-  uint8_t* stage;
-  uint32_t w0;
-  __device__ __forceinline__ void word(uint32_t a, uint32_t w) { if (a - w0 < BIN_STAGE) *reinterpret_cast<volatile uint32_t*>(stage + (a - w0)) = w; }
-  __device__ __forceinline__ void byte(uint32_t a, uint32_t b) { if (a - w0 < BIN_STAGE) *reinterpret_cast<volatile uint8_t*>(stage + (a - w0)) = (uint8_t)b; }
+  uint32_t stage, w0;
+  __device__ __forceinline__ void word(uint32_t a, uint32_t w) { if (a - w0 < BIN_STAGE) asm volatile("st.shared.u32 [%0], %1;" :: "r"(stage + (a - w0)), "r"(w) : "memory"); }
+  __device__ __forceinline__ void byte(uint32_t a, uint32_t b) { if (a - w0 < BIN_STAGE) asm volatile("st.shared.u8 [%0], %1;" :: "r"(stage + (a - w0)), "r"(b) : "memory"); }
   __device__ __forceinline__ void words(BinAcc& A, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t nfb) { bin_words_plain(*this, A, x0, x1, x2, nfb); }
 };
 
 // fast-table entry of a symbol: v = its value, u = its neighbour's, up = the neighbour exists
-__device__ __forceinline__ uint2 bin8_entry(const SymCfg& cfg, uint32_t dom, uint32_t lut8, uint32_t v, uint32_t u, bool up, uint32_t& idx) {
+__device__ __forceinline__ uint2 bin8_entry(const SymCfg& cfg, uint32_t dom, uint32_t esc, uint32_t lut8, uint32_t v, uint32_t u, bool up, uint32_t& idx) {
   idx = lut_index(cfg, dom, v, u, up);
-  if (idx == LUT_ESC) idx = BIN8_ESC;
-  uint2 e;       // the table does not change after the set-up barrier: a plain (movable) load
-  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(lut8 + idx * 8u));
+  if (idx == LUT_ESC) idx = esc;
+  uint2 e;       // volatile: in program order with the appends (a movable load is hoisted a whole run ahead and spilled)
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(lut8 + idx * 8u));
   return e;
 }
 // one symbol, whatever its string
@@ -418,7 +416,7 @@ template <class St>
 __device__ __forceinline__ void bin8_symbol(const SymCfg& cfg, uint32_t dom, uint32_t entries, uint32_t lut8, const uint4* lut16,
                                             BinAcc& A, St& st, uint32_t v, uint32_t u, bool up) {
   uint32_t idx;
-  const uint2 e = bin8_entry(cfg, dom, lut8, v, u, up, idx);
+  const uint2 e = bin8_entry(cfg, dom, entries, lut8, v, u, up, idx);
   if (e.y >> 24) {
     bin_append(A, st, e.x, e.y & 0x00ffffffu, e.y >> 24);
   } else {
@@ -433,50 +431,62 @@ __device__ __forceinline__ uint32_t pinned(uint32_t x) {      // a value the com
   return y;
 }
 
-constexpr uint32_t BIN_SOFF = BIN_THREADS + 2;      // stream offsets of a tile kept in shared memory (profiles with neighbours)
+// 128 threads x 16 symbols per tile of 2,048: what a thread does once per tile (scan, tail bytes, its share of the pieces
+// and of the stream pass, the look-ahead loads) is a third of its instructions with 8 symbols per thread
+constexpr int B8_THREADS = 128, B8_ITEMS = 16, B8_MIN_CTAS = 8;
+static_assert(B8_THREADS * B8_ITEMS == BIN_TILE, "the emit kernel's tile is the count kernel's");
+constexpr uint32_t BIN_SOFF = 258;      // stream offsets of a tile kept in shared memory (profiles with neighbours)
+
+// symbol k (0..15) of a run held in four words; k need not be a constant
+__device__ __forceinline__ uint32_t run_sym(const uint32_t q[4], uint32_t k) {
+  const uint32_t w = k < 8u ? (k < 4u ? q[0] : q[1]) : (k < 12u ? q[2] : q[3]);
+  return (w >> (8u * (k & 3u))) & 0xffu;
+}
 
 template <int PROF, int METH>
-__global__ void __launch_bounds__(BIN_THREADS) k_bin_emit8(isscabac_symcfg c, const uint8_t* __restrict__ sym, uint64_t n,
-                                                            const uint64_t* __restrict__ sym_off, uint32_t n_streams,
-                                                            const uint32_t* __restrict__ tile_stream, const uint32_t* __restrict__ tile_first,
-                                                            const uint64_t* __restrict__ tile_prefix, uint64_t* op_off, uint8_t* ops,
-                                                            uint64_t cap, const uint4* __restrict__ lut, const uint16_t* __restrict__ len_tab,
-                                                            uint32_t n_tiles, uint32_t tpc) {
-  __shared__ uint32_t s_warp[BIN_THREADS / 32];
-  __shared__ uint32_t s_pre[BIN_THREADS];
+__global__ void __launch_bounds__(B8_THREADS, B8_MIN_CTAS) k_bin_emit8(isscabac_symcfg c, const uint8_t* __restrict__ sym, uint64_t n,
+                                                           const uint64_t* __restrict__ sym_off, uint32_t n_streams,
+                                                           const uint32_t* __restrict__ tile_stream, const uint32_t* __restrict__ tile_first,
+                                                           const uint64_t* __restrict__ tile_prefix, uint64_t* op_off, uint8_t* ops,
+                                                           uint64_t cap, const uint4* __restrict__ lut, const uint16_t* __restrict__ len_tab,
+                                                           uint32_t n_tiles, uint32_t tpc) {
+  __shared__ uint32_t s_warp[B8_THREADS / 32];
+  __shared__ uint32_t s_pre[B8_THREADS];
   __shared__ __align__(16) uint8_t s_stage[BIN_STAGE];
-  __shared__ __align__(8) uint2 s_lut8[LUT_MAX + 1];
+  extern __shared__ __align__(8) uint2 s_lut8[];      // the fast table: geom.entries + 1 slots (the last one: "not in the table")
   __shared__ __align__(8) uint64_t s_soff[BIN_SOFF];
   __shared__ uint16_t s_len[256];
   const SymCfg cfg = fixed_cfg<PROF, METH>(c);
   const LutGeom geom = lut_geom(cfg.profile, cfg.method, cfg.Nq);
+  const uint32_t esc = geom.entries;
   const bool need_up = cfg.profile == PROFILE_ISS || cfg.profile == PROFILE_DEMO;   // the other profiles' ops do not depend on the position
-  s_len[threadIdx.x] = len_tab[threadIdx.x];
+  for (uint32_t v = threadIdx.x; v < 256u; v += B8_THREADS) s_len[v] = len_tab[v];
   if (ops) {
-    for (uint32_t e = threadIdx.x; e < geom.entries; e += BIN_THREADS) {
+    for (uint32_t e = threadIdx.x; e < geom.entries; e += B8_THREADS) {
       const uint4 q = __ldg(lut + e);
       uint2 f;
       lut8_from16(q.x, q.y, q.w, f.x, f.y);
       s_lut8[e] = f;
     }
-    if (threadIdx.x == 0) s_lut8[BIN8_ESC] = make_uint2(0u, 0u);
+    if (threadIdx.x == 0) s_lut8[esc] = make_uint2(0u, 0u);
   }
   __syncthreads();
   const uint32_t lut8 = pinned((uint32_t)__cvta_generic_to_shared(s_lut8)), stage0 = pinned((uint32_t)__cvta_generic_to_shared(s_stage));
+  const uint32_t len0 = s_len[0];
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-  const bool vec = (reinterpret_cast<uintptr_t>(sym) & 7u) == 0;
-  // the 8 symbols of this thread in tile t (zero past the end)
-  auto load_run = [&](uint32_t t, uint32_t& qx, uint32_t& qy) {
-    const uint64_t i0 = (uint64_t)t * BIN_TILE + (uint64_t)threadIdx.x * BIN_ITEMS;
-    qx = qy = 0u;
-    if (vec && i0 + BIN_ITEMS <= n) {
-      const uint2 q = __ldg(reinterpret_cast<const uint2*>(sym + i0));
-      qx = q.x;
-      qy = q.y;
+  const bool vec = (reinterpret_cast<uintptr_t>(sym) & 15u) == 0;
+  // the 16 symbols of this thread in tile t (zero past the end), as four words (scalars: an array would live in local memory)
+  auto load_run = [&](uint32_t t, uint32_t& q0, uint32_t& q1, uint32_t& q2, uint32_t& q3) {
+    const uint64_t i0 = (uint64_t)t * BIN_TILE + (uint64_t)threadIdx.x * B8_ITEMS;
+    if (vec && i0 + B8_ITEMS <= n) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(sym + i0));
+      q0 = v.x; q1 = v.y; q2 = v.z; q3 = v.w;
     } else {
-      for (uint32_t k = 0; k < BIN_ITEMS && i0 + k < n; ++k) {
-        const uint32_t b = sym[i0 + k];
-        if (k < 4u) qx |= b << (8u * k); else qy |= b << (8u * (k - 4u));
+      q0 = q1 = q2 = q3 = 0u;
+#pragma unroll 1
+      for (uint32_t k = 0; k < B8_ITEMS && i0 + k < n; ++k) {
+        const uint32_t b = (uint32_t)sym[i0 + k] << (8u * (k & 3u));
+        if (k < 4u) q0 |= b; else if (k < 8u) q1 |= b; else if (k < 12u) q2 |= b; else q3 |= b;
       }
     }
   };
@@ -486,38 +496,39 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit8(isscabac_symcfg c, co
   // A tile's inputs are asked for one tile ahead: its symbols, its first op position, the streams it touches
   // ([s_lo, s_hi], tile_stream) and the streams that start in it ([f0, f1), tile_first).  Without this the kernel is a chain
   // of dependent load latencies per tile (first measurement: phase A alone 2.25 ms at C4, phase B 1.25).
-  uint32_t nqx, nqy;
-  load_run(tile_begin, nqx, nqy);
+  uint32_t nq0, nq1, nq2, nq3;
+  load_run(tile_begin, nq0, nq1, nq2, nq3);
   uint64_t nbase = tile_prefix[tile_begin];
   uint32_t nf0 = tile_first[tile_begin], nf1 = tile_first[tile_begin + 1];
   uint32_t ns_lo = need_up ? tile_stream[tile_begin] : 0u, ns_hi = need_up ? tile_stream[tile_begin + 1] : 0u;
   for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
     const uint64_t t0 = (uint64_t)tile * BIN_TILE;
-    const uint64_t i0 = t0 + (uint64_t)threadIdx.x * BIN_ITEMS;
-    const uint32_t nvalid = i0 >= n ? 0u : (n - i0 < BIN_ITEMS ? (uint32_t)(n - i0) : (uint32_t)BIN_ITEMS);
-    const uint32_t qx = nqx, qy = nqy, f0 = nf0, f1 = nf1, s_lo = ns_lo, s_hi = ns_hi;
+    const uint32_t in_tile = n - t0 < BIN_TILE ? (uint32_t)(n - t0) : (uint32_t)BIN_TILE;       // symbols of this tile (>= 1)
+    const uint32_t r0 = threadIdx.x * B8_ITEMS;                                                // this thread's first, tile-relative
+    const uint32_t nvalid = r0 >= in_tile ? 0u : (in_tile - r0 < B8_ITEMS ? in_tile - r0 : (uint32_t)B8_ITEMS);
+    const uint64_t i0 = t0 + r0;
+    const uint32_t qa[4] = {nq0, nq1, nq2, nq3};
+    const uint32_t f0 = nf0, f1 = nf1, s_lo = ns_lo, s_hi = ns_hi;
     const uint64_t tile_base = nbase;
     if (tile + 1 < tile_end) {
-      load_run(tile + 1, nqx, nqy);
+      load_run(tile + 1, nq0, nq1, nq2, nq3);
       nbase = tile_prefix[tile + 1];
       nf0 = f1;
       nf1 = tile_first[tile + 2];
       if (need_up) { ns_lo = s_hi; ns_hi = tile_stream[tile + 2]; }
     }
-    // ---- phase A: bin counts by table, the block scan (per-thread part in s_pre, per-warp totals in s_warp: the stream
-    // pass at the end of the tile reads other threads' positions out of them)
+    // ---- phase A: bin counts by table (the symbols past the end read as zeros: their counts are taken off again), the
+    // block scan (per-thread part in s_pre, per-warp totals in s_warp: the stream pass at the end of the tile reads other
+    // threads' positions out of them)
     uint32_t tot = 0;
 #pragma unroll
-    for (int k = 0; k < BIN_ITEMS; ++k) {
-      const uint32_t vk = ((k < 4 ? qx : qy) >> (8 * (k & 3))) & 0xffu;
-      const uint32_t l = s_len[vk];
-      tot += (uint32_t)k < nvalid ? l : 0u;
-    }
+    for (int k = 0; k < B8_ITEMS; ++k) tot += s_len[(qa[k >> 2] >> (8 * (k & 3))) & 0xffu];
+    tot -= (B8_ITEMS - nvalid) * len0;
     // the offsets of the streams this tile touches, in shared memory: every thread looks its stream up in them
     const uint32_t n_soff = s_hi - s_lo + 2u;
     const bool soff_shared = need_up && n_soff <= BIN_SOFF;
     if (soff_shared)
-      for (uint32_t j = threadIdx.x; j < n_soff; j += BIN_THREADS) s_soff[j] = sym_off[s_lo + j];
+      for (uint32_t j = threadIdx.x; j < n_soff; j += B8_THREADS) s_soff[j] = sym_off[s_lo + j];
     uint32_t inc = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -529,7 +540,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit8(isscabac_symcfg c, co
     __syncthreads();
     uint32_t lo = inc - tot, block_total = 0;
 #pragma unroll
-    for (uint32_t w = 0; w < BIN_THREADS / 32; ++w) {
+    for (uint32_t w = 0; w < B8_THREADS / 32; ++w) {
       const uint32_t t = s_warp[w];
       if (w < wid) lo += t;
       block_total += t;
@@ -542,16 +553,16 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit8(isscabac_symcfg c, co
       const uint64_t* so = soff_shared ? s_soff - s_lo : sym_off;
       uint32_t s = find_stream(so, s_lo, s_hi + 1, i0);
       uint64_t start = so[s], next = so[s + 1];
-      if (i0 > start && i0 + BIN_ITEMS <= next) {
+      if (i0 > start && i0 + B8_ITEMS <= next) {
         // the whole run lies inside one stream, away from its first symbol: the neighbour flags follow from the row of
         // the run's first symbol
         if (cfg.profile == PROFILE_DEMO || cfg.rows == 0) {
-          up_mask = 0xffu;
+          up_mask = 0xffffu;
         } else {
           const uint64_t rel = i0 - start;
           uint32_t r = rel >> 32 ? (uint32_t)(rel % cfg.rows) : (uint32_t)rel % cfg.rows;
 #pragma unroll
-          for (int k = 0; k < BIN_ITEMS; ++k) {
+          for (int k = 0; k < B8_ITEMS; ++k) {
             if (r != 0) up_mask |= 1u << k;
             if (++r == cfg.rows) r = 0;
           }
@@ -581,85 +592,90 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit8(isscabac_symcfg c, co
       for (uint32_t w0 = 0; w0 < span; w0 += BIN_STAGE) {
         bin_acc_start(A, pos);
         const uint32_t wp_first = A.wp, fb_first = A.fb;
-        // the common case -- the whole tile in the stage, 8 symbols, all strings in the fast table -- is straight-line:
-        // 8 table loads, then 8 appends
-        bool fast = span <= BIN_STAGE && nvalid == BIN_ITEMS;
-        uint2 e[BIN_ITEMS];
-        if (fast) {
-          uint32_t all = 0xffffffffu;
+        StageWindow sw{stage0, w0};
+        if (pos < w0 + BIN_STAGE && pos + tot + 4u > w0) {    // (span and w0 are the block's: the barriers below are met by all)
+          // the common case -- the whole tile in the stage, 8 symbols in a row whose strings are all in the fast table --
+          // is straight-line: 8 table loads, then 8 appends.  Otherwise symbol by symbol: a tile larger than the stage
+          // leaves in rounds (every thread appends all its symbols in every round it has a byte in, the stores outside
+          // the round's window are dropped), and the last tile's short runs come this way too.
 #pragma unroll
-          for (int k = 0; k < BIN_ITEMS; ++k) {
-            const uint32_t vk = ((k < 4 ? qx : qy) >> (8 * (k & 3))) & 0xffu;
-            const uint32_t uk = k == 0 ? before : (((k - 1 < 4 ? qx : qy) >> (8 * ((k - 1) & 3))) & 0xffu);
-            uint32_t idx;
-            e[k] = bin8_entry(cfg, geom.dom, lut8, vk, uk, (up_mask >> k) & 1u, idx);
-            all = min(all, e[k].y);
-          }
-          fast = all >> 24;        // every length is at least 1
-        }
-        if (fast) {
-          StageStore st{stage0};
+          for (int h = 0; h < B8_ITEMS; h += 8) {
+            bool fast = span <= BIN_STAGE && nvalid == B8_ITEMS;
+            uint2 e[8];
+            if (fast) {
+              // (this half's two words again, opaque to the compiler and in program order behind the previous half's
+              // appends: it would otherwise form all 16 table addresses ahead -- from phase A's byte extraction, across the
+              // barrier -- and keep them in local memory)
+              const uint32_t qh[2] = {pinned(qa[h >> 2]), pinned(qa[(h >> 2) + 1])};
+              const uint32_t ub = h == 0 ? before : qa[(h >> 2) - 1] >> 24;
+              uint32_t all = 0xffffffffu;
 #pragma unroll
-          for (int k = 0; k < BIN_ITEMS; ++k) bin_append(A, st, e[k].x, e[k].y & 0x00ffffffu, e[k].y >> 24);
-        } else if (pos < w0 + BIN_STAGE && pos + tot + 4u > w0) {    // (span and w0 are the block's: the barriers below are met by all)
-          // a tile larger than the stage leaves in rounds (every thread appends all its symbols in every round it has a
-          // byte in, the stores outside the round's window are dropped); the last tile's short runs come here too
-          StageWindow st{s_stage, w0};
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t vk = (qh[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                const uint32_t uk = k == 0 ? ub : ((qh[(k - 1) >> 2] >> (8 * ((k - 1) & 3))) & 0xffu);
+                uint32_t idx;
+                e[k] = bin8_entry(cfg, geom.dom, esc, lut8, vk, uk, (up_mask >> (h + k)) & 1u, idx);
+                all = min(all, e[k].y);
+              }
+              fast = all >> 24;        // every length is at least 1
+            }
+            if (fast) {
+              StageStore st{stage0};
+#pragma unroll
+              for (int k = 0; k < 8; ++k) bin_append(A, st, e[k].x, e[k].y & 0x00ffffffu, e[k].y >> 24);
+            } else {
+              const uint32_t kend = nvalid < (uint32_t)h + 8u ? nvalid : (uint32_t)h + 8u;
 #pragma unroll 1
-          for (uint32_t k = 0; k < nvalid; ++k) {
-            const uint32_t vk = ((k < 4u ? qx : qy) >> (8u * (k & 3u))) & 0xffu;
-            const uint32_t uk = k == 0u ? before : (((k - 1u < 4u ? qx : qy) >> (8u * ((k - 1u) & 3u))) & 0xffu);
-            bin8_symbol(cfg, geom.dom, geom.entries, lut8, lut, A, st, vk, uk, (up_mask >> k) & 1u);
+              for (uint32_t k = h; k < kend; ++k)
+                bin8_symbol(cfg, geom.dom, geom.entries, lut8, lut, A, sw, run_sym(qa, k), k == 0u ? before : run_sym(qa, k - 1u), (up_mask >> k) & 1u);
+            }
           }
         } else {
           A.a0 = 0u;                     // nothing of this thread in the window: neither words nor tail bytes
           A.fb = 0u;
         }
         __syncthreads();       // every word is in the stage: now the incomplete last words, byte by byte
-        {
-          StageWindow st{s_stage, w0};
-          bin_tail(A, st, wp_first, fb_first);
-        }
+        bin_tail(A, sw, wp_first, fb_first);
         __syncthreads();
         // pieces of this window: stage bytes [16 p, 16 p + 16) <-> tile positions [w0 + 16 p - skew, ...)
         const uint32_t w1 = w0 + BIN_STAGE;
         const uint32_t wend = w1 < span ? w1 : span;
         const uint32_t npieces = (wend - w0 + 15u) >> 4;
-        for (uint32_t pc = threadIdx.x; pc < npieces; pc += BIN_THREADS) {
+        for (uint32_t pc = threadIdx.x; pc < npieces; pc += B8_THREADS) {
           const int32_t pbeg = (int32_t)(w0 + 16u * pc) - (int32_t)skew;           // tile position of byte 0 of the piece
           const uint32_t e0 = pbeg < 0 ? (uint32_t)(-pbeg) : 0u;                   // valid bytes: [e0, e1)
           const int32_t left = (int32_t)room - pbeg;
           const uint32_t e1 = left <= 0 ? 0u : (left < 16 ? (uint32_t)left : 16u);
           if (e0 >= e1) continue;
-          const uint4 q = *reinterpret_cast<const uint4*>(s_stage + 16u * pc);
+          uint4 qq;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(qq.x), "=r"(qq.y), "=r"(qq.z), "=r"(qq.w) : "r"(stage0 + 16u * pc) : "memory");
           uint8_t* dst = ops + tile_base + pbeg;       // 16-byte aligned by the choice of skew
           if (e0 == 0 && e1 == 16) {
-            *reinterpret_cast<uint4*>(dst) = q;
+            *reinterpret_cast<uint4*>(dst) = qq;
           } else {
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (uint32_t e = 0; e < 16; ++e)
-              if (e >= e0 && e < e1) dst[e] = (uint8_t)(w[e >> 2] >> (8u * (e & 3u)));
+            const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll 1
+            for (uint32_t e = e0; e < e1; ++e) dst[e] = (uint8_t)(w[e >> 2] >> (8u * (e & 3u)));
           }
         }
         if (w1 < span) __syncthreads();          // the next round overwrites the stage
       }
     }
     // ---- the stream pass: op_off of the streams that start in this tile, one stream per thread.  A stream that starts
-    // at tile position p begins with symbol p % 8 of thread p / 8: that thread's first op position is in s_pre / s_warp,
-    // the counts of the symbols in front are looked up again (at most 7 bytes, in L1 since the tile was loaded).
+    // at tile position p begins with symbol p % 16 of thread p / 16: that thread's first op position is in s_pre / s_warp,
+    // the counts of the symbols in front are looked up again (at most 15 bytes, in L1 since the tile was loaded).
     {
       uint64_t so_e = my_soff;
-      for (uint32_t e = f0 + threadIdx.x; e < f1; e += BIN_THREADS) {
+      for (uint32_t e = f0 + threadIdx.x; e < f1; e += B8_THREADS) {
         if (e != f0 + threadIdx.x) so_e = sym_off[e];
-        const uint32_t p = (uint32_t)(so_e - t0), owner = p >> 3;
+        const uint32_t p = (uint32_t)(so_e - t0), owner = p / B8_ITEMS;
         uint32_t o = s_pre[owner];
         for (uint32_t w = 0; w < (owner >> 5); ++w) o += s_warp[w];
-        for (uint32_t j = 0; j < (p & 7u); ++j) o += s_len[sym[t0 + (p & ~7u) + j]];
+        for (uint32_t j = 0; j < p % B8_ITEMS; ++j) o += s_len[sym[t0 + (p - p % B8_ITEMS) + j]];
         op_off[e] = tile_base + o;
       }
       if (tile + 1 == n_tiles)      // the streams at the very end are empty; op_off[n_streams] = the total
-        for (uint32_t e = f1 + threadIdx.x; e <= n_streams; e += BIN_THREADS) op_off[e] = tile_base + block_total;
+        for (uint32_t e = f1 + threadIdx.x; e <= n_streams; e += B8_THREADS) op_off[e] = tile_base + block_total;
     }
     __syncthreads();       // s_pre, s_warp, s_soff and the stage are free for the next tile
   }
@@ -1989,7 +2005,7 @@ int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const
   uint32_t tpc = 1;
   while (tpc < 8u && tiles / (tpc * 2u) >= (uint32_t)sm_count() * 8u) tpc *= 2u;
 #define BIN_EMIT8(PR, ME) \
-  k_bin_emit8<PR, ME><<<(tiles + tpc - 1) / tpc, BIN_THREADS, 0, st>>>(*cfg, static_cast<const uint8_t*>(d_symbols), n_symbols, d_sym_off, n_streams, \
+  k_bin_emit8<PR, ME><<<(tiles + tpc - 1) / tpc, B8_THREADS, (geom.entries + 1) * sizeof(uint2), st>>>(*cfg, static_cast<const uint8_t*>(d_symbols), n_symbols, d_sym_off, n_streams, \
                                                                       tile_stream, tile_first, tile_prefix, d_op_off, d_ops, ops_cap, lut, len_tab, tiles, tpc)
 #define BIN_EMIT(WW, PR, ME) \
   k_bin_emit<WW, PR, ME><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, d_sym_off, n_streams, tile_stream, tile_prefix, d_op_off, d_ops, ops_cap, lut)

@@ -120,7 +120,7 @@ struct EmulStage {
 uint64_t emul_bin_emit8(const int32_t* cfgv, const uint8_t* sym, uint64_t n, uint8_t* ops, uint32_t skew0,
                         uint32_t stage_bytes, int order) {
   SymCfg cfg{cfgv[0], cfgv[1], (uint32_t)cfgv[2], cfgv[3], (uint32_t)cfgv[4], (uint32_t)cfgv[5]};
-  const uint32_t T = 256, ITEMS = 8, TILE = T * ITEMS;
+  const uint32_t T = 128, ITEMS = 16, TILE = T * ITEMS;      // the kernel's geometry
   const LutGeom geom = lut_geom(cfg.profile, cfg.method, cfg.Nq);
   std::vector<uint32_t> lut16(4 * (LUT_MAX + 1), 0u), lut8(2 * (LUT_MAX + 1), 0u);
   for (uint32_t e = 0; e < geom.entries; ++e) {
@@ -134,7 +134,7 @@ uint64_t emul_bin_emit8(const int32_t* cfgv, const uint8_t* sym, uint64_t n, uin
   for (uint32_t t = 0; t < T; ++t) perm[t] = order == 0 ? t : (order == 1 ? T - 1 - t : (t < T / 2 ? 2 * t + 1 : 2 * (t - T / 2)));
   uint64_t tile_base = 0;
   for (uint64_t t0 = 0; t0 < n; t0 += TILE) {
-    uint32_t lo[256], tot[256], nvalid[256];
+    uint32_t lo[128], tot[128], nvalid[128];
     uint32_t block_total = 0;
     for (uint32_t t = 0; t < T; ++t) {
       const uint64_t i0 = t0 + (uint64_t)t * ITEMS;
@@ -147,8 +147,8 @@ uint64_t emul_bin_emit8(const int32_t* cfgv, const uint8_t* sym, uint64_t n, uin
     const uint32_t skew = (uint32_t)((skew0 + tile_base) & 15u), span = block_total + skew;
     for (uint32_t w0 = 0; w0 < span; w0 += stage_bytes) {
       std::fill(stage.begin(), stage.end(), (uint8_t)0xEE);
-      BinAcc acc[256];
-      uint32_t wpf[256], fbf[256];
+      BinAcc acc[128];
+      uint32_t wpf[128], fbf[128];
       EmulStage st{stage.data(), w0, stage_bytes};
       for (uint32_t tt = 0; tt < T; ++tt) {
         const uint32_t t = perm[tt];
