@@ -189,10 +189,11 @@ __global__ void k_bin_lut(isscabac_symcfg c, uint4* lut) {
   lut[e] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 // bin count of every 8-bit symbol value (the u8 kernels sum and scan table entries instead of evaluating the closed form)
-__global__ void k_bin_lentab(isscabac_symcfg c, uint16_t* len_tab) {
+// (one byte per value: the host takes the closed-form kernels when a count does not fit)
+__global__ void k_bin_lentab(isscabac_symcfg c, uint8_t* len_tab) {
   const SymCfg cfg = to_cfg(c);
   const uint32_t l = sym_code(threadIdx.x, cfg.Nq, cfg.method).len;
-  len_tab[threadIdx.x] = (uint16_t)(l < 0xffffu ? l : 0xffffu);
+  len_tab[threadIdx.x] = (uint8_t)(l < 0xffu ? l : 0xffu);
 }
 
 // Pass 2.  Phase A (symbol-parallel, 8 symbols per thread): codes, block scan, the op_off entries of the streams that
@@ -353,9 +354,9 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, con
 //                  store -- bin_emit.cuh has the scheme, its proof obligations and the host emulation's entry points.
 //                  A CTA walks `tpc` consecutive tiles, so the tables are set up once per 8 K symbols or more.
 
-__global__ void __launch_bounds__(BIN_THREADS) k_bin_count8(const uint8_t* __restrict__ sym, uint64_t n, const uint16_t* __restrict__ len_tab,
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_count8(const uint8_t* __restrict__ sym, uint64_t n, const uint8_t* __restrict__ len_tab,
                                                              uint32_t n_tiles, uint32_t* __restrict__ tile_sums) {
-  __shared__ uint16_t s_len[256];
+  __shared__ uint8_t s_len[256];
   s_len[threadIdx.x] = len_tab[threadIdx.x];
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
@@ -448,14 +449,14 @@ __global__ void __launch_bounds__(B8_THREADS, B8_MIN_CTAS) k_bin_emit8(isscabac_
                                                            const uint64_t* __restrict__ sym_off, uint32_t n_streams,
                                                            const uint32_t* __restrict__ tile_stream, const uint32_t* __restrict__ tile_first,
                                                            const uint64_t* __restrict__ tile_prefix, uint64_t* op_off, uint8_t* ops,
-                                                           uint64_t cap, const uint4* __restrict__ lut, const uint16_t* __restrict__ len_tab,
+                                                           uint64_t cap, const uint4* __restrict__ lut, const uint8_t* __restrict__ len_tab,
                                                            uint32_t n_tiles, uint32_t tpc) {
   __shared__ uint32_t s_warp[B8_THREADS / 32];
   __shared__ uint32_t s_pre[B8_THREADS];
   __shared__ __align__(16) uint8_t s_stage[BIN_STAGE];
   extern __shared__ __align__(8) uint2 s_lut8[];      // the fast table: geom.entries + 1 slots (the last one: "not in the table")
   __shared__ __align__(8) uint64_t s_soff[BIN_SOFF];
-  __shared__ uint16_t s_len[256];
+  __shared__ uint8_t s_len[256];
   const SymCfg cfg = fixed_cfg<PROF, METH>(c);
   const LutGeom geom = lut_geom(cfg.profile, cfg.method, cfg.Nq);
   const uint32_t esc = geom.entries;
@@ -637,25 +638,29 @@ __global__ void __launch_bounds__(B8_THREADS, B8_MIN_CTAS) k_bin_emit8(isscabac_
         __syncthreads();       // every word is in the stage: now the incomplete last words, byte by byte
         bin_tail(A, sw, wp_first, fb_first);
         __syncthreads();
-        // pieces of this window: stage bytes [16 p, 16 p + 16) <-> tile positions [w0 + 16 p - skew, ...)
+        // The window leaves: stage byte b <-> op array byte ops + tile_base - skew + b, so the stage's 16-byte pieces are
+        // the op array's aligned ones.  Whole pieces with one LDS.128 + STG.128 each; the (at most two) incomplete ones --
+        // in front of the tile's first op, behind its last or behind the caller's capacity -- byte by byte by warp 0.
         const uint32_t w1 = w0 + BIN_STAGE;
         const uint32_t wend = w1 < span ? w1 : span;
-        const uint32_t npieces = (wend - w0 + 15u) >> 4;
-        for (uint32_t pc = threadIdx.x; pc < npieces; pc += B8_THREADS) {
-          const int32_t pbeg = (int32_t)(w0 + 16u * pc) - (int32_t)skew;           // tile position of byte 0 of the piece
-          const uint32_t e0 = pbeg < 0 ? (uint32_t)(-pbeg) : 0u;                   // valid bytes: [e0, e1)
-          const int32_t left = (int32_t)room - pbeg;
-          const uint32_t e1 = left <= 0 ? 0u : (left < 16 ? (uint32_t)left : 16u);
-          if (e0 >= e1) continue;
-          uint4 qq;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(qq.x), "=r"(qq.y), "=r"(qq.z), "=r"(qq.w) : "r"(stage0 + 16u * pc) : "memory");
-          uint8_t* dst = ops + tile_base + pbeg;       // 16-byte aligned by the choice of skew
-          if (e0 == 0 && e1 == 16) {
-            *reinterpret_cast<uint4*>(dst) = qq;
-          } else {
-            const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
-#pragma unroll 1
-            for (uint32_t e = e0; e < e1; ++e) dst[e] = (uint8_t)(w[e >> 2] >> (8u * (e & 3u)));
+        const uint32_t vb = w0 > skew ? w0 : skew, ve = wend < room + skew ? wend : room + skew;     // bytes of the window to write
+        if (vb < ve) {
+          uint8_t* gbase = ops + tile_base - skew;
+          const uint32_t fb0 = (vb + 15u) & ~15u, fe0 = ve & ~15u;
+          for (uint32_t bb = fb0 + threadIdx.x * 16u; bb < fe0; bb += B8_THREADS * 16u) {
+            uint4 qq;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(qq.x), "=r"(qq.y), "=r"(qq.z), "=r"(qq.w) : "r"(stage0 + bb - w0) : "memory");
+            *reinterpret_cast<uint4*>(gbase + bb) = qq;
+          }
+          if (threadIdx.x < 32u) {
+            const bool tail = threadIdx.x >= 16u;
+            const uint32_t hb = tail ? (fe0 > fb0 ? fe0 : fb0) + (threadIdx.x - 16u) : vb + threadIdx.x;
+            const uint32_t he = tail ? (fe0 >= fb0 ? ve : 0u) : (fb0 < ve ? fb0 : ve);
+            if (hb < he) {
+              uint32_t byte;
+              asm volatile("ld.shared.u8 %0, [%1];" : "=r"(byte) : "r"(stage0 + hb - w0) : "memory");
+              gbase[hb] = (uint8_t)byte;
+            }
           }
         }
         if (w1 < span) __syncthreads();          // the next round overwrites the stage
@@ -1983,12 +1988,14 @@ int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const
   k_bin_tile_streams<<<(tiles + 1 + 255) / 256, 256, 0, st>>>(d_sym_off, n_streams, n_symbols, tiles, tile_stream, tile_first);
   uint4* lut = reinterpret_cast<uint4*>(static_cast<uint8_t*>(scan_scr) + ((cabac_compact_scratch_bytes(tiles) + 255) & ~(size_t)255));
   const LutGeom geom = lut_geom(cfg->profile, cfg->method, cfg->Nq);
-  uint16_t* len_tab = reinterpret_cast<uint16_t*>(lut + LUT_MAX);
+  uint8_t* len_tab = reinterpret_cast<uint8_t*>(lut + LUT_MAX);
   if (d_ops && geom.entries) k_bin_lut<<<(geom.entries + 127) / 128, 128, 0, st>>>(*cfg, lut);
   // 8-bit symbols: counts by table, ops appended word-wise (k_bin_count8 / k_bin_emit8); ISSCABAC_BIN8=0 keeps the
   // closed-form kernels (both run against the oracle in the tests)
   const char* bin8_env = getenv("ISSCABAC_BIN8");
-  const bool bin8 = sym_width == 1 && !(bin8_env && bin8_env[0] == '0');
+  bool bin8 = sym_width == 1 && !(bin8_env && bin8_env[0] == '0');
+  if (bin8)      // the count table holds bytes (a string of 256 ops: unary codes of the value 255)
+    for (uint32_t v = 0; v < 256u && bin8; ++v) bin8 = sym_code(v, cfg->Nq, cfg->method).len <= 255u;
   if (bin8) k_bin_lentab<<<1, 256, 0, st>>>(*cfg, len_tab);
 #define BIN_COUNT(WW, ME) k_bin_count<WW, ME><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, tile_sums)
   if (bin8 && (reinterpret_cast<uintptr_t>(d_symbols) & 15u) == 0)
