@@ -668,6 +668,21 @@ def cfg_c4(env):
            "compaction_plus_exchange_ms": ms_p2p, "decode_ms": ms_dec, "decode_gbins": tot_bins / (ms_dec * 1e-3) / 1e9,
            "assembled_payload_bytes": total_bytes, "bits_per_symbol": 8.0 * total_bytes / (n_total * per)}
     out.update(env.fracs(ms_fused, (n * per + 4 * n) + 2 * pb + pb * max(env.world - 1, 0), _int_ops(n_bins - n_ep, n_ep, pb, True)))
+    if env.world == 1:
+        # the two-pass route beside the fused one: symbol-parallel binarizer (the two-call API: offsets, then ops) -> op-array
+        # encoder; same bytes.  The binarizer is HBM work: algorithmically 2 x symbols in (once to size the op array, once to fill it) + the ops out.
+        ms_bin = env.timed(lambda: I.binarize_symbols(cfg, sym, off))
+        ops, op_off2 = I.binarize_symbols(cfg, sym, off)
+        enc2 = I.Encoded(torch.empty((n, stride), dtype=torch.uint8, device=env.dev), torch.empty(n, dtype=torch.int32, device=env.dev),
+                         torch.zeros(4, dtype=torch.int32, device=env.dev))
+        ms_eops = env.timed(lambda: I.encode_ops(ops, op_off2, ctx, out=enc2))
+        assert bool((enc2.lengths == enc.lengths).all().item()) and bool((enc2.slab[::4097] == enc.slab[::4097]).all().item()), \
+            "c4: fused and two-pass encoders disagree"
+        bin_bytes = 2 * n * per + int(ops.numel()) + 16 * (n + 1)
+        out["encode_two_pass_ms"] = {"binarize_two_call_api": ms_bin, "encode_ops": ms_eops,
+                                     "binarize_hbm_frac": bin_bytes / (ms_bin * 1e-3) / 1e9 / env.hbm_peak,
+                                     "binarize_algorithmic_bytes": bin_bytes}
+        del ops, op_off2, enc2
     if env.rank == 0 and env.world == 1 and not a.no_cpu:
         out["cpu_baseline"] = _cpu_symbols(env, cfg_args, sym, off.cpu().numpy(), _sample_ids(n, 2048), np.full(8, 1, np.uint8), enc, "c4")
     mg.close_symmetric()
