@@ -676,8 +676,10 @@ def cfg_c4(env):
         enc2 = I.Encoded(torch.empty((n, stride), dtype=torch.uint8, device=env.dev), torch.empty(n, dtype=torch.int32, device=env.dev),
                          torch.zeros(4, dtype=torch.int32, device=env.dev))
         ms_eops = env.timed(lambda: I.encode_ops(ops, op_off2, ctx, out=enc2))
-        assert bool((enc2.lengths == enc.lengths).all().item()) and bool((enc2.slab[::4097] == enc.slab[::4097]).all().item()), \
-            "c4: fused and two-pass encoders disagree"
+        assert bool((enc2.lengths == enc.lengths).all().item()), "c4: fused and two-pass encoders disagree"
+        for s_id in _sample_ids(n, 64):       # the bytes of a stream sample (a slab row is only defined up to its length)
+            ln = int(enc.lengths[s_id].item())
+            assert bool((enc2.slab[s_id, :ln] == enc.slab[s_id, :ln]).all().item()), "c4: fused and two-pass encoders disagree"
         bin_bytes = 2 * n * per + int(ops.numel()) + 16 * (n + 1)
         out["encode_two_pass_ms"] = {"binarize_two_call_api": ms_bin, "encode_ops": ms_eops,
                                      "binarize_hbm_frac": bin_bytes / (ms_bin * 1e-3) / 1e9 / env.hbm_peak,
