@@ -197,7 +197,9 @@ int cabac_multi_gpu_barrier(isscabac_mgpu* mg, void* stream);
 /* ---- symbol level: binarizer + context selection on device ---------------- */
 /* symbols -> ops (u8 op format).  Two calls: with d_ops == NULL only d_op_off[0..n_streams]
  * (u64, exclusive scan of bins per stream) is produced; then call again with a d_ops buffer of
- * at least op_off[n_streams] bytes.  sym_width 1, 2 or 4 bytes per symbol.
+ * at least op_off[n_streams] bytes (a caller that knows a bound for the op count can skip the first call: a call with
+ * d_ops fills d_op_off too, and writes no op past ops_cap).  sym_width 1, 2 or 4 bytes per symbol; 8-bit symbols take the
+ * table kernels (bin counts and op strings by table, one table load and a word-wise append per symbol).
  * d_scratch: cabac_binarize_scratch_bytes(n_symbols) bytes. */
 size_t cabac_binarize_scratch_bytes(uint64_t n_symbols, uint32_t n_streams);
 int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_sym_off,
