@@ -113,9 +113,16 @@ def fuzz_symbols(rng):
         os.environ.pop("ISSCABAC_SYM_TREE")
         assert bool(ok.all().item()) and (dec.cpu().numpy().view(dt)[:n] == sym).all(), ("symbol decode", tree)
     if n:
-        ops, op_off = I.binarize_symbols(cfg, sym, off.astype(np.int64))
-        want = np.concatenate([O.symbols_to_ops(ocfg, sym[int(off[s]):int(off[s + 1])]) for s in range(n_streams)])
-        assert (ops.cpu().numpy() == want).all(), "binarizer"
+        per_stream = [O.symbols_to_ops(ocfg, sym[int(off[s]):int(off[s + 1])]) for s in range(n_streams)]
+        want = np.concatenate(per_stream)
+        want_off = np.zeros(n_streams + 1, dtype=np.int64)
+        np.cumsum([len(x) for x in per_stream], out=want_off[1:])
+        for bin8 in (("1", "0") if dt == np.uint8 else ("1",)):     # u8 symbols: the table kernels and the closed-form ones
+            os.environ["ISSCABAC_BIN8"] = bin8
+            ops, op_off = I.binarize_symbols(cfg, sym, off.astype(np.int64))
+            os.environ.pop("ISSCABAC_BIN8")
+            assert (ops.cpu().numpy() == want).all(), ("binarizer", bin8)
+            assert (op_off.cpu().numpy() == want_off).all(), ("binarizer offsets", bin8)
     return n
 
 
