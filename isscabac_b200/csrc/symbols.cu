@@ -68,6 +68,7 @@ __device__ __forceinline__ SymCfg to_cfg(const isscabac_symcfg& c) {
 // records op_off[s]): one binary search per tile, a short one per thread inside the tile's range.
 // HBM traffic: 2 x symbols in, ops out, 12 B per tile.
 constexpr int BIN_THREADS = 256, BIN_ITEMS = 8, BIN_TILE = BIN_THREADS * BIN_ITEMS;
+constexpr uint32_t BIN_CHUNKS = BIN_TILE / 64;      // k_bin_count8 / k_bin_offsets8: runs of 64 symbols per tile
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& block_total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(isscabac_symcfg c, con
 //                  A CTA walks `tpc` consecutive tiles, so the tables are set up once per 8 K symbols or more.
 
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_count8(const uint8_t* __restrict__ sym, uint64_t n, const uint8_t* __restrict__ len_tab,
-                                                             uint32_t n_tiles, uint32_t* __restrict__ tile_sums) {
+                                                             uint32_t n_tiles, uint32_t* __restrict__ tile_sums, uint16_t* __restrict__ chunks) {
   __shared__ uint8_t s_len[256];
   s_len[threadIdx.x] = len_tab[threadIdx.x];
   __syncthreads();
@@ -367,17 +368,52 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_count8(const uint8_t* __res
 #pragma unroll
   for (int j = 0; j < BIN_TILE / (32 * 16); ++j) {
     const uint64_t b = t0 + (uint64_t)(lane + 32u * j) * 16u;
+    uint32_t c = 0;
     if (b + 16u <= n) {
       const uint4 q = __ldg(reinterpret_cast<const uint4*>(sym + b));
       const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-      for (int k = 0; k < 16; ++k) tot += s_len[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
+      for (int k = 0; k < 16; ++k) c += s_len[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
     } else {
-      for (uint64_t i = b; i < n && i < b + 16u; ++i) tot += s_len[sym[i]];
+      for (uint64_t i = b; i < n && i < b + 16u; ++i) c += s_len[sym[i]];
+    }
+    tot += c;
+    if (chunks) {      // the sizing call: bin counts of the tile's 32 runs of 64 symbols (four neighbouring lanes each) for k_bin_offsets8
+      c += __shfl_xor_sync(0xffffffffu, c, 1);
+      c += __shfl_xor_sync(0xffffffffu, c, 2);
+      if ((lane & 3u) == 0u) chunks[(size_t)tile * BIN_CHUNKS + 8u * j + (lane >> 2)] = (uint16_t)c;
     }
   }
   tot = __reduce_add_sync(0xffffffffu, tot);
   if (lane == 0) tile_sums[tile] = tot;
+}
+
+// The sizing call's offsets, one thread per stream: op_off[e] = the op position of symbol sym_off[e] = its tile's first op
+// (the scan over the tile sums) + the counts of the 64-symbol runs in front of it inside the tile (k_bin_count8) + the counts
+// of the at most 63 symbols in front of it inside its run.  No second walk over the symbols (the emit kernel's phase A took
+// 0.55 ms of the 0.81 ms sizing call at C4).
+__global__ void __launch_bounds__(256) k_bin_offsets8(const uint8_t* __restrict__ sym, uint64_t n, const uint64_t* __restrict__ sym_off,
+                                                       uint32_t n_streams, const uint8_t* __restrict__ len_tab, uint32_t n_tiles,
+                                                       const uint64_t* __restrict__ tile_prefix, const uint16_t* __restrict__ chunks,
+                                                       uint64_t* __restrict__ op_off) {
+  __shared__ uint8_t s_len[256];
+  s_len[threadIdx.x] = len_tab[threadIdx.x];
+  __syncthreads();
+  const uint64_t e = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+  if (e > n_streams) return;
+  const uint64_t so = sym_off[e];
+  if (so >= n) {           // the empty streams at the very end, and the total
+    op_off[e] = tile_prefix[n_tiles];
+    return;
+  }
+  const uint32_t tile = (uint32_t)(so / BIN_TILE), p = (uint32_t)(so % BIN_TILE), run = p / 64u;
+  uint64_t o = tile_prefix[tile];
+  const uint16_t* c = chunks + (size_t)tile * BIN_CHUNKS;
+  uint32_t acc = 0;
+  for (uint32_t r = 0; r < run; ++r) acc += c[r];
+  const uint8_t* s0 = sym + (so - p % 64u);
+  for (uint32_t j = 0; j < p % 64u; ++j) acc += s_len[s0[j]];
+  op_off[e] = o + acc;
 }
 
 struct StageStore {            // the whole tile is in the stage; `stage` = its shared-window address
@@ -1958,7 +1994,8 @@ size_t cabac_binarize_scratch_bytes(uint64_t n_symbols, uint32_t n_streams) {
   const size_t sums = ((size_t)tiles * 4 + 255) & ~(size_t)255;
   const size_t pref = (((size_t)tiles + 1) * 8 + 255) & ~(size_t)255;
   const size_t tstr = (((size_t)tiles + 1) * 4 + 255) & ~(size_t)255;
-  return sums + pref + 2 * tstr + ((cabac_compact_scratch_bytes((uint32_t)tiles) + 255) & ~(size_t)255) + LUT_MAX * sizeof(uint4) + 512 + 256;
+  const size_t chk = ((size_t)tiles * BIN_CHUNKS * sizeof(uint16_t) + 255) & ~(size_t)255;
+  return sums + pref + 2 * tstr + chk + ((cabac_compact_scratch_bytes((uint32_t)tiles) + 255) & ~(size_t)255) + LUT_MAX * sizeof(uint4) + 512 + 256;
 }
 
 int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const uint64_t* d_sym_off,
@@ -1984,22 +2021,34 @@ int cabac_binarize_symbols(const isscabac_symcfg* cfg, uint32_t n_streams, const
   const size_t tstr_b = (((size_t)tiles + 1) * 4 + 255) & ~(size_t)255;
   uint32_t* tile_stream = reinterpret_cast<uint32_t*>(scr + sums_b + pref_b);
   uint32_t* tile_first = reinterpret_cast<uint32_t*>(scr + sums_b + pref_b + tstr_b);
-  void* scan_scr = scr + sums_b + pref_b + 2 * tstr_b;
-  k_bin_tile_streams<<<(tiles + 1 + 255) / 256, 256, 0, st>>>(d_sym_off, n_streams, n_symbols, tiles, tile_stream, tile_first);
+  const size_t chk_b = ((size_t)tiles * BIN_CHUNKS * sizeof(uint16_t) + 255) & ~(size_t)255;
+  uint16_t* chunks = reinterpret_cast<uint16_t*>(scr + sums_b + pref_b + 2 * tstr_b);
+  void* scan_scr = scr + sums_b + pref_b + 2 * tstr_b + chk_b;
   uint4* lut = reinterpret_cast<uint4*>(static_cast<uint8_t*>(scan_scr) + ((cabac_compact_scratch_bytes(tiles) + 255) & ~(size_t)255));
   const LutGeom geom = lut_geom(cfg->profile, cfg->method, cfg->Nq);
   uint8_t* len_tab = reinterpret_cast<uint8_t*>(lut + LUT_MAX);
-  if (d_ops && geom.entries) k_bin_lut<<<(geom.entries + 127) / 128, 128, 0, st>>>(*cfg, lut);
   // 8-bit symbols: counts by table, ops appended word-wise (k_bin_count8 / k_bin_emit8); ISSCABAC_BIN8=0 keeps the
   // closed-form kernels (both run against the oracle in the tests)
   const char* bin8_env = getenv("ISSCABAC_BIN8");
   bool bin8 = sym_width == 1 && !(bin8_env && bin8_env[0] == '0');
   if (bin8)      // the count table holds bytes (a string of 256 ops: unary codes of the value 255)
     for (uint32_t v = 0; v < 256u && bin8; ++v) bin8 = sym_code(v, cfg->Nq, cfg->method).len <= 255u;
+  const bool count8 = bin8 && (reinterpret_cast<uintptr_t>(d_symbols) & 15u) == 0;
   if (bin8) k_bin_lentab<<<1, 256, 0, st>>>(*cfg, len_tab);
+  if (count8 && !d_ops) {
+    // the sizing call: the offsets come out of the count pass (k_bin_offsets8), the symbols are read once
+    k_bin_count8<<<(tiles + BIN_THREADS / 32 - 1) / (BIN_THREADS / 32), BIN_THREADS, 0, st>>>(static_cast<const uint8_t*>(d_symbols), n_symbols, len_tab, tiles, tile_sums, chunks);
+    if ((rc = exclusive_scan_u32_u64(tile_sums, tile_prefix, tiles, scan_scr, st))) return rc;
+    k_bin_offsets8<<<(uint32_t)(((uint64_t)n_streams + 1 + 255) / 256), 256, 0, st>>>(static_cast<const uint8_t*>(d_symbols), n_symbols, d_sym_off, n_streams, len_tab, tiles,
+                                                                                   tile_prefix, chunks, d_op_off);
+    cudaError_t e8 = cudaGetLastError();
+    return e8 == cudaSuccess ? ISSCABAC_OK : cuda_fail(e8, "cabac_binarize_symbols");
+  }
+  k_bin_tile_streams<<<(tiles + 1 + 255) / 256, 256, 0, st>>>(d_sym_off, n_streams, n_symbols, tiles, tile_stream, tile_first);
+  if (d_ops && geom.entries) k_bin_lut<<<(geom.entries + 127) / 128, 128, 0, st>>>(*cfg, lut);
 #define BIN_COUNT(WW, ME) k_bin_count<WW, ME><<<tiles, BIN_THREADS, 0, st>>>(*cfg, d_symbols, n_symbols, tile_sums)
-  if (bin8 && (reinterpret_cast<uintptr_t>(d_symbols) & 15u) == 0)
-    k_bin_count8<<<(tiles + BIN_THREADS / 32 - 1) / (BIN_THREADS / 32), BIN_THREADS, 0, st>>>(static_cast<const uint8_t*>(d_symbols), n_symbols, len_tab, tiles, tile_sums);
+  if (count8)
+    k_bin_count8<<<(tiles + BIN_THREADS / 32 - 1) / (BIN_THREADS / 32), BIN_THREADS, 0, st>>>(static_cast<const uint8_t*>(d_symbols), n_symbols, len_tab, tiles, tile_sums, nullptr);
   else if (sym_width == 1 && cfg->method == ISSCABAC_BIN_EG0) BIN_COUNT(1, ISSCABAC_BIN_EG0);
   else if (sym_width == 1 && cfg->method == ISSCABAC_BIN_EG2) BIN_COUNT(1, ISSCABAC_BIN_EG2);
   else if (sym_width == 1 && cfg->method == ISSCABAC_BIN_TU) BIN_COUNT(1, ISSCABAC_BIN_TU);
