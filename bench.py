@@ -681,10 +681,26 @@ def cfg_c4(env):
             ln = int(enc.lengths[s_id].item())
             assert bool((enc2.slab[s_id, :ln] == enc.slab[s_id, :ln]).all().item()), "c4: fused and two-pass encoders disagree"
         bin_bytes = 2 * n * per + int(ops.numel()) + 16 * (n + 1)
+        # ... and as ONE stream-ordered sequence when the caller knows a bound for the op array (here: the total of the
+        # sizing call above): binarizer full call into the preallocated buffer + op-array encoder, no host read in between
+        bscr = torch.empty(int(L.cabac_binarize_scratch_bytes(n * per, n)), dtype=torch.uint8, device=env.dev)
+        opsb, offb = torch.empty_like(ops), torch.empty_like(op_off2)
+
+        def two_pass():
+            I.binarize_symbols(cfg, sym, off, ops=opsb, op_off=offb, scratch=bscr)
+            I.encode_ops(opsb, offb, ctx, out=enc2)
+
+        ms_bin1 = env.timed(lambda: I.binarize_symbols(cfg, sym, off, ops=opsb, op_off=offb, scratch=bscr))
+        ms_two = env.timed(two_pass)
+        assert bool((enc2.lengths == enc.lengths).all().item()) and bool((offb == op_off2).all().item()), "c4: two-pass route, one sequence"
         out["encode_two_pass_ms"] = {"binarize_two_call_api": ms_bin, "encode_ops": ms_eops,
                                      "binarize_hbm_frac": bin_bytes / (ms_bin * 1e-3) / 1e9 / env.hbm_peak,
-                                     "binarize_algorithmic_bytes": bin_bytes}
-        del ops, op_off2, enc2
+                                     "binarize_algorithmic_bytes": bin_bytes,
+                                     "binarize_full_call_known_bound": ms_bin1,
+                                     "binarize_full_call_hbm_frac": bin_bytes / (ms_bin1 * 1e-3) / 1e9 / env.hbm_peak,
+                                     "binarize_plus_encode_ops_known_bound": ms_two,
+                                     "gbins_known_bound": tot_bins / (ms_two * 1e-3) / 1e9}
+        del ops, op_off2, enc2, opsb, offb, bscr
     if env.rank == 0 and env.world == 1 and not a.no_cpu:
         out["cpu_baseline"] = _cpu_symbols(env, cfg_args, sym, off.cpu().numpy(), _sample_ids(n, 2048), np.full(8, 1, np.uint8), enc, "c4")
     mg.close_symmetric()

@@ -211,16 +211,25 @@ def _sym_tensor(symbols, dev) -> tuple[torch.Tensor, int]:
     return torch.as_tensor(a.astype(np.uint32).view(np.int32), device=dev), 4
 
 
-def binarize_symbols(cfg: SymCfg, symbols, sym_off):
-    """Vectorised binarizer + context selector: symbols -> (ops u8, op_off int64[n_streams+1])."""
+def binarize_symbols(cfg: SymCfg, symbols, sym_off, ops=None, op_off=None, scratch=None):
+    """Vectorised binarizer + context selector: symbols -> (ops u8, op_off int64[n_streams+1]).
+    Without `ops`: the two-call API (sizing call, one host read of the total, then the ops into a buffer of that size).
+    With `ops` (a device u8 buffer whose size the caller knows to be enough, e.g. from an earlier sizing call): ONE
+    stream-ordered call, no host read; no op is written past the buffer and op_off[-1] tells the true total."""
     dev = _require_cuda()
     sym_t, width = _sym_tensor(symbols, dev)
     off_t = _dev(sym_off, torch.int64, dev)
     n = off_t.numel() - 1
     n_sym = sym_t.numel()
     L = lib()
-    scratch = torch.empty(int(L.cabac_binarize_scratch_bytes(C.c_uint64(n_sym), C.c_uint32(n))), dtype=torch.uint8, device=dev)
-    op_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    if scratch is None:
+        scratch = torch.empty(int(L.cabac_binarize_scratch_bytes(C.c_uint64(n_sym), C.c_uint32(n))), dtype=torch.uint8, device=dev)
+    if op_off is None:
+        op_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    if ops is not None:
+        check(L.cabac_binarize_symbols(C.byref(cfg), C.c_uint32(n), vp(off_t), vp(sym_t), width, C.c_uint64(n_sym),
+                                       vp(op_off), vp(ops), C.c_uint64(ops.numel()), vp(scratch), _stream_ptr()))
+        return ops, op_off
     check(L.cabac_binarize_symbols(C.byref(cfg), C.c_uint32(n), vp(off_t), vp(sym_t), width, C.c_uint64(n_sym),
                                    vp(op_off), None, C.c_uint64(0), vp(scratch), _stream_ptr()))
     total = int(op_off[-1].item())
