@@ -406,3 +406,24 @@ def test_binarizer_u8_table_kernels(I, prof, meth, Nq, rows, shape):
         bad = np.nonzero(got[op_shift:op_shift + len(want)] != want)[0]
         assert len(bad) == 0, ("ops", sym_shift, op_shift, int(bad[0]), len(bad))
         assert (got[:op_shift] == 0xAB).all() and (got[op_shift + len(want):] == 0xAB).all()
+
+
+def test_binarizer_single_call_into_callers_buffer(I):
+    """engine.binarize_symbols(..., ops=buffer): one stream-ordered call, ops and offsets equal the two-call form's; a
+    buffer that is too small is filled up to its size and op_off[-1] still tells the true total."""
+    rng = np.random.default_rng(77)
+    counts = rng.integers(0, 3000, size=90)
+    off = np.zeros(len(counts) + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    sym = np.minimum(np.floor(rng.exponential(2.0, size=int(off[-1]))), 15).astype(np.uint8)
+    cfg = I.make_cfg(O.PROFILE_FLAT, O.BIN_EG0, 16, 3, 0, 0)
+    ops2, off2 = I.binarize_symbols(cfg, sym, off)
+    total = int(off2[-1].item())
+    dev = torch.device("cuda")
+    buf = torch.full((total + 100,), 0xCD, dtype=torch.uint8, device=dev)
+    ops1, off1 = I.binarize_symbols(cfg, sym, off, ops=buf)
+    assert bool((off1 == off2).all().item()) and bool((ops1[:total] == ops2).all().item()) and bool((buf[total:] == 0xCD).all().item())
+    small = torch.full((total - 1234,), 0xCD, dtype=torch.uint8, device=dev)
+    guard = torch.full((4096,), 0xCD, dtype=torch.uint8, device=dev)
+    ops3, off3 = I.binarize_symbols(cfg, sym, off, ops=small)
+    assert int(off3[-1].item()) == total and bool((ops3 == ops2[:total - 1234]).all().item()) and bool((guard == 0xCD).all().item())
