@@ -487,8 +487,8 @@ __global__ void __launch_bounds__(B8_THREADS, B8_MIN_CTAS) k_bin_emit8(isscabac_
                                                            const uint64_t* __restrict__ tile_prefix, uint64_t* op_off, uint8_t* ops,
                                                            uint64_t cap, const uint4* __restrict__ lut, const uint8_t* __restrict__ len_tab,
                                                            uint32_t n_tiles, uint32_t tpc) {
-  __shared__ uint32_t s_warp[B8_THREADS / 32];
-  __shared__ uint32_t s_pre[B8_THREADS];
+  __shared__ uint32_t s_warp2[2][B8_THREADS / 32];     // (two copies, by tile parity: the stream pass of a tile reads them while
+  __shared__ uint32_t s_pre2[2][B8_THREADS];           //  the next tile's scan is already being written -- no barrier at the tile's end)
   __shared__ __align__(16) uint8_t s_stage[BIN_STAGE];
   extern __shared__ __align__(8) uint2 s_lut8[];      // the fast table: geom.entries + 1 slots (the last one: "not in the table")
   __shared__ __align__(8) uint64_t s_soff[BIN_SOFF];
@@ -539,6 +539,8 @@ __global__ void __launch_bounds__(B8_THREADS, B8_MIN_CTAS) k_bin_emit8(isscabac_
   uint32_t nf0 = tile_first[tile_begin], nf1 = tile_first[tile_begin + 1];
   uint32_t ns_lo = need_up ? tile_stream[tile_begin] : 0u, ns_hi = need_up ? tile_stream[tile_begin + 1] : 0u;
   for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
+    uint32_t* s_warp = s_warp2[tile & 1u];
+    uint32_t* s_pre = s_pre2[tile & 1u];
     const uint64_t t0 = (uint64_t)tile * BIN_TILE;
     const uint32_t in_tile = n - t0 < BIN_TILE ? (uint32_t)(n - t0) : (uint32_t)BIN_TILE;       // symbols of this tile (>= 1)
     const uint32_t r0 = threadIdx.x * B8_ITEMS;                                                // this thread's first, tile-relative
@@ -718,7 +720,9 @@ __global__ void __launch_bounds__(B8_THREADS, B8_MIN_CTAS) k_bin_emit8(isscabac_
       if (tile + 1 == n_tiles)      // the streams at the very end are empty; op_off[n_streams] = the total
         for (uint32_t e = f1 + threadIdx.x; e <= n_streams; e += B8_THREADS) op_off[e] = tile_base + block_total;
     }
-    __syncthreads();       // s_pre, s_warp, s_soff and the stage are free for the next tile
+    // no barrier here: the next tile writes the other copy of s_pre / s_warp, s_soff was last read in front of this tile's
+    // word barrier, and the stage is not written before the next tile's scan barrier, which every thread reaches only after
+    // its pieces and its streams of this tile
   }
 }
 
