@@ -427,3 +427,30 @@ def test_binarizer_single_call_into_callers_buffer(I):
     guard = torch.full((4096,), 0xCD, dtype=torch.uint8, device=dev)
     ops3, off3 = I.binarize_symbols(cfg, sym, off, ops=small)
     assert int(off3[-1].item()) == total and bool((ops3 == ops2[:total - 1234]).all().item()) and bool((guard == 0xCD).all().item())
+
+
+@pytest.mark.parametrize("meth", [O.BIN_TU, O.BIN_EG0])
+def test_c1_demo_sequence_full_size(I, meth):
+    """BASELINE configs[0] at its full size: the cabacDemo sequence (cabacDemo.m:26-37: 10,000 correlated half-normal samples,
+    Nq = 4), demo context rule (3 contexts, p0 = 0.5), TU as the reference runs it and EG0 as BASELINE.json words it -- one
+    stream through the fused kernels and through binarizer + op encoder, bytes equal to the oracle's, symbols decode back."""
+    rng = np.random.default_rng(0)
+    N, Nq = 10000, 4
+    x = np.abs(rng.standard_normal(N))
+    x[1:] += 0.8 * x[:-1]
+    delta = np.quantile(x, 0.99) / Nq
+    sym = np.minimum(np.floor(x / delta + 0.5), Nq - 1).astype(np.uint8)
+    off = np.array([0, N], dtype=np.int64)
+    ctx = O.ctx_from_p0(O.matlab_uint8(0.5 * np.ones(3) * 255) / 255.0)
+    cfg, ocfg = I.make_cfg(O.PROFILE_DEMO, meth, Nq), O.make_cfg(O.PROFILE_DEMO, meth, Nq)
+    s_ref, l_ref = O.encode_symbols(ocfg, sym.astype(np.uint32), off.astype(np.uint64), ctx, 8192)
+    want = bytes(s_ref[0, :l_ref[0]])
+    enc = I.encode_symbols(cfg, sym, off, ctx, slab_stride=8192)
+    enc.check_overflow()
+    assert int(enc.lengths[0].item()) == len(want) and bytes(enc.slab[0, :len(want)].cpu().numpy()) == want
+    ops, op_off = I.binarize_symbols(cfg, sym, off)
+    assert (ops.cpu().numpy() == O.symbols_to_ops(ocfg, sym.astype(np.uint32))).all()
+    enc2 = I.encode_ops(ops, op_off, ctx, slab_stride=8192)
+    assert int(enc2.lengths[0].item()) == len(want) and bytes(enc2.slab[0, :len(want)].cpu().numpy()) == want
+    dec, ok = I.decode_symbols(cfg, I.compact(enc), off, ctx, sym_dtype=torch.uint8)
+    assert bool(ok.all().item()) and (dec.cpu().numpy() == sym).all()
