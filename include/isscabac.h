@@ -124,6 +124,10 @@ int cabac_encode_ops(uint32_t n_streams, const uint64_t* d_op_off, const void* d
                      uint8_t* d_slab, uint64_t slab_stride, uint32_t* d_lengths,
                      uint32_t* d_overflow, void* stream);
 uint64_t cabac_slab_stride_bound(uint64_t max_ops_per_stream);
+/* The kernel formulation cabac_encode_ops picks for a call of this shape with u8 ops (one warp per 32 streams; the same with one
+ * hand-over per SM when an SM holds 4k + 2 tiles; two warps per 32 streams when there are few tiles per SM; ...): the name a
+ * profiler shows for it.  Informational (bench.py labels its per-kernel numbers with it); "" without a device. */
+const char* cabac_encode_ops_kernel(uint32_t n_streams, uint32_t n_ctx);
 
 /* Stream s is d_bytes[byte_off[s] .. byte_off[s+1]); the op array gives the kind of
  * every bin (bit 0 ignored); d_bins[i] = decoded bin of op i.  d_finish_ok[s]

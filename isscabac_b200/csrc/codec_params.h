@@ -25,6 +25,7 @@ struct CodecParams {
   uint8_t* finish_ok;
   // launch-dependent choices made by the host (run_codec)
   uint32_t prefetch_ops;   // wide decoder: ask the op stream into L1 four blocks ahead (pays with few tiles per SM only)
+  uint32_t ho_eighths;     // hand-over encoder: the giving warps code this many eighths of the lockstep blocks (k_encode_ops_wide_ho)
 };
 
 // Latency kernels (cabac_spec.cuh) for the u8 op format.  done = false: the geometry does not fit (too many contexts for

@@ -383,6 +383,166 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_ops_wide(CodecPa
 }
 
 // ---------------------------------------------------------------------------
+// k_encode_ops_wide with ONE hand-over per SM (round 2, last part; ISSCABAC_HANDOVER=0 switches it off).
+// 2,048 tiles on 592 schedulers is 3.46 warps per scheduler: with 14 warps per CTA two schedulers of every SM hold 4
+// warps and two hold 3 (warp w issues on scheduler w % 4), the launch lasts as long as a 4-warp scheduler needs, and the
+// 3-warp ones idle at its end.  Here the CTA has two more warps, NW and NW + 1, on the light schedulers 2 and 3.  They
+// sleep on a named barrier.  Warps NW - 2 and NW - 1 (the fourth warps of schedulers 0 and 1) code the first HALF of
+// their tile's lockstep blocks, park the lane state (window, range, pending word, op pointer) in shared memory, arrive
+// at the barrier and exit; the sleeping warp adopts state and context block (the tokens are lane-relative, so they stay
+// valid) and codes the rest.  In the throughput-bound picture every scheduler then carries 3.5 tiles instead of 4 / 3.
+// Only for full tiles of streams with >= 64 common blocks; otherwise the giver says "no hand-over" and codes on.
+// ---------------------------------------------------------------------------
+#if !WIDE_CTX_ROWS
+constexpr uint32_t HO_WORDS = 12;                                    // per lane: W (2), range, n, pend, wp, slot (2), p (2), blocks left, tail
+constexpr uint32_t HO_SLOT_BYTES = HO_WORDS * 32 * 4 + 16;           // + the flag word: 0 = no hand-over, else lockstep blocks left + 1
+constexpr uint32_t HO_BYTES = 2 * HO_SLOT_BYTES;
+
+__global__ void __launch_bounds__(WIDE_MAX_WARPS * 32) k_encode_ops_wide_ho(CodecParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t nwarps = blockDim.x >> 5, home = nwarps - 2u;
+  const uint32_t warp = threadIdx.x >> 5, lane = cb_keep32(threadIdx.x & 31);
+  const bool receiver = warp >= home;                     // warp home adopts warp home - 2, warp home + 1 adopts warp home - 1
+  const uint32_t ewarp = receiver ? warp - 2u : warp;     // the warp whose tile and context block this warp works on
+  const bool giver = !receiver && warp + 2u >= home;
+  const uint32_t xid = ewarp - (home - 2u);               // exchange slot (givers and receivers only)
+  // set-up (wide_setup with `home` warps of tiles per CTA; the receivers initialise nothing)
+  WRow* t = reinterpret_cast<WRow*>(smem);
+  const uint32_t tab0 = (uint32_t)__cvta_generic_to_shared(smem);
+  for (uint32_t i = threadIdx.x; i < kNumRows * WIDE_COLS; i += blockDim.x) {
+    WRow r = c_wide_rows.r[i / WIDE_COLS];
+    const uint32_t col = tab0 + (i % WIDE_COLS) * (uint32_t)sizeof(WRow);
+    r.next_mps = col + r.next_mps * WIDE_ROW_STRIDE;
+    r.next_lps = col + r.next_lps * WIDE_ROW_STRIDE;
+    t[i] = r;
+  }
+  const uint32_t n_ctx = cb_keep32(P.n_ctx);
+  const uint32_t s = (blockIdx.x * home + ewarp) * 32 + lane;
+  const bool valid = s < P.n_streams;
+  WTab tab;
+  WCtx ctx;
+  tab.base = cb_keep32(tab0 + (lane % WIDE_COLS) * (uint32_t)sizeof(WRow));
+  ctx.p = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + cb_keep32(ewarp * (n_ctx + 1) * 32 + lane);
+  if (!receiver) {
+    const uint8_t* init = P.ctx_init + (P.per_stream_init && valid ? (uint64_t)s * n_ctx : 0);
+    for (uint32_t c = 0; c < n_ctx; ++c) ctx.store(c, tab.token(init[c] & 127u));
+    ctx.store(n_ctx, tab.token(kEpState));
+  }
+  uint32_t* xch = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES + (size_t)home * (n_ctx + 1) * WIDE_CTX_STRIDE + (size_t)(giver || receiver ? xid : 0u) * HO_SLOT_BYTES);
+  uint32_t* flag = xch + HO_WORDS * 32;
+  __syncthreads();
+  const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+  const uint32_t bar_id = 1u + xid;
+
+  EncWide E;
+  const uint32_t cap = (uint32_t)(P.slab_stride > 0xfffffffcull ? 0xfffffffcull : P.slab_stride);
+  const uint8_t* p = nullptr;
+  uint64_t nblk = 0;
+  uint32_t tail = 0, common = 0, hand_at = 0xffffffffu;
+  if (receiver) {
+    // every lane waits (the barrier counts threads); then the giver's verdict
+    asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
+    const uint32_t f = *reinterpret_cast<volatile uint32_t*>(flag);
+    if (f == 0u) return;
+    volatile uint32_t* x = xch + lane;
+    E.W = (uint64_t)x[0 * 32] | ((uint64_t)x[1 * 32] << 32);
+    E.range = x[2 * 32];
+    E.n = (int32_t)x[3 * 32];
+    E.pend = x[4 * 32];
+    E.wp = x[5 * 32];
+    E.cap_words = cap >> 2;
+    E.slot = cb_keep(reinterpret_cast<uint32_t*>((uintptr_t)x[6 * 32] | ((uintptr_t)x[7 * 32] << 32)));
+    p = reinterpret_cast<const uint8_t*>((uintptr_t)x[8 * 32] | ((uintptr_t)x[9 * 32] << 32));
+    nblk = x[10 * 32];
+    tail = x[11 * 32];
+    common = f - 1u;
+  } else {
+    if (giver && vmask != 0xffffffffu) {     // not a full tile: no hand-over (all 32 lanes arrive, then the idle ones leave)
+      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(flag) = 0u;
+      __syncwarp();
+      __threadfence_block();
+      asm volatile("bar.arrive %0, 64;" :: "r"(bar_id) : "memory");
+    }
+    if (!valid) return;
+    const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
+    p = reinterpret_cast<const uint8_t*>(P.ops) + o0;
+    const uint64_t n = o1 - o0;
+    encw_start(E, P.slab + (uint64_t)s * P.slab_stride, cap);
+    uint64_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u;
+    if (head > n) head = n;
+    for (uint64_t i = 0; i < head; ++i) encw_general(E, p[i], ctx, tab, n_ctx);
+    p += head;
+    nblk = (n - head) >> 4;
+    tail = (uint32_t)((n - head) & 15u);
+    common = __reduce_min_sync(vmask, (uint32_t)(nblk > 0xffffffffull ? 0xffffffffull : nblk));
+    if (giver && vmask == 0xffffffffu) {
+      const uint32_t worth = __reduce_max_sync(0xffffffffu, (uint32_t)(nblk > 0xfffffff0ull ? 1u : 0u));   // block counts that do not fit a word: no hand-over
+      if (common >= 64u && !worth) {
+        hand_at = (uint32_t)(((uint64_t)common * P.ho_eighths) >> 3);
+      } else {
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(flag) = 0u;
+        __syncwarp();
+        __threadfence_block();
+        asm volatile("bar.arrive %0, 64;" :: "r"(bar_id) : "memory");
+      }
+    }
+  }
+  const bool lockstep = receiver || vmask == 0xffffffffu;
+  if (nblk) {
+    uint4 cur = __ldg(reinterpret_cast<const uint4*>(p));
+    uint64_t b = 0;
+    auto block = [&](auto lock) {
+      constexpr bool LOCK = decltype(lock)::value;
+      uint4 nxt = cur;
+      if (b + 1 < nblk) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
+      const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+      const uint32_t cw[4] = {op_codes4(cur.x), op_codes4(cur.y), op_codes4(cur.z), op_codes4(cur.w)};
+      if (cb_any<LOCK>(block_has_trm(cw))) {
+        for (int k = 0; k < 16; ++k) encw_general(E, p[k], ctx, tab, n_ctx);
+      } else {
+        encw_block16<LOCK>(E, w, cw, ctx, tab, n_ctx);
+      }
+      cur = nxt;
+      p += 16;
+    };
+    if (lockstep) {
+      const uint32_t stop = hand_at < common ? hand_at : common;
+      for (; b < stop; ++b) block(std::true_type{});
+      if (hand_at != 0xffffffffu) {
+        // the first half is coded: park the lane state, tell the sleeping warp, leave
+        volatile uint32_t* x = xch + lane;
+        x[0 * 32] = (uint32_t)E.W;
+        x[1 * 32] = (uint32_t)(E.W >> 32);
+        x[2 * 32] = E.range;
+        x[3 * 32] = (uint32_t)E.n;
+        x[4 * 32] = E.pend;
+        x[5 * 32] = E.wp;
+        x[6 * 32] = (uint32_t)reinterpret_cast<uintptr_t>(E.slot);
+        x[7 * 32] = (uint32_t)(reinterpret_cast<uintptr_t>(E.slot) >> 32);
+        x[8 * 32] = (uint32_t)reinterpret_cast<uintptr_t>(p);
+        x[9 * 32] = (uint32_t)(reinterpret_cast<uintptr_t>(p) >> 32);
+        x[10 * 32] = (uint32_t)(nblk - b);
+        x[11 * 32] = tail;
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(flag) = common - hand_at + 1u;
+        __syncwarp();
+        __threadfence_block();
+        asm volatile("bar.arrive %0, 64;" :: "r"(bar_id) : "memory");
+        return;
+      }
+    }
+    for (; b < nblk; ++b) block(std::false_type{});
+  } else if (hand_at != 0xffffffffu) {
+    // (cannot happen: hand_at is set only with common >= 64 blocks)
+  }
+  for (uint32_t i = 0; i < tail; ++i) encw_general(E, p[i], ctx, tab, n_ctx);
+
+  const uint32_t len = encw_finish(E);
+  P.lengths[s] = len;
+  if (len > cap && P.overflow) atomicOr(P.overflow, 1u);
+}
+#endif
+
+// ---------------------------------------------------------------------------
 // The encoder as two warps per tile of 32 streams (used when there are few tiles per SM, see run_codec).
 // The context side of a bin (token -> row -> next token) does not depend on the arithmetic side
 // (range / low), so a PRODUCER warp walks the ops and the context states and hands, per bin, the row's
@@ -956,6 +1116,22 @@ constexpr uint32_t kLatTilesPerSm = LAT_TILES_PER_SM;
 #endif
 constexpr uint32_t kPrefetchOpsTilesPerSm = PF_OPS_TILES_PER_SM;   // the wide decoder's op-stream prefetch (k_decode_ops_wide)
 
+// the hand-over encoder (k_encode_ops_wide_ho) runs when the wide geometry is one CTA per SM with 4k + 2 warps
+inline bool handover_geometry(uint32_t nw, uint32_t grid, size_t wsmem, size_t lim) {
+#if WIDE_CTX_ROWS
+  return false;
+#else
+  const char* ho_env = getenv("ISSCABAC_HANDOVER");
+  return !(ho_env && ho_env[0] == '0') && nw % 4u == 2u && nw + 2u <= (uint32_t)WIDE_MAX_WARPS && grid <= (uint32_t)sm_count() &&
+         wsmem + HO_BYTES <= lim;
+#endif
+}
+inline bool encoder_split_on(uint32_t n_streams) {
+  const char* split_env = getenv("ISSCABAC_ENC_SPLIT");
+  const uint32_t split_tiles = (n_streams + 31) / 32;
+  return split_env && (split_env[0] == '0' || split_env[0] == '1') ? split_env[0] == '1' : split_tiles <= 11u * (uint32_t)sm_count();
+}
+
 template <bool ENC>
 int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   if (op_width != 1 && op_width != 2) { set_error("op_width must be 1 or 2"); return ISSCABAC_ERR_INVALID; }
@@ -971,10 +1147,8 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   // Encoder with few tiles per SM: the two-warp formulation (k_encode_ops_split).  Measured on B200 over 65,536-bin
   // streams: 4.20 against 5.36 ms up to 16 K streams, 5.11 / 5.84 at 32 K, 6.28 / 6.49 at 48 K, equal from 56 K on, where
   // both are bound by the ALU pipe and the ring traffic only adds to it.  ISSCABAC_ENC_SPLIT=0 / 1 forces the choice.
-  const char* split_env = getenv("ISSCABAC_ENC_SPLIT");
   const uint32_t split_tiles = (P.n_streams + 31) / 32;
-  const bool split_on = split_env && (split_env[0] == '0' || split_env[0] == '1') ? split_env[0] == '1'
-                                                                                  : split_tiles <= 11u * (uint32_t)sm_count();
+  const bool split_on = encoder_split_on(P.n_streams);
   // Few tiles per SM: the latency decoder (kernels_lat.cu, cabac_spec.cuh) -- context rows in the slots, successor rows
   // loaded ahead, LPS arm by table: fewer exposed latencies per bin, more instructions.  Measured on B200 over 65,536-bin
   // streams (profiles/r2_v1_ops_latency.jsonl): decode 4.42 / 5.42 / 5.32 ms against 4.97 / 5.92 / 5.67 ms of the wide
@@ -1014,6 +1188,19 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
     }
   }
   if (op_width == 1 && wide_geometry(P.n_streams, P.n_ctx, nw, grid, wsmem)) {
+#if !WIDE_CTX_ROWS
+    // one CTA per SM with 4k + 2 warps: the hand-over variant (see k_encode_ops_wide_ho)
+    const char* ho_frac = getenv("ISSCABAC_HANDOVER_EIGHTHS");       // measured at C3: 4/8 7.05, 5/8 7.03, 6/8 7.02 ms (plain kernel 7.19)
+    P.ho_eighths = ho_frac && ho_frac[0] >= '1' && ho_frac[0] <= '7' ? (uint32_t)(ho_frac[0] - '0') : 6u;
+    if (ENC && handover_geometry(nw, grid, wsmem, lim)) {
+      const size_t hsmem = wsmem + HO_BYTES;
+      cudaError_t e = cudaFuncSetAttribute(k_encode_ops_wide_ho, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+      k_encode_ops_wide_ho<<<grid, (nw + 2u) * 32u, hsmem, st>>>(P);
+      e = cudaGetLastError();
+      return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_encode_ops_wide_ho");
+    }
+#endif
     auto kernel = ENC ? k_encode_ops_wide : k_decode_ops_wide;
     P.prefetch_ops = (!ENC && split_tiles <= kPrefetchOpsTilesPerSm * (uint32_t)sm_count()) ? 1u : 0u;
 #if CABAC_DEC_TMA
@@ -1076,6 +1263,19 @@ int cabac_encode_ops(uint32_t n_streams, const uint64_t* d_op_off, const void* d
   P.op_off = d_op_off; P.ops = d_ops; P.ctx_init = d_ctx_init;
   P.slab = d_slab; P.slab_stride = slab_stride; P.lengths = d_lengths; P.overflow = d_overflow;
   return run_codec<true>(P, op_width, static_cast<cudaStream_t>(stream));
+}
+
+// Which kernel formulation cabac_encode_ops picks for a call of this shape (u8 ops): the name the profiler will show.
+const char* cabac_encode_ops_kernel(uint32_t n_streams, uint32_t n_ctx) {
+  const size_t lim = smem_limit();
+  if (!lim || n_streams == 0) return "";
+  const char* lat_env = getenv("ISSCABAC_LAT");
+  if (lat_env && lat_env[0] == '1' && n_ctx <= 125) return "k_encode_ops_lat";
+  if (encoder_split_on(n_streams) && n_ctx <= 125) return "k_encode_ops_split";
+  uint32_t nw, grid;
+  size_t wsmem;
+  if (wide_geometry(n_streams, n_ctx, nw, grid, wsmem)) return handover_geometry(nw, grid, wsmem, lim) ? "k_encode_ops_wide_ho" : "k_encode_ops_wide";
+  return "k_encode_ops";
 }
 
 // <= 6 shift bits per context bin, 1 per bypass bin, 7 per terminate bin, <= 13 tail bits
