@@ -287,3 +287,43 @@ def test_worst_case_window_growth_on_device(I, enc_kernel):
         live = np.arange(8192)[None, :] < l_ref[:, None]
         assert (slab[live] == s_ref[live]).all(), state
         assert ok.all() and (bins_g == (ops & 1)).all(), state
+
+
+@pytest.mark.parametrize("warps,ragged,partial", [(6, False, False), (6, True, False), (10, False, True)])
+def test_encoder_handover_between_schedulers(I, monkeypatch, warps, ragged, partial):
+    """k_encode_ops_wide_ho: with 4k + 2 tiles per SM the fourth warps of two schedulers hand their tile over, half-coded, to
+    warps that slept on the other two (lane state through shared memory).  A job of exactly that geometry -- one CTA per SM,
+    `warps` tiles each; ragged lengths; a last CTA whose giving warps have no or partial tiles -- against the oracle for a
+    stream sample taken from every warp role, and against the plain kernel for ALL streams."""
+    monkeypatch.setenv("ISSCABAC_LAT", "0")
+    monkeypatch.setenv("ISSCABAC_ENC_SPLIT", "0")
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n_streams = sms * warps * 32 - (warps * 32 + 40 if partial else 0)      # partial: the last CTA loses a warp's tiles and a bit
+    n_ops = 1500
+    assert I.lib().cabac_encode_ops_kernel(n_streams, 23) == b"k_encode_ops_wide_ho"
+    ops, off = rand_ops(11 + warps, n_streams, n_ops, 23, 0.25, ragged)
+    if ragged:      # keep every stream long enough for the hand-over to take place (>= 64 common blocks)
+        lens = np.maximum(np.diff(off.astype(np.int64)), 1100)
+        off = np.zeros(n_streams + 1, dtype=np.uint64)
+        np.cumsum(lens, out=off[1:])
+        ops = rand_ops(12 + warps, 1, int(off[-1]), 23, 0.25, False)[0]
+    ci = np.random.default_rng(5).integers(0, 126, size=23).astype(np.uint8)
+    stride = ((n_ops // 4 + 80) + 15) & ~15
+    d_ops, d_off = torch.as_tensor(ops, device="cuda"), torch.as_tensor(off.astype(np.int64), device="cuda")
+    enc = I.encode_ops(d_ops, d_off, ci, slab_stride=stride)
+    monkeypatch.setenv("ISSCABAC_HANDOVER", "0")
+    assert I.lib().cabac_encode_ops_kernel(n_streams, 23) == b"k_encode_ops_wide"
+    plain = I.encode_ops(d_ops, d_off, ci, slab_stride=stride)
+    torch.cuda.synchronize()
+    enc.check_overflow()
+    lens_g, lens_p = enc.lengths.cpu().numpy(), plain.lengths.cpu().numpy()
+    assert (lens_g == lens_p).all()
+    assert same_rows(enc.slab.cpu().numpy(), plain.slab.cpu().numpy(), lens_p)
+    # the oracle on streams of every warp of the first, a middle and the last CTA (givers are the last two warps of a CTA)
+    ids = np.unique(np.concatenate([np.arange(c * warps * 32, min((c + 1) * warps * 32, n_streams))[::7] for c in (0, sms // 2, sms - 1)]))
+    sub_off = np.zeros(len(ids) + 1, dtype=np.uint64)
+    np.cumsum([int(off[i + 1] - off[i]) for i in ids], out=sub_off[1:])
+    sub_ops = np.concatenate([ops[int(off[i]):int(off[i + 1])] for i in ids])
+    s_ref, l_ref = O.encode_ops(sub_ops, sub_off, ci, out_stride=stride, n_threads=8)
+    assert (lens_g[ids].astype(np.uint32) == l_ref).all()
+    assert same_rows(enc.slab[torch.as_tensor(ids, device="cuda")].cpu().numpy(), s_ref, l_ref)
