@@ -128,6 +128,7 @@ uint64_t cabac_slab_stride_bound(uint64_t max_ops_per_stream);
  * hand-over per SM when an SM holds 4k + 2 tiles; two warps per 32 streams when there are few tiles per SM; ...): the name a
  * profiler shows for it.  Informational (bench.py labels its per-kernel numbers with it); "" without a device. */
 const char* cabac_encode_ops_kernel(uint32_t n_streams, uint32_t n_ctx);
+const char* cabac_decode_ops_kernel(uint32_t n_streams, uint32_t n_ctx);
 
 /* Stream s is d_bytes[byte_off[s] .. byte_off[s+1]); the op array gives the kind of
  * every bin (bit 0 ignored); d_bins[i] = decoded bin of op i.  d_finish_ok[s]

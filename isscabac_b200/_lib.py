@@ -56,6 +56,9 @@ def lib() -> C.CDLL:
         if hasattr(L, "cabac_encode_ops_kernel"):
             L.cabac_encode_ops_kernel.restype = C.c_char_p
             L.cabac_encode_ops_kernel.argtypes = [C.c_uint32, C.c_uint32]
+        if hasattr(L, "cabac_decode_ops_kernel"):
+            L.cabac_decode_ops_kernel.restype = C.c_char_p
+            L.cabac_decode_ops_kernel.argtypes = [C.c_uint32, C.c_uint32]
         if hasattr(L, "cabac_binarize_scratch_bytes"):
             L.cabac_binarize_scratch_bytes.restype = C.c_size_t
             L.cabac_binarize_scratch_bytes.argtypes = [C.c_uint64, C.c_uint32]

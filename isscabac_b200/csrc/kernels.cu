@@ -836,6 +836,163 @@ __global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, WIDE_DEC_MINBLOCKS) k_dec
 }
 
 // ---------------------------------------------------------------------------
+// k_decode_ops_wide with the encoder's hand-over (k_encode_ops_wide_ho: one tile per 4-warp scheduler moves, part-decoded,
+// to a warp asleep on a 3-warp scheduler).  The lane state is the window (DecWide: 15 words with the two payload words in
+// flight) + the op / bin pointers and counts: 20 words.
+// ---------------------------------------------------------------------------
+#if !WIDE_CTX_ROWS && !CABAC_DEC_TMA
+constexpr uint32_t HOD_WORDS = 20;
+constexpr uint32_t HOD_SLOT_BYTES = HOD_WORDS * 32 * 4 + 16;
+constexpr uint32_t HOD_BYTES = 2 * HOD_SLOT_BYTES;
+
+__global__ void __launch_bounds__(WIDE_MAX_WARPS * 32, WIDE_DEC_MINBLOCKS) k_decode_ops_wide_ho(CodecParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t nwarps = blockDim.x >> 5, home = nwarps - 2u;
+  const uint32_t warp = threadIdx.x >> 5, lane = cb_keep32(threadIdx.x & 31);
+  const bool receiver = warp >= home;
+  const uint32_t ewarp = receiver ? warp - 2u : warp;
+  const bool giver = !receiver && warp + 2u >= home;
+  const uint32_t xid = ewarp - (home - 2u);
+  WRow* t = reinterpret_cast<WRow*>(smem);
+  const uint32_t tab0 = (uint32_t)__cvta_generic_to_shared(smem);
+  for (uint32_t i = threadIdx.x; i < kNumRows * WIDE_COLS; i += blockDim.x) {
+    WRow r = c_wide_rows.r[i / WIDE_COLS];
+    const uint32_t col = tab0 + (i % WIDE_COLS) * (uint32_t)sizeof(WRow);
+    r.next_mps = col + r.next_mps * WIDE_ROW_STRIDE;
+    r.next_lps = col + r.next_lps * WIDE_ROW_STRIDE;
+    t[i] = r;
+  }
+  const uint32_t n_ctx = cb_keep32(P.n_ctx);
+  const uint32_t s = (blockIdx.x * home + ewarp) * 32 + lane;
+  const bool valid = s < P.n_streams;
+  WTab tab;
+  WCtx ctx;
+  tab.base = cb_keep32(tab0 + (lane % WIDE_COLS) * (uint32_t)sizeof(WRow));
+  ctx.p = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES) + cb_keep32(ewarp * (n_ctx + 1) * 32 + lane);
+  if (!receiver) {
+    const uint8_t* init = P.ctx_init + (P.per_stream_init && valid ? (uint64_t)s * n_ctx : 0);
+    for (uint32_t c = 0; c < n_ctx; ++c) ctx.store(c, tab.token(init[c] & 127u));
+    ctx.store(n_ctx, tab.token(kEpState));
+  }
+  uint32_t* xch = reinterpret_cast<uint32_t*>(smem + WIDE_TAB_BYTES + (size_t)home * (n_ctx + 1) * WIDE_CTX_STRIDE + (size_t)(giver || receiver ? xid : 0u) * HOD_SLOT_BYTES);
+  uint32_t* flag = xch + HOD_WORDS * 32;
+  __syncthreads();
+  const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+  const uint32_t bar_id = 1u + xid;
+
+  DecWide D;
+  const uint8_t* p = nullptr;
+  uint8_t* q = nullptr;
+  uint64_t nblk = 0;
+  uint32_t tail = 0, common = 0, hand_at = 0xffffffffu;
+  if (receiver) {
+    asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
+    const uint32_t f = *reinterpret_cast<volatile uint32_t*>(flag);
+    if (f == 0u) return;
+    volatile uint32_t* x = xch + lane;
+    D.lo = x[0 * 32]; D.hi = x[1 * 32]; D.range = x[2 * 32]; D.f = (int32_t)x[3 * 32]; D.p = x[4 * 32]; D.len = x[5 * 32];
+    D.cur = x[6 * 32]; D.nxt = x[7 * 32]; D.sel = x[8 * 32]; D.widx = x[9 * 32]; D.wcnt = x[10 * 32];
+    D.wbase = cb_keep(reinterpret_cast<const uint32_t*>((uintptr_t)x[11 * 32] | ((uintptr_t)x[12 * 32] << 32)));
+    D.in = reinterpret_cast<const uint8_t*>((uintptr_t)x[13 * 32] | ((uintptr_t)x[14 * 32] << 32));
+    p = reinterpret_cast<const uint8_t*>((uintptr_t)x[15 * 32] | ((uintptr_t)x[16 * 32] << 32));
+    q = reinterpret_cast<uint8_t*>((uintptr_t)x[17 * 32] | ((uintptr_t)x[18 * 32] << 32));
+    nblk = x[19 * 32] >> 4;
+    tail = x[19 * 32] & 15u;
+    common = f - 1u;
+  } else {
+    if (giver && vmask != 0xffffffffu) {
+      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(flag) = 0u;
+      __syncwarp();
+      __threadfence_block();
+      asm volatile("bar.arrive %0, 64;" :: "r"(bar_id) : "memory");
+    }
+    if (!valid) return;
+    const uint64_t o0 = P.op_off[s], o1 = P.op_off[s + 1];
+    p = reinterpret_cast<const uint8_t*>(P.ops) + o0;
+    q = P.bins + o0;
+    const uint64_t n = o1 - o0;
+    const uint64_t b0 = P.byte_off[s], b1 = P.byte_off[s + 1];
+    decw_start(D, P.bytes + b0, (uint32_t)(b1 - b0));
+    uint64_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u;
+    if (head > n) head = n;
+    for (uint64_t i = 0; i < head; ++i) q[i] = (uint8_t)decw_general(D, p[i], ctx, tab, n_ctx);
+    p += head;
+    q += head;
+    nblk = (n - head) >> 4;
+    tail = (uint32_t)((n - head) & 15u);
+    common = __reduce_min_sync(vmask, (uint32_t)(nblk > 0xffffffffull ? 0xffffffffull : nblk));
+    if (giver && vmask == 0xffffffffu) {
+      const uint32_t huge = __reduce_max_sync(0xffffffffu, (uint32_t)(nblk > 0x0ffffff0ull ? 1u : 0u));   // (blocks left, tail) share a word
+      if (common >= 64u && !huge) {
+        hand_at = (uint32_t)(((uint64_t)common * P.ho_eighths) >> 3);
+      } else {
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(flag) = 0u;
+        __syncwarp();
+        __threadfence_block();
+        asm volatile("bar.arrive %0, 64;" :: "r"(bar_id) : "memory");
+      }
+    }
+  }
+  const bool out_vec = (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
+  const bool lockstep = receiver || vmask == 0xffffffffu;
+  if (nblk) {
+    uint4 cur = __ldg(reinterpret_cast<const uint4*>(p));
+    uint64_t b = 0;
+    auto block = [&](auto lock) {
+      constexpr bool LOCK = decltype(lock)::value;
+      uint4 nxt = cur;
+      if (b + 1 < nblk) nxt = __ldg(reinterpret_cast<const uint4*>(p + 16));
+      const uint32_t cw[4] = {op_codes4(cur.x), op_codes4(cur.y), op_codes4(cur.z), op_codes4(cur.w)};
+      if (cb_any<LOCK>(block_has_trm(cw))) {
+        if (LOCK && CABAC_REFILL_P == 3 && CABAC_REFILL_FIRST) decw_refill(D);
+        for (int k = 0; k < 16; ++k) q[k] = (uint8_t)decw_general(D, p[k], ctx, tab, n_ctx);
+      } else {
+        uint32_t r[4];
+        decw_block16<LOCK>(D, cw, r, ctx, tab, n_ctx);
+        if (out_vec) {
+          *reinterpret_cast<uint4*>(q) = make_uint4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) q[k] = (uint8_t)(r[k >> 2] >> (8 * (k & 3)));
+        }
+      }
+      cur = nxt;
+      p += 16;
+      q += 16;
+    };
+    if (lockstep) {
+      const uint32_t stop = hand_at < common ? hand_at : common;
+      for (; b < stop; ++b) block(std::true_type{});
+      if (hand_at != 0xffffffffu) {
+        volatile uint32_t* x = xch + lane;
+        x[0 * 32] = D.lo; x[1 * 32] = D.hi; x[2 * 32] = D.range; x[3 * 32] = (uint32_t)D.f; x[4 * 32] = D.p; x[5 * 32] = D.len;
+        x[6 * 32] = D.cur; x[7 * 32] = D.nxt; x[8 * 32] = D.sel; x[9 * 32] = D.widx; x[10 * 32] = D.wcnt;
+        x[11 * 32] = (uint32_t)reinterpret_cast<uintptr_t>(D.wbase);
+        x[12 * 32] = (uint32_t)(reinterpret_cast<uintptr_t>(D.wbase) >> 32);
+        x[13 * 32] = (uint32_t)reinterpret_cast<uintptr_t>(D.in);
+        x[14 * 32] = (uint32_t)(reinterpret_cast<uintptr_t>(D.in) >> 32);
+        x[15 * 32] = (uint32_t)reinterpret_cast<uintptr_t>(p);
+        x[16 * 32] = (uint32_t)(reinterpret_cast<uintptr_t>(p) >> 32);
+        x[17 * 32] = (uint32_t)reinterpret_cast<uintptr_t>(q);
+        x[18 * 32] = (uint32_t)(reinterpret_cast<uintptr_t>(q) >> 32);
+        x[19 * 32] = ((uint32_t)(nblk - b) << 4) | tail;
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(flag) = common - hand_at + 1u;
+        __syncwarp();
+        __threadfence_block();
+        asm volatile("bar.arrive %0, 64;" :: "r"(bar_id) : "memory");
+        return;
+      }
+      if (CABAC_REFILL_P == 3 && CABAC_REFILL_FIRST) decw_refill(D);
+    }
+    for (; b < nblk; ++b) block(std::false_type{});
+  }
+  for (uint32_t i = 0; i < tail; ++i) q[i] = (uint8_t)decw_general(D, p[i], ctx, tab, n_ctx);
+
+  if (P.finish_ok) P.finish_ok[s] = (uint8_t)decw_finish(D);
+}
+#endif
+
+// ---------------------------------------------------------------------------
 // device-wide exclusive scan (u32 -> u64), single pass, decoupled look-back
 // ---------------------------------------------------------------------------
 // Tiles of SCAN_TILE elements; tile order is taken from an atomic ticket so a tile only
@@ -1132,6 +1289,17 @@ inline bool encoder_split_on(uint32_t n_streams) {
   return split_env && (split_env[0] == '0' || split_env[0] == '1') ? split_env[0] == '1' : split_tiles <= 11u * (uint32_t)sm_count();
 }
 
+// the hand-over decoder: the same geometry, and only where the plain kernel runs without its op-stream prefetch (more than
+// kPrefetchOpsTilesPerSm tiles per SM: the hand-over kernel has none)
+inline bool decode_handover_geometry(uint32_t n_streams, uint32_t nw, uint32_t grid, size_t wsmem, size_t lim) {
+#if WIDE_CTX_ROWS || CABAC_DEC_TMA
+  return false;
+#else
+  return (n_streams + 31) / 32 > kPrefetchOpsTilesPerSm * (uint32_t)sm_count() && !getenv("ISSCABAC_HANDOVER_ENC_ONLY") &&
+         handover_geometry(nw, grid, wsmem + HOD_BYTES - HO_BYTES, lim);
+#endif
+}
+
 template <bool ENC>
 int run_codec(CodecParams P, int op_width, cudaStream_t st) {
   if (op_width != 1 && op_width != 2) { set_error("op_width must be 1 or 2"); return ISSCABAC_ERR_INVALID; }
@@ -1192,6 +1360,17 @@ int run_codec(CodecParams P, int op_width, cudaStream_t st) {
     // one CTA per SM with 4k + 2 warps: the hand-over variant (see k_encode_ops_wide_ho)
     const char* ho_frac = getenv("ISSCABAC_HANDOVER_EIGHTHS");       // measured at C3: 4/8 7.05, 5/8 7.03, 6/8 7.02 ms (plain kernel 7.19)
     P.ho_eighths = ho_frac && ho_frac[0] >= '1' && ho_frac[0] <= '7' ? (uint32_t)(ho_frac[0] - '0') : 6u;
+#if !CABAC_DEC_TMA
+    if (!ENC && decode_handover_geometry(P.n_streams, nw, grid, wsmem, lim)) {
+      const size_t hsmem = wsmem + HOD_BYTES;
+      P.prefetch_ops = 0u;
+      cudaError_t e = cudaFuncSetAttribute(k_decode_ops_wide_ho, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+      k_decode_ops_wide_ho<<<grid, (nw + 2u) * 32u, hsmem, st>>>(P);
+      e = cudaGetLastError();
+      return e == cudaSuccess ? ISSCABAC_OK : cuda_fail(e, "k_decode_ops_wide_ho");
+    }
+#endif
     if (ENC && handover_geometry(nw, grid, wsmem, lim)) {
       const size_t hsmem = wsmem + HO_BYTES;
       cudaError_t e = cudaFuncSetAttribute(k_encode_ops_wide_ho, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
@@ -1276,6 +1455,19 @@ const char* cabac_encode_ops_kernel(uint32_t n_streams, uint32_t n_ctx) {
   size_t wsmem;
   if (wide_geometry(n_streams, n_ctx, nw, grid, wsmem)) return handover_geometry(nw, grid, wsmem, lim) ? "k_encode_ops_wide_ho" : "k_encode_ops_wide";
   return "k_encode_ops";
+}
+
+const char* cabac_decode_ops_kernel(uint32_t n_streams, uint32_t n_ctx) {
+  const size_t lim = smem_limit();
+  if (!lim || n_streams == 0) return "";
+  const char* lat_env = getenv("ISSCABAC_LAT");
+  if (lat_env && lat_env[0] == '1' && n_ctx <= 125) return "k_decode_ops_lat";
+  uint32_t nw, grid;
+  size_t wsmem;
+  if (wide_geometry(n_streams, n_ctx, nw, grid, wsmem)) {
+    return decode_handover_geometry(n_streams, nw, grid, wsmem, lim) ? "k_decode_ops_wide_ho" : "k_decode_ops_wide";
+  }
+  return "k_decode_ops";
 }
 
 // <= 6 shift bits per context bin, 1 per bypass bin, 7 per terminate bin, <= 13 tail bits

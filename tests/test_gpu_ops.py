@@ -289,7 +289,7 @@ def test_worst_case_window_growth_on_device(I, enc_kernel):
         assert ok.all() and (bins_g == (ops & 1)).all(), state
 
 
-@pytest.mark.parametrize("warps,ragged,partial", [(6, False, False), (6, True, False), (10, False, True)])
+@pytest.mark.parametrize("warps,ragged,partial", [(6, False, False), (6, True, False), (10, False, True), (10, True, False), (14, False, False)])
 def test_encoder_handover_between_schedulers(I, monkeypatch, warps, ragged, partial):
     """k_encode_ops_wide_ho: with 4k + 2 tiles per SM the fourth warps of two schedulers hand their tile over, half-coded, to
     warps that slept on the other two (lane state through shared memory).  A job of exactly that geometry -- one CTA per SM,
@@ -327,3 +327,8 @@ def test_encoder_handover_between_schedulers(I, monkeypatch, warps, ragged, part
     s_ref, l_ref = O.encode_ops(sub_ops, sub_off, ci, out_stride=stride, n_threads=8)
     assert (lens_g[ids].astype(np.uint32) == l_ref).all()
     assert same_rows(enc.slab[torch.as_tensor(ids, device="cuda")].cpu().numpy(), s_ref, l_ref)
+    # ... and back: the hand-over decoder where it applies (more than 8 tiles per SM), bins and finish() flags of all streams
+    monkeypatch.setenv("ISSCABAC_HANDOVER", "1")
+    assert I.lib().cabac_decode_ops_kernel(n_streams, 23) == (b"k_decode_ops_wide_ho" if warps > 8 else b"k_decode_ops_wide")
+    bins, ok = I.decode_ops(I.compact(enc), d_ops, d_off, ci)
+    assert bool(ok.all().item()) and bool((bins == (d_ops & 1)).all().item())

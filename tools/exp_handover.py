@@ -67,9 +67,22 @@ def main():
     for k in fracs:
         same_len = same_len and bool((outs["0"].lengths == outs[k].lengths).all().item())
         same_bytes = same_bytes and bool(((outs["0"].slab[:, :w] == outs[k].slab[:, :w]) | ~live).all().item())
-    print(json.dumps({"streams": n, "ops_per_stream": L, "ragged": ragged, "ms": res, "gbins": {k: tot / (v * 1e-3) / 1e9 for k, v in res.items()},
+    # decode: the plain encoder's payload through the plain and the hand-over decoder, bins and finish flags of all streams
+    os.environ["ISSCABAC_HANDOVER"] = "0"
+    pay = I.compact(outs["0"])
+    dres, douts = {}, {}
+    for ho in ("0", "1"):
+        os.environ["ISSCABAC_HANDOVER"] = ho
+        os.environ["ISSCABAC_HANDOVER_EIGHTHS"] = fracs[-1]
+        bins_o, ok = I.decode_ops(pay, ops, off, ctx)
+        torch.cuda.synchronize()
+        douts[ho] = (bins_o, ok)
+        dres["decode plain" if ho == "0" else "decode handover at %s/8" % fracs[-1]] = timed(lambda: I.decode_ops(pay, ops, off, ctx))
+    dec_ok = bool(douts["1"][1].all().item()) and bool((douts["1"][0] == (ops & 1)).all().item()) and bool((douts["0"][0] == douts["1"][0]).all().item())
+    res.update(dres)
+    print(json.dumps({"streams": n, "ops_per_stream": L, "ragged": ragged, "decode_identical": dec_ok, "decode_kernel": I.lib().cabac_decode_ops_kernel(n, 23).decode(), "ms": res, "gbins": {k: tot / (v * 1e-3) / 1e9 for k, v in res.items()},
                       "identical_lengths": same_len, "identical_bytes": same_bytes}), flush=True)
-    assert same_len and same_bytes
+    assert same_len and same_bytes and dec_ok
 
 
 if __name__ == "__main__":
